@@ -1,0 +1,296 @@
+"""Generate the golden fixtures ``tests/golden/*.npz`` from the UNMODIFIED reference.
+
+Run in the build container (needs ``/root/reference``):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors, so parity is pinned by
+running the reference's own numpy path (``use_theano=False``; py2->py3 syntax patched in
+memory by ``refimport.py``) on small seeded inputs and storing inputs + outputs.  Every
+number stored under a key starting with ``ref_`` was produced by reference code:
+
+  * ``ref_score_rows``  per-gene ``score_row`` (fitnoise.py:44-50) at theta = ``theta``,
+                        NaN for genes the REML prep skips (fitnoise.py:28)
+  * ``ref_noise_p_values, ref_averages, ref_noise_combined_p_value, ref_df``
+                        Model.fit_noise(force_param=theta) (fitnoise.py:207-291)
+  * ``ref_coef, ref_coef_covar, ref_coef_df``  Model.fit_coef (fitnoise.py:294-347)
+  * ``ref_contrasts, ref_contrast_covar, ref_p_values, ref_q_values``  Model.test (:368-396)
+  * ``ref_weights``     Model.get_weights (:399-404)
+  * ``ref_description`` repr(fitted)  (:185-196)
+  * ``ref_opt_x, ref_opt_fun``  (some cases) the reference's own optimiser result,
+                        scipy L-BFGS-B with numeric gradient and default tolerances (:73-76)
+  * ``ref_initial, ref_bounds``  Model._configured output
+
+Inputs are stored under ``y, design, weights, counts, controls, control_design, theta,
+test_coef | test_contrasts`` and ``model`` (reference class name).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refimport  # noqa: E402
+
+warnings.simplefilter("ignore")
+
+
+def two_group(m):
+    h = m // 2
+    return np.array([[1.0, 0.0]] * h + [[1.0, 1.0]] * (m - h))
+
+
+def three_group(m):
+    g = np.arange(m) % 3
+    return np.stack([np.ones(m), (g == 1) * 1.0, (g == 2) * 1.0], axis=1)
+
+
+def t_noise(rng, n, m, df):
+    return rng.normal(size=(n, m)) * np.sqrt(df / rng.chisquare(df, size=(n, 1)))
+
+
+def run_case(ref, name, model, y, design, theta, context=None, test_coef=None,
+             test_contrasts=None, controls=None, control_design=None, noise_design=None,
+             optimise=False):
+    context = context or {}
+    cls = getattr(ref, model)
+    data = ref.Dataset(y, context)
+    n, m = y.shape
+    kwargs = dict(design=design, use_theano=False)
+    if noise_design is not None:
+        kwargs["noise_design"] = noise_design
+    if controls is not None:
+        kwargs["controls"] = list(controls)
+    if control_design is not None:
+        kwargs["control_design"] = control_design
+
+    fitted = cls().fit(data, force_param=theta, **kwargs)
+    out = dict(model=model, y=y, design=design, theta=np.asarray(theta, float))
+    for key, value in context.items():
+        out[key] = np.asarray(value, float)
+    if controls is not None:
+        out["controls"] = np.asarray(controls, bool)
+    if control_design is not None:
+        out["control_design"] = control_design
+    if noise_design is not None:
+        out["noise_design"] = noise_design
+
+    # per-gene score_row through the reference's own objects (fitnoise.py:23-50)
+    nd = design if noise_design is None else noise_design
+    cd = np.ones((m, 1)) if control_design is None else control_design
+    flags = [False] * n if controls is None else list(controls)
+    configured = cls()._with(data=data, noise_design=nd, control_design=cd,
+                             controls=np.asarray(flags, bool),
+                             _aux=np.zeros((n, 0)))._configured()
+    get_dist = lambda param, aux: configured._get_dist(configured._unpack(param), aux)
+    designs = [cd if f else nd for f in flags]
+    _, prepared = ref.fitnoise._fit_noise(
+        y=data.y, designs=designs, get_model_cost=lambda p: 0.0, get_dist=get_dist,
+        initial=ref.env.as_vector(configured._initial), aux=configured._aux,
+        bounds=configured._bounds, use_theano=False, verbose=False,
+        force_param=np.asarray(theta, float))
+    scores = np.repeat(np.nan, n)
+    th = ref.env.as_vector(theta)
+    for row, (retain, tQ2, z2) in prepared.items():
+        scores[row] = -(get_dist(th, configured._aux[row]).marginal(retain)
+                        .transformed(tQ2).log_density(z2))
+    out["ref_score_rows"] = scores
+    out["ref_initial"] = np.asarray(configured._initial, float)
+    out["ref_bounds"] = np.asarray(configured._bounds, float).reshape(-1, 2)
+
+    out["ref_noise_p_values"] = fitted.noise_p_values
+    out["ref_averages"] = fitted.averages
+    out["ref_noise_combined_p_value"] = np.float64(fitted.noise_combined_p_value)
+    out["ref_df"] = np.float64(fitted.df)
+    out["ref_coef"] = fitted.coef
+    c = design.shape[1]
+    cov = np.tile(np.nan, (n, c, c))
+    cdf = np.tile(np.nan, n)
+    for i, dist in enumerate(fitted.coef_dists):
+        if dist is not None:
+            cov[i] = dist.covar
+            if hasattr(dist, "df"):
+                cdf[i] = dist.df
+    out["ref_coef_covar"] = cov
+    out["ref_coef_df"] = cdf
+    out["ref_weights"] = fitted.get_weights()
+    out["ref_description"] = np.array(repr(fitted))
+
+    if test_coef is not None:
+        tested = fitted.test(coef=list(test_coef))
+        out["test_coef"] = np.asarray(test_coef, int)
+    else:
+        tested = fitted.test(contrasts=test_contrasts)
+        out["test_contrasts"] = np.asarray(test_contrasts, float)
+    out["ref_contrasts"] = tested.contrasts
+    kc = tested.contrasts.shape[1]
+    ccov = np.tile(np.nan, (n, kc, kc))
+    for i, dist in enumerate(tested.contrast_dists):
+        if dist is not None:
+            ccov[i] = dist.covar
+    out["ref_contrast_covar"] = ccov
+    out["ref_p_values"] = tested.p_values
+    out["ref_q_values"] = tested.q_values
+
+    if optimise:
+        opt = cls().fit(data, **kwargs)
+        out["ref_opt_x"] = np.asarray(opt.optimization_result.x, float)
+        out["ref_opt_fun"] = np.float64(opt.optimization_result.fun)
+        out["ref_opt_score"] = np.float64(opt.score)
+        out["ref_opt_deviance"] = np.float64(opt.deviance)
+        out["ref_opt_description"] = np.array(repr(opt))
+
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-34s n=%d m=%d finite scores=%d  p finite=%d  %.1f KB" % (
+        name, n, m, np.isfinite(scores).sum(), np.isfinite(tested.p_values).sum(),
+        os.path.getsize(path) / 1024.0))
+
+
+def punch_status_rows(y, m, c_groups):
+    """Rows of every status in SURVEY 8a's quirk table (two-group design, first half group 1)."""
+    h = m // 2
+    y[1, h:] = np.nan                 # k > c, a whole group missing: rank-deficient sub-design
+    y[2, :] = np.nan
+    y[2, 0] = 0.3; y[2, h] = -0.2     # k == c
+    y[3, 1:] = np.nan                 # k < c
+    y[4, :] = np.nan                  # all missing
+    y[5, 0] = np.nan                  # one missing
+    y[6, [0, h]] = np.nan             # one missing per group
+    y[7, :h] = np.nan                 # the other whole group missing
+    y[8, :] = np.nan
+    y[8, [0, 1, h]] = [1.0, 1.5, 0.2]  # k == c + 1
+    return y
+
+
+def main():
+    ref = refimport.load()
+    rng = np.random.default_rng(20151019)
+
+    # 1. Model_t, two groups, complete data; the reference optimiser too.
+    n, m = 120, 6
+    y = t_noise(rng, n, m, 10.0)
+    y[:12, 3:] += 5.0
+    run_case(ref, "t_twogroup", "Model_t", y, two_group(m), [7.3, 0.8], test_coef=[1], optimise=True)
+
+    # 2. Model_normal with precision weights (one zero weight, one NaN weight), 3 groups, F-test.
+    n, m = 90, 9
+    w = np.exp(rng.normal(0, 0.5, size=(n, m)))
+    y = rng.normal(size=(n, m)) / np.sqrt(w)
+    y[:9, 1::3] += 3.0
+    w[3, 4] = 0.0
+    w[5, 0] = 0.0; w[5, 8] = 0.0
+    w[7, 2] = np.nan
+    run_case(ref, "normal_weights", "Model_normal", y, three_group(m), [1.3],
+             context={"weights": w}, test_contrasts=np.array([[0, 0], [1, 0], [0, 1.0]]))
+
+    # 3. Model_independent with weights (voom style), contrast F-test: cfg2 in miniature.
+    n, m = 100, 12
+    w = np.exp(rng.normal(0, 0.5, size=(n, m)))
+    y = rng.normal(size=(n, m)) / np.sqrt(w)
+    y[:10, 2::3] -= 2.5
+    run_case(ref, "independent_weights", "Model_independent", y, three_group(m), [],
+             context={"weights": w}, test_contrasts=np.array([[0, 0], [1, 0], [-1, 1.0]]))
+
+    # 4. Model_independent with every row status of the quirk table.
+    n, m = 40, 6
+    y = punch_status_rows(rng.normal(size=(n, m)), m, 2)
+    run_case(ref, "independent_status", "Model_independent", y, two_group(m), [], test_coef=[1])
+
+    # 5. Model_t_patseq (= v2), 15 % missing, cfg3 in miniature; with the reference optimiser.
+    def patseq_data(n, m, frac=0.15):
+        counts = rng.poisson(np.exp(rng.normal(3, 1, size=(n, m)))).astype(float)
+        counts[rng.random(size=(n, m)) < frac] = 0.0
+        mu = rng.uniform(20, 100, size=(n, 1))
+        var = 28.0 ** 2 / np.maximum(counts, 1) + (0.05 * mu) ** 2
+        y = mu + rng.normal(size=(n, m)) * np.sqrt(var) * np.sqrt(12.6 / rng.chisquare(12.6, size=(n, 1)))
+        y[:, m // 2:] += np.where(np.arange(n)[:, None] < n // 20, 15.0, 0.0)
+        y[counts == 0] = np.nan
+        return y, counts
+    n, m = 150, 10
+    y, counts = patseq_data(n, m)
+    y[3, :] = np.nan; counts[3, :] = 0
+    y[4, 2:] = np.nan; counts[4, 2:] = 0
+    y[5, m // 2:] = np.nan; counts[5, m // 2:] = 0
+    run_case(ref, "t_patseq_v2", "Model_t_patseq", y, two_group(m), [12.6, 700.0, 0.003],
+             context={"counts": counts}, test_coef=[1], optimise=True)
+
+    # 6. The other PAT-Seq families at fixed theta.
+    n, m = 60, 8
+    y, counts = patseq_data(n, m)
+    run_case(ref, "t_patseq_v1", "Model_t_v1_patseq", y, two_group(m), [9.0, 600.0, 0.004],
+             context={"counts": counts}, test_coef=[1])
+    y, counts = patseq_data(n, m)
+    run_case(ref, "normal_patseq_v3", "Model_normal_patseq_v3", y, two_group(m), [0.2, 0.006],
+             context={"counts": counts}, test_coef=[1])
+    y, counts = patseq_data(n, m)
+    th = [11.0] + list(rng.uniform(400, 900, size=m)) + list(rng.uniform(0.002, 0.006, size=m))
+    run_case(ref, "t_patseq_v2_per_sample", "Model_t_patseq_per_sample", y, two_group(m), th,
+             context={"counts": counts}, test_coef=[1])
+    y, counts = patseq_data(n, m)
+    th = [8.0, 650.0] + list(rng.uniform(0.002, 0.006, size=m))
+    run_case(ref, "t_patseq_v1_per_sample", "Model_t_patseq_v1_per_sample", y, two_group(m), th,
+             context={"counts": counts}, test_coef=[1])
+    y, counts = patseq_data(n, m)
+    run_case(ref, "normal_patseq_v2", "Model_normal_patseq", y, two_group(m), [800.0, 0.002],
+             context={"counts": counts}, test_coef=[1])
+
+    # 7. Model_t_per_sample with control genes and a control design (cfg4 in miniature),
+    #    design != noise_design.
+    n, m = 80, 8
+    treat = (np.arange(m) >= m // 2) * 1.0
+    batch = (np.arange(m) % 2) * 1.0
+    covar = rng.normal(size=m)
+    design = np.stack([np.ones(m), treat, batch, covar], axis=1)
+    control_design = np.stack([np.ones(m), batch, covar], axis=1)
+    sds = rng.uniform(0.6, 1.6, size=m)
+    y = t_noise(rng, n, m, 6.0) * sds
+    y[:8] += 3.0 * treat
+    controls = np.arange(n) % 2 == 1
+    th = [6.0] + list(sds ** 2)
+    run_case(ref, "t_per_sample_controls", "Model_t_per_sample", y, design, th,
+             test_coef=[1], controls=controls, control_design=control_design)
+    # Model_t on the same data, with the optimiser, controls on.
+    run_case(ref, "t_controls_opt", "Model_t", y, design, [6.0, 1.1],
+             test_coef=[1], controls=controls, control_design=control_design, optimise=True)
+    # Model_normal_per_sample with weights; noise design differs from the coefficient design.
+    w = np.exp(rng.normal(0, 0.4, size=(n, m)))
+    run_case(ref, "normal_per_sample_weights", "Model_normal_per_sample", y / np.sqrt(w), design,
+             list(sds ** 2 * 1.1), context={"weights": w},
+             test_contrasts=np.array([[0.0], [1.0], [-1.0], [0.0]]),
+             noise_design=control_design)
+
+    # 8. Model_t at m=24, c=6: a wider design.
+    n, m = 50, 24
+    X = np.stack([np.ones(m), (np.arange(m) >= 12) * 1.0, (np.arange(m) % 4 == 1) * 1.0,
+                  (np.arange(m) % 4 == 2) * 1.0, (np.arange(m) % 4 == 3) * 1.0, rng.normal(size=m)], axis=1)
+    y = t_noise(rng, n, m, 4.0) * 1.4 + 7.0
+    y[:5] += 2.0 * X[:, 1]
+    w = np.ones((n, m))
+    w[9, 3] = 0.0; w[10, 20:] = 0.0; w[11, ::2] = 0.0
+    run_case(ref, "t_wide_design", "Model_t", y, X, [4.0, 2.0], context={"weights": w},
+             test_coef=[1, 5])
+
+    # 8b. The reference quirk: NaN in y with Model_t makes the initial variance NaN
+    #     (fitnoise.py:546), so `good` is all-False at the initial theta and the REML prep skips
+    #     every gene.  Stored to document the behaviour the product deliberately diverges from.
+    n, m = 12, 6
+    y = rng.normal(size=(n, m))
+    y[2, 1] = np.nan
+    run_case(ref, "t_nan_quirk", "Model_t", y, two_group(m), [5.0, 1.0], test_coef=[1])
+
+    # 9. fdr vectors (p_adjust.py:3-21).
+    p1 = rng.random(500); p1[::17] = np.nan; p1[5] = p1[6] = p1[7]; p1[20] = 0.0; p1[21] = 1.0
+    p2 = rng.random(37) ** 6
+    p3 = np.array([np.nan, np.nan])
+    p4 = np.array([0.5])
+    np.savez_compressed(os.path.join(HERE, "fdr.npz"),
+                        p1=p1, ref_q1=ref.fdr(p1), p2=p2, ref_q2=ref.fdr(p2),
+                        p3=p3, ref_q3=ref.fdr(p3), p4=p4, ref_q4=ref.fdr(p4))
+    print("fdr")
+
+
+if __name__ == "__main__":
+    main()

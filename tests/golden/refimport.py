@@ -1,0 +1,70 @@
+"""Import the UNMODIFIED reference (pfh/fitnoise, Python 2) under Python 3, in memory.
+
+Test infrastructure only.  Used by ``tests/golden/make_golden.py`` (run in the build
+container, where ``/root/reference`` is mounted) to generate the golden fixtures that
+pin the oracle.  Nothing here is imported by the product (``fitnoise_b200``), by
+``-m gpu`` tests, by ``smoke()`` or by ``bench.py``: ``/root/reference`` does not exist
+on the GPU box.
+
+The reference is Python-2 source.  Its numpy path (``use_theano=False``) runs under
+Python 3 after two purely syntactic rewrites applied to the source TEXT at import time:
+
+  * ``xrange`` -> ``range``
+  * ``print a, b`` statements -> ``print(a, b)``  (6 sites in fitnoise/fitnoise.py)
+
+No reference source is written to disk or copied into this repository; the four modules
+are read from ``/root/reference/fitnoise`` and exec'd into synthetic module objects.
+``fittransform`` (needs Theano) is not loaded.
+"""
+import os
+import re
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("FITNOISE_REFERENCE", "/root/reference")
+_PKG = "_fitnoise_reference"
+
+
+def _py3(text):
+    text = re.sub(r"\bxrange\b", "range", text)
+    out = []
+    for line in text.split("\n"):
+        mo = re.match(r"^(\s*)print (.*?)(,?)\s*$", line)
+        if mo:
+            indent, body, trailing = mo.groups()
+            end = ", end=' '" if trailing else ""
+            line = "%sprint(%s%s)" % (indent, body, end)
+        out.append(line)
+    return "\n".join(out)
+
+
+def available():
+    return os.path.exists(os.path.join(REFERENCE_ROOT, "fitnoise", "fitnoise.py"))
+
+
+def load():
+    """Return the reference package as a module object with the public names of
+    ``fitnoise/__init__.py`` (minus ``transform``)."""
+    if _PKG in sys.modules:
+        return sys.modules[_PKG]
+    if not available():
+        raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
+    pkg = types.ModuleType(_PKG)
+    pkg.__path__ = []
+    sys.modules[_PKG] = pkg
+    for name in ("env", "distributions", "p_adjust", "fitnoise"):
+        path = os.path.join(REFERENCE_ROOT, "fitnoise", name + ".py")
+        with open(path) as f:
+            source = _py3(f.read())
+        mod = types.ModuleType(_PKG + "." + name)
+        mod.__package__ = _PKG
+        mod.__file__ = path
+        sys.modules[mod.__name__] = mod
+        setattr(pkg, name, mod)
+        exec(compile(source, path, "exec"), mod.__dict__)
+    for key, value in pkg.fitnoise.__dict__.items():
+        if not key.startswith("_"):
+            setattr(pkg, key, value)
+    pkg.fdr = pkg.p_adjust.fdr
+    pkg.as_jsonic = pkg.env.as_jsonic
+    return pkg
