@@ -1,0 +1,266 @@
+"""ctypes binding of libfitnoise_b200.so (include/fitnoise_b200.h).
+
+This is the only way the package computes anything: there is no CPU fallback.  Importing the
+package works without a GPU (so that host-side logic can be tested), but creating an Engine
+raises unless the CUDA library loads and a CUDA device is present.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
+c_int32_p = ctypes.POINTER(ctypes.c_int32)
+
+KIND_SCALE1, KIND_SCALE_PS, KIND_PATSEQ = 0, 1, 2
+DIST_NORMAL, DIST_T, DIST_T_FIXED = 0, 1, 2
+
+EXPORTS = [
+    "fn_last_error", "fn_device_count", "fn_version", "fn_create", "fn_destroy", "fn_synchronize",
+    "fn_upload", "fn_upload_dev", "fn_nll_grad", "fn_nll_grad_dev", "fn_per_gene", "fn_noise_stats",
+    "fn_coef", "fn_test", "fn_bh", "fn_bh_dev", "fn_weights", "fn_set_tuning", "fn_launch_count",
+    "fn_set_timing", "fn_last_kernel_ms",
+]
+
+
+class Family(ctypes.Structure):
+    """fn_family (include/fitnoise_b200.h)."""
+    _fields_ = [("kind", ctypes.c_int32), ("na", ctypes.c_int32), ("nb", ctypes.c_int32),
+                ("tail_own", ctypes.c_int32), ("v3", ctypes.c_int32), ("dist", ctypes.c_int32),
+                ("fixed_df", ctypes.c_double)]
+
+    def theta_length(self):
+        return (1 if self.dist == DIST_T else 0) + self.na + self.nb
+
+
+class PrepInfo(ctypes.Structure):
+    _fields_ = [("row_variance_mean", ctypes.c_double), ("cst_sum", ctypes.c_double),
+                ("n_eligible", ctypes.c_int64), ("n_bad_counts", ctypes.c_int64),
+                ("n_variance_rows", ctypes.c_int64)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load_library():
+    """Load (building first if the sources are newer) the CUDA library.  Raises when it is missing
+    and cannot be built -- never substitutes another implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on the box
+            raise NativeError("libfitnoise_b200.so is not built and cannot be built here (%s). "
+                              "Run `python __graft_entry__.py` / fitnoise_b200.build.build(); "
+                              "there is no CPU fallback." % exc)
+    lib = ctypes.CDLL(path)
+    lib.fn_last_error.restype = ctypes.c_char_p
+    lib.fn_version.restype = ctypes.c_char_p
+    lib.fn_launch_count.restype = ctypes.c_int64
+    lib.fn_launch_count.argtypes = [ctypes.c_void_p]
+    lib.fn_last_kernel_ms.restype = ctypes.c_double
+    lib.fn_last_kernel_ms.argtypes = [ctypes.c_void_p]
+    lib.fn_create.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.fn_destroy.argtypes = [ctypes.c_void_p]
+    lib.fn_synchronize.argtypes = [ctypes.c_void_p]
+    upload_args = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                   ctypes.POINTER(Family), ctypes.c_void_p, ctypes.c_int32, c_double_p,
+                   ctypes.c_int32, c_double_p, ctypes.POINTER(PrepInfo)]
+    lib.fn_upload.argtypes = upload_args
+    lib.fn_upload_dev.argtypes = upload_args
+    lib.fn_nll_grad.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p,
+                                ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    lib.fn_nll_grad_dev.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_void_p]
+    lib.fn_per_gene.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_int32_p]
+    lib.fn_noise_stats.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p]
+    lib.fn_coef.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p,
+                            c_double_p, c_double_p, c_double_p]
+    lib.fn_test.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.fn_bh.argtypes = [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p]
+    lib.fn_bh_dev.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    lib.fn_weights.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p]
+    lib.fn_set_tuning.argtypes = [ctypes.c_void_p] + [ctypes.c_int32] * 4
+    lib.fn_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    _LIB = lib
+    return lib
+
+
+def device_count():
+    return int(load_library().fn_device_count())
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        assert a.shape == tuple(shape), "expected shape %s, got %s" % (tuple(shape), a.shape)
+    return a
+
+
+class Engine(object):
+    """One GPU's shard of the genes (an fn_handle)."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        rc = self._lib.fn_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise NativeError(self._lib.fn_last_error().decode())
+        self.device = int(device)
+        self.n = self.m = 0
+        self.family = None
+        self.info = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NativeError(self._lib.fn_last_error().decode())
+
+    # ---- data -----------------------------------------------------------------------------
+    def upload(self, y, aux, family, controls, design_noise, design_ctrl=None):
+        y = _f64(y)
+        n, m = y.shape
+        aux = None if aux is None else _f64(aux, (n, m))
+        controls = None if controls is None else np.ascontiguousarray(controls, dtype=np.uint8)
+        dn = _f64(design_noise)
+        assert dn.ndim == 2 and dn.shape[0] == m, "design must have one row per sample"
+        dc = None if design_ctrl is None else _f64(design_ctrl)
+        info = PrepInfo()
+        self._keep = (y, aux, controls)
+        self._check(self._lib.fn_upload(
+            self._h, n, m, y.ctypes.data, aux.ctypes.data if aux is not None else None,
+            ctypes.byref(family), controls.ctypes.data if controls is not None else None,
+            dn.shape[1], _dp(dn), dc.shape[1] if dc is not None else 0, _dp(dc), ctypes.byref(info)))
+        self._keep = None
+        self.n, self.m, self.family, self.info = n, m, family, info
+        return info
+
+    def upload_dev(self, n, m, y_ptr, aux_ptr, family, controls_ptr, design_noise, design_ctrl=None):
+        """Device-resident inputs (raw CUDA pointers, e.g. torch tensor .data_ptr())."""
+        dn = _f64(design_noise)
+        dc = None if design_ctrl is None else _f64(design_ctrl)
+        info = PrepInfo()
+        self._check(self._lib.fn_upload_dev(
+            self._h, n, m, y_ptr, aux_ptr or None, ctypes.byref(family), controls_ptr or None,
+            dn.shape[1], _dp(dn), dc.shape[1] if dc is not None else 0, _dp(dc), ctypes.byref(info)))
+        self.n, self.m, self.family, self.info = n, m, family, info
+        return info
+
+    # ---- likelihood -----------------------------------------------------------------------
+    def nll_grad(self, theta):
+        theta = _f64(theta).reshape(-1)
+        P = len(theta)
+        value = ctypes.c_double()
+        grad = np.zeros(max(P, 1))
+        used, bad = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.fn_nll_grad(self._h, _dp(theta), P, ctypes.byref(value), _dp(grad),
+                                          ctypes.byref(used), ctypes.byref(bad)))
+        return value.value, grad[:P], used.value, bad.value
+
+    def nll_grad_dev(self, theta, out_ptr):
+        theta = _f64(theta).reshape(-1)
+        self._check(self._lib.fn_nll_grad_dev(self._h, _dp(theta), len(theta), out_ptr))
+
+    def per_gene(self, theta):
+        theta = _f64(theta).reshape(-1)
+        score, d2, p = np.empty(self.n), np.empty(self.n), np.empty(self.n, dtype=np.int32)
+        self._check(self._lib.fn_per_gene(self._h, _dp(theta), len(theta), _dp(score), _dp(d2),
+                                          p.ctypes.data_as(c_int32_p)))
+        return score, d2, p
+
+    def noise_stats(self, theta):
+        theta = _f64(theta).reshape(-1)
+        noise_p, averages = np.empty(self.n), np.empty(self.n)
+        self._check(self._lib.fn_noise_stats(self._h, _dp(theta), len(theta), _dp(noise_p), _dp(averages)))
+        return noise_p, averages
+
+    # ---- coefficients and tests -----------------------------------------------------------
+    def coef(self, theta, design, want_covar=True):
+        theta = _f64(theta).reshape(-1)
+        design = _f64(design)
+        c = design.shape[1]
+        coef = np.empty((self.n, c))
+        covar = np.empty((self.n, c, c)) if want_covar else None
+        dfpost = np.empty(self.n)
+        self._check(self._lib.fn_coef(self._h, _dp(theta), len(theta), c, _dp(design), _dp(coef),
+                                      _dp(covar), _dp(dfpost)))
+        return coef, covar, dfpost
+
+    def test(self, contrasts, want_covar=False):
+        contrasts = _f64(contrasts)
+        kc = contrasts.shape[1]
+        contrasted = np.empty((self.n, kc))
+        ccov = np.empty((self.n, kc, kc)) if want_covar else None
+        p = np.empty(self.n)
+        self._check(self._lib.fn_test(self._h, kc, _dp(contrasts), _dp(contrasted), _dp(ccov), _dp(p)))
+        return contrasted, ccov, p
+
+    def bh(self, p):
+        p = _f64(p).reshape(-1)
+        q = np.empty(len(p))
+        self._check(self._lib.fn_bh(self._h, len(p), _dp(p), _dp(q)))
+        return q
+
+    def bh_dev(self, n, p_ptr, q_ptr):
+        self._check(self._lib.fn_bh_dev(self._h, n, p_ptr, q_ptr))
+
+    def weights(self, theta):
+        theta = _f64(theta).reshape(-1)
+        out = np.empty((self.n, self.m))
+        self._check(self._lib.fn_weights(self._h, _dp(theta), len(theta), _dp(out)))
+        return out
+
+    # ---- instrumentation ------------------------------------------------------------------
+    def synchronize(self):
+        self._check(self._lib.fn_synchronize(self._h))
+
+    def set_tuning(self, lpg=0, threads=0, stages=0, ctas_per_sm=0):
+        self._check(self._lib.fn_set_tuning(self._h, lpg, threads, stages, ctas_per_sm))
+
+    def set_timing(self, on=True):
+        self._check(self._lib.fn_set_timing(self._h, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        return float(self._lib.fn_last_kernel_ms(self._h))
+
+    def launch_count(self):
+        return int(self._lib.fn_launch_count(self._h))
+
+
+_DEFAULT = {}
+
+
+def default_engine(device=None):
+    """Process-wide engine for the given (or the rank's) device."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _DEFAULT:
+        _DEFAULT[device] = Engine(device)
+    return _DEFAULT[device]

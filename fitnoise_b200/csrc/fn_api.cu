@@ -1,0 +1,769 @@
+// C-ABI layer of libfitnoise_b200.so (declarations and reference citations: include/fitnoise_b200.h).
+// Owns device memory, picks the tile geometry, launches the kernels of fn_kernels.cuh / fn_bh.cuh.
+// There is no CPU path here: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fitnoise_b200.h"
+#include "fn_bh.cuh"
+#include "fn_host.hpp"
+#include "fn_kernels.cuh"
+
+using namespace fn;
+
+static thread_local std::string g_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define FN_ERR_CUDA -1
+#define FN_ERR_ARG -2
+#define FN_ERR_STATE -3
+#define FN_ERR_UNSUPPORTED -4
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(FN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+static_assert(sizeof(fn_family) == sizeof(Family), "fn_family and fn::Family must match");
+
+struct Geom {
+    int threads, lpg, genes, stages, grid;
+    size_t smem;
+    long long n_tiles;
+};
+
+struct fn_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    int64_t n = 0, n_pad = 0;
+    int m = 0;
+    bool has_aux = false, loaded = false;
+    Family fam{};
+    Design dn, dc;
+    int width = 0;
+    double cst_sum = 0.0;
+
+    double *y = nullptr, *aux = nullptr, *gs = nullptr, *cst = nullptr, *avg = nullptr;
+    uint8_t* status = nullptr;
+    double *xn = nullptr, *xc = nullptr;
+
+    double* partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int* ticket = nullptr;
+    double* out_dev = nullptr;
+    double* out_host = nullptr;        // pinned, mapped
+    double* out_host_devptr = nullptr;
+    size_t out_cap = 0;
+    double* tab_dev = nullptr;         // 2m
+    double* tab_host = nullptr;        // pinned 2m
+
+    double *pg_score = nullptr, *pg_d2 = nullptr, *noise_p = nullptr;
+    int* pg_p = nullptr;
+
+    int coef_c = 0;
+    bool coef_is_t = false;
+    double *coef = nullptr, *covar = nullptr, *dfpost = nullptr, *x_coef = nullptr, *rinv_dev = nullptr;
+    double* scratch_dev = nullptr;     // misc device scratch
+    size_t scratch_cap = 0;
+
+    int tune_lpg = 0, tune_threads = 0, tune_stages = 0, tune_ctas = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    std::map<const void*, size_t> smem_set;
+};
+
+template <class T>
+static void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static void release_data(fn_handle* h) {
+    dfree(h->y); dfree(h->aux); dfree(h->gs); dfree(h->cst); dfree(h->avg); dfree(h->status);
+    dfree(h->xn); dfree(h->xc); dfree(h->tab_dev);
+    dfree(h->pg_score); dfree(h->pg_d2); dfree(h->noise_p); dfree(h->pg_p);
+    dfree(h->coef); dfree(h->covar); dfree(h->dfpost); dfree(h->x_coef); dfree(h->rinv_dev);
+    if (h->tab_host) { cudaFreeHost(h->tab_host); h->tab_host = nullptr; }
+    h->loaded = false;
+    h->coef_c = 0;
+}
+
+extern "C" const char* fn_last_error(void) { return g_error.c_str(); }
+extern "C" const char* fn_version(void) { return "fitnoise_b200 0.1 (sm_100a)"; }
+
+extern "C" int fn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int fn_create(int device, void* stream, fn_handle** out) {
+    if (!out) return fail(FN_ERR_ARG, "fn_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(FN_ERR_CUDA, "fn_create: no CUDA device (%s); fitnoise_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(FN_ERR_ARG, "fn_create: device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    fn_handle* h = new fn_handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    CUDA_TRY(cudaMalloc(&h->ticket, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    const char* env;
+    if ((env = getenv("FN_LPG"))) h->tune_lpg = atoi(env);
+    if ((env = getenv("FN_THREADS"))) h->tune_threads = atoi(env);
+    if ((env = getenv("FN_STAGES"))) h->tune_stages = atoi(env);
+    if ((env = getenv("FN_CTAS"))) h->tune_ctas = atoi(env);
+    *out = h;
+    return 0;
+}
+
+extern "C" int fn_destroy(fn_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    release_data(h);
+    dfree(h->partials); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
+    if (h->out_host) cudaFreeHost(h->out_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int fn_synchronize(fn_handle* h) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int fn_set_tuning(fn_handle* h, int32_t lpg, int32_t threads, int32_t stages, int32_t ctas) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    if (lpg && (lpg & (lpg - 1))) return fail(FN_ERR_ARG, "lpg must be a power of two");
+    if (threads && (threads % 32 || threads > 256)) return fail(FN_ERR_ARG, "threads must be a multiple of 32, <= 256");
+    h->tune_lpg = lpg; h->tune_threads = threads; h->tune_stages = stages; h->tune_ctas = ctas;
+    return 0;
+}
+extern "C" int64_t fn_launch_count(fn_handle* h) { return h ? h->launches : 0; }
+extern "C" int fn_set_timing(fn_handle* h, int32_t on) { if (!h) return FN_ERR_ARG; h->timing = on != 0; return 0; }
+extern "C" double fn_last_kernel_ms(fn_handle* h) { return h ? h->last_ms : 0.0; }
+
+// ------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------
+static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_bytes, Geom& g) {
+    const int m = h->m;
+    int ctas = h->tune_ctas > 0 ? h->tune_ctas : 2;
+    int threads = h->tune_threads > 0 ? h->tune_threads : 256;
+    // small problems: more, smaller CTAs so that every SM gets work
+    if (h->tune_threads == 0 && h->n < (int64_t)h->sm_count * 256) threads = 128;
+    const size_t budget = (h->smem_optin - 2048) / ctas;       // per CTA
+    const size_t stage_target = 50 * 1024;
+    int lpg = h->tune_lpg > 0 ? h->tune_lpg : 1;
+    if (h->tune_lpg == 0) {
+        while (lpg < 32 && threads / (lpg * 2) >= 16 &&
+               tile_stage_bytes(threads / lpg, m, aux, gs, cst) > stage_target) lpg *= 2;
+    }
+    if (lpg > 32 || threads % lpg || (threads / lpg) % 16)
+        return fail(FN_ERR_ARG, "invalid geometry: threads %d lpg %d (genes per tile must be a multiple of 16)", threads, lpg);
+    const int genes = threads / lpg;
+    const size_t stage = tile_stage_bytes(genes, m, aux, gs, cst);
+    const size_t fixed = table_bytes + 256;
+    if (fixed + stage > h->smem_optin - 1024)
+        return fail(FN_ERR_UNSUPPORTED, "m = %d is too large for one tile stage in shared memory (%zu bytes)", m, fixed + stage);
+    int stages = h->tune_stages > 0 ? h->tune_stages : 3;
+    if (stages > FN_MAX_STAGES) stages = FN_MAX_STAGES;
+    while (stages > 1 && fixed + (size_t)stages * stage > budget) --stages;
+    if (fixed + (size_t)stages * stage > budget) ctas = 1;      // a single CTA per SM then
+    g.threads = threads; g.lpg = lpg; g.genes = genes; g.stages = stages;
+    g.smem = fixed + (size_t)stages * stage;
+    g.n_tiles = (h->n + genes - 1) / genes;
+    long long grid = (long long)h->sm_count * ctas;
+    if (grid > g.n_tiles) grid = g.n_tiles;
+    if (grid < 1) grid = 1;
+    g.grid = (int)grid;
+    return 0;
+}
+
+static GeomParams geom_params(const fn_handle* h, const Geom& g) {
+    GeomParams gp;
+    gp.n = h->n; gp.n_tiles = g.n_tiles; gp.m = h->m; gp.genes = g.genes; gp.lpg = g.lpg;
+    gp.stages = g.stages; gp.width = h->width;
+    return gp;
+}
+
+template <class K>
+static int set_smem(fn_handle* h, K kernel, size_t bytes) {
+    const void* key = (const void*)kernel;
+    auto it = h->smem_set.find(key);
+    if (it != h->smem_set.end() && it->second >= bytes) return 0;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    h->smem_set[key] = bytes;
+    return 0;
+}
+
+static int ensure_reduce(fn_handle* h, int grid, int nacc) {
+    const size_t need = (size_t)grid * nacc;
+    if (need > h->partials_cap) {
+        dfree(h->partials);
+        CUDA_TRY(cudaMalloc(&h->partials, need * sizeof(double)));
+        h->partials_cap = need;
+    }
+    if ((size_t)nacc > h->out_cap) {
+        dfree(h->out_dev);
+        if (h->out_host) { cudaFreeHost(h->out_host); h->out_host = nullptr; }
+        const size_t cap = (size_t)nacc + 64;
+        CUDA_TRY(cudaMalloc(&h->out_dev, cap * sizeof(double)));
+        CUDA_TRY(cudaHostAlloc(&h->out_host, cap * sizeof(double), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(&h->out_host_devptr, h->out_host, 0));
+        h->out_cap = cap;
+    }
+    return 0;
+}
+
+static int ensure_scratch(fn_handle* h, size_t bytes) {
+    if (bytes > h->scratch_cap) {
+        dfree(h->scratch_dev);
+        CUDA_TRY(cudaMalloc(&h->scratch_dev, bytes));
+        h->scratch_cap = bytes;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// upload + prepare
+// ------------------------------------------------------------------------------------------
+__global__ void controls_to_status_kernel(long long n, long long n_pad, const uint8_t* controls, uint8_t* status) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    status[i] = (i < n && controls && controls[i]) ? 2 : 0;
+}
+
+static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, const double* aux,
+                         const fn_family* family, const uint8_t* controls, int32_t c_noise,
+                         const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
+                         fn_prep_info* info, cudaMemcpyKind kind) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    if (!y || !family || !design_noise) return fail(FN_ERR_ARG, "fn_upload: y, family and design_noise are required");
+    if (n < 1 || m < 1) return fail(FN_ERR_ARG, "fn_upload: empty data (n=%lld, m=%d)", (long long)n, m);
+    if (n >= (1LL << 31)) return fail(FN_ERR_UNSUPPORTED, "fn_upload: more than 2^31 genes per handle; shard across handles");
+    Family fam;
+    memcpy(&fam, family, sizeof fam);
+    if (!family_valid(fam, m, aux != nullptr))
+        return fail(FN_ERR_ARG, "fn_upload: inconsistent family (kind %d, na %d, nb %d, m %d, aux %s)", fam.kind, fam.na,
+                    fam.nb, m, aux ? "given" : "missing");
+    if ((fam.na == m && fam.kind != KIND_SCALE1) || fam.nb == m)
+        if (m > 256) return fail(FN_ERR_UNSUPPORTED, "per-sample variance models support m <= 256 (m = %d)", m);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Design dn, dc;
+    if (c_noise < 1 || c_noise > FN_MAXC) return fail(FN_ERR_UNSUPPORTED, "design has %d columns; 1..%d supported", c_noise, FN_MAXC);
+    if (!dn.build(m, c_noise, design_noise)) return fail(FN_ERR_ARG, "noise design (%d x %d) is rank deficient", m, c_noise);
+    const double one = 1.0;
+    std::vector<double> ones((size_t)m, one);
+    if (!design_ctrl) { design_ctrl = ones.data(); c_ctrl = 1; }      // fitnoise.py:216
+    if (c_ctrl < 1 || c_ctrl > FN_MAXC) return fail(FN_ERR_UNSUPPORTED, "control design has %d columns; 1..%d supported", c_ctrl, FN_MAXC);
+    if (!dc.build(m, c_ctrl, design_ctrl)) return fail(FN_ERR_ARG, "control design (%d x %d) is rank deficient", m, c_ctrl);
+    const int width = dn.width > dc.width ? dn.width : dc.width;
+    auto repad = [&](Design& d) {
+        std::vector<double> q((size_t)m * width, 0.0);
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < d.c; ++i) q[(size_t)j * width + i] = d.q[(size_t)j * d.width + i];
+        d.q.swap(q);
+        d.width = width;
+    };
+    repad(dn); repad(dc);
+
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    release_data(h);
+    h->n = n; h->m = m; h->fam = fam; h->has_aux = aux != nullptr; h->dn = dn; h->dc = dc; h->width = width;
+    h->n_pad = (n + FN_ROW_PAD - 1) / FN_ROW_PAD * FN_ROW_PAD;
+    const size_t rows = (size_t)h->n_pad * m * sizeof(double);
+    const size_t used = (size_t)n * m * sizeof(double);
+    CUDA_TRY(cudaMalloc(&h->y, rows));
+    CUDA_TRY(cudaMemsetAsync((char*)h->y + used, 0xFF, rows - used, h->stream));       // NaN padding rows
+    CUDA_TRY(cudaMemcpyAsync(h->y, y, used, kind, h->stream));
+    if (aux) {
+        CUDA_TRY(cudaMalloc(&h->aux, rows));
+        CUDA_TRY(cudaMemsetAsync((char*)h->aux + used, 0xFF, rows - used, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->aux, aux, used, kind, h->stream));
+    }
+    CUDA_TRY(cudaMalloc(&h->status, h->n_pad));
+    CUDA_TRY(cudaMalloc(&h->cst, h->n_pad * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->avg, h->n_pad * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(h->cst, 0, h->n_pad * sizeof(double), h->stream));
+    const bool patseq = fam.kind == KIND_PATSEQ;
+    const bool want_gs = patseq && (!fam.tail_own || fam.v3);
+    if (want_gs) {
+        CUDA_TRY(cudaMalloc(&h->gs, h->n_pad * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(h->gs, 0, h->n_pad * sizeof(double), h->stream));
+    }
+    {
+        uint8_t* ctl_dev = nullptr;
+        if (controls) {
+            if (kind == cudaMemcpyHostToDevice) {
+                const int rcs = ensure_scratch(h, (size_t)n);
+                if (rcs) return rcs;
+                ctl_dev = (uint8_t*)h->scratch_dev;
+                CUDA_TRY(cudaMemcpyAsync(ctl_dev, controls, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+            } else {
+                ctl_dev = const_cast<uint8_t*>(controls);
+            }
+        }
+        const int tb = 256;
+        controls_to_status_kernel<<<(unsigned)((h->n_pad + tb - 1) / tb), tb, 0, h->stream>>>(n, h->n_pad, ctl_dev, h->status);
+        ++h->launches;
+    }
+    CUDA_TRY(cudaMalloc(&h->xn, (size_t)m * width * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->xc, (size_t)m * width * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(h->xn, dn.q.data(), (size_t)m * width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->xc, dc.q.data(), (size_t)m * width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMalloc(&h->tab_dev, 2 * (size_t)m * sizeof(double)));
+    CUDA_TRY(cudaHostAlloc(&h->tab_host, 2 * (size_t)m * sizeof(double), cudaHostAllocDefault));
+
+    // K1
+    Geom g;
+    const size_t table_bytes = 2 * (size_t)m * width * sizeof(double);
+    int rc = choose_geom(h, h->has_aux, false, false, table_bytes, g);
+    if (rc) return rc;
+    rc = ensure_reduce(h, g.grid, PREP_NACC);
+    if (rc) return rc;
+    PrepParams pp;
+    pp.g = geom_params(h, g);
+    pp.src.y = h->y; pp.src.aux = h->aux; pp.src.gs = nullptr; pp.src.cst = nullptr; pp.src.status = h->status;
+    pp.src.m = m; pp.src.genes = g.genes;
+    pp.fam = fam;
+    pp.xn = h->xn; pp.xc = h->xc; pp.c_noise = c_noise; pp.c_ctrl = c_ctrl;
+    pp.status_out = h->status; pp.cst_out = h->cst; pp.avg_out = h->avg; pp.gs_out = h->gs;
+    pp.gr.partials = h->partials; pp.gr.ticket = h->ticket; pp.gr.out_dev = h->out_dev;
+    pp.gr.out_host = h->out_host_devptr; pp.gr.nacc = PREP_NACC;
+    FN_DISPATCH_WIDTH(width, {
+        rc = set_smem(h, prepare_kernel<C>, g.smem);
+        if (rc) return rc;
+        prepare_kernel<C><<<g.grid, g.threads, g.smem, h->stream>>>(pp);
+    });
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (patseq) {
+        counts_to_rc_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->aux, (long long)n * m);
+        ++h->launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->cst_sum = h->out_host[PREP_CSTSUM];
+    if (info) {
+        const double cnt = h->out_host[PREP_VARCNT];
+        info->row_variance_mean = cnt > 0 ? h->out_host[PREP_VARSUM] / cnt : NAN;
+        info->cst_sum = h->cst_sum;
+        info->n_eligible = (int64_t)h->out_host[PREP_ELIG];
+        info->n_bad_counts = (int64_t)h->out_host[PREP_BAD];
+        info->n_variance_rows = (int64_t)cnt;
+    }
+    h->loaded = true;
+    return 0;
+}
+
+extern "C" int fn_upload(fn_handle* h, int64_t n, int32_t m, const double* y, const double* aux,
+                         const fn_family* family, const uint8_t* controls, int32_t c_noise,
+                         const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
+                         fn_prep_info* info) {
+    return upload_common(h, n, m, y, aux, family, controls, c_noise, design_noise, c_ctrl, design_ctrl, info,
+                         cudaMemcpyHostToDevice);
+}
+
+extern "C" int fn_upload_dev(fn_handle* h, int64_t n, int32_t m, const double* y, const double* aux,
+                             const fn_family* family, const uint8_t* controls, int32_t c_noise,
+                             const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
+                             fn_prep_info* info) {
+    return upload_common(h, n, m, y, aux, family, controls, c_noise, design_noise, c_ctrl, design_ctrl, info,
+                         cudaMemcpyDeviceToDevice);
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------
+struct ThetaState {
+    double v = 0, theta0 = 1;
+    int is_t = 0;
+    std::vector<double> ta, tb;
+};
+
+static int stage_theta(fn_handle* h, const double* theta, int32_t P, ThetaState& ts) {
+    if (!h || !h->loaded) return fail(FN_ERR_STATE, "no data uploaded");
+    if (P != theta_length(h->fam)) return fail(FN_ERR_ARG, "theta has %d entries, the family needs %d", P, theta_length(h->fam));
+    if (P > 0 && !theta) return fail(FN_ERR_ARG, "theta is NULL");
+    if (!unpack_theta(h->fam, h->m, theta, ts.v, ts.is_t, ts.theta0, ts.ta, ts.tb))
+        return fail(FN_ERR_ARG, "theta must be finite and positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->fam.kind != KIND_SCALE1) {
+        // the previous evaluation was synchronised (or is ordered on the same stream before the copy)
+        memcpy(h->tab_host, ts.ta.data(), h->m * sizeof(double));
+        memcpy(h->tab_host + h->m, ts.tb.data(), h->m * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(h->tab_dev, h->tab_host, 2 * (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    return 0;
+}
+
+static int eval_nacc(const fn_handle* h) {
+    const bool ia = h->fam.na == h->m && h->fam.kind != KIND_SCALE1, ib = h->fam.nb == h->m;
+    return ACC_FIXED + ((ia || ib) ? 2 * h->m : 0);
+}
+
+static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene) {
+    const int m = h->m;
+    const bool ia = h->fam.na == m && h->fam.kind != KIND_SCALE1, ib = h->fam.nb == m;
+    const bool inplace = ia || ib;
+    Geom g;
+    int threads_for_cols = 0;
+    (void)threads_for_cols;
+    const size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
+    int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g);
+    if (rc) return rc;
+    if (inplace && m > g.threads) return fail(FN_ERR_UNSUPPORTED, "per-sample variance models need m <= threads per CTA (%d)", g.threads);
+    const int nacc = eval_nacc(h);
+    rc = ensure_reduce(h, g.grid, nacc);
+    if (rc) return rc;
+    if (per_gene && !h->pg_score) {
+        CUDA_TRY(cudaMalloc(&h->pg_score, h->n * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->pg_d2, h->n * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->pg_p, h->n * sizeof(int)));
+    }
+    EvalParams ep;
+    ep.g = geom_params(h, g);
+    ep.src.y = h->y; ep.src.aux = h->aux; ep.src.gs = h->gs; ep.src.cst = per_gene ? h->cst : nullptr;
+    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes;
+    ep.xn = h->xn; ep.xc = h->xc; ep.c_noise = h->dn.c; ep.c_ctrl = h->dc.c;
+    ep.kind = h->fam.kind; ep.tail_own = h->fam.tail_own; ep.v3 = h->fam.v3; ep.is_t = ts.is_t;
+    ep.v = ts.v; ep.theta0 = ts.theta0;
+    ep.ta = h->fam.kind != KIND_SCALE1 ? h->tab_dev : nullptr;
+    ep.tb = h->fam.kind != KIND_SCALE1 ? h->tab_dev + m : nullptr;
+    ep.inplace_a = ia; ep.inplace_b = ib;
+    ep.pg_score = per_gene ? h->pg_score : nullptr;
+    ep.pg_d2 = per_gene ? h->pg_d2 : nullptr;
+    ep.pg_p = per_gene ? h->pg_p : nullptr;
+    ep.gr.partials = h->partials; ep.gr.ticket = h->ticket; ep.gr.out_dev = h->out_dev;
+    ep.gr.out_host = h->out_host_devptr; ep.gr.nacc = nacc;
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    FN_DISPATCH_WIDTH(h->width, {
+        if (h->fam.kind == KIND_SCALE1) {
+            rc = set_smem(h, eval_kernel<C, KIND_SCALE1>, g.smem);
+            if (rc) return rc;
+            eval_kernel<C, KIND_SCALE1><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
+        } else if (h->fam.kind == KIND_SCALE_PS) {
+            rc = set_smem(h, eval_kernel<C, KIND_SCALE_PS>, g.smem);
+            if (rc) return rc;
+            eval_kernel<C, KIND_SCALE_PS><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
+        } else {
+            rc = set_smem(h, eval_kernel<C, KIND_PATSEQ>, g.smem);
+            if (rc) return rc;
+            eval_kernel<C, KIND_PATSEQ><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
+        }
+    });
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// raw accumulators -> [value, grad[P], n_used, n_bad]
+static void assemble(const fn_handle* h, const double* acc, double* out) {
+    const Family& f = h->fam;
+    const int m = h->m;
+    int at = 0;
+    out[at++] = acc[ACC_VALUE] + 0.5 * h->cst_sum * (acc[ACC_USED] > 0 ? 1.0 : 0.0);
+    if (f.dist == DIST_T) out[at++] = acc[ACC_DV];
+    if (f.na == 1) out[at++] = acc[ACC_GA];
+    else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + j];
+    if (f.nb == 1) out[at++] = acc[ACC_GB];
+    else if (f.nb == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + m + j];
+    out[at++] = acc[ACC_USED];
+    out[at++] = acc[ACC_BAD];
+}
+
+extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double* value, double* grad,
+                           int64_t* n_used, int64_t* n_bad) {
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    rc = launch_eval(h, ts, false);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->timing) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->last_ms = ms;
+    }
+    std::vector<double> out(P + 3);
+    assemble(h, h->out_host, out.data());
+    if (value) *value = out[0];
+    if (grad) for (int i = 0; i < P; ++i) grad[i] = out[1 + i];
+    if (n_used) *n_used = (int64_t)out[P + 1];
+    if (n_bad) *n_bad = (int64_t)out[P + 2];
+    return 0;
+}
+
+// device-side assemble for the asynchronous (multi-GPU) form
+__global__ void assemble_kernel(const double* acc, double* out, Family f, int m, double cst_sum) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int at = 0;
+    out[at++] = acc[ACC_VALUE] + 0.5 * cst_sum * (acc[ACC_USED] > 0 ? 1.0 : 0.0);
+    if (f.dist == DIST_T) out[at++] = acc[ACC_DV];
+    if (f.na == 1) out[at++] = acc[ACC_GA];
+    else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + j];
+    if (f.nb == 1) out[at++] = acc[ACC_GB];
+    else if (f.nb == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + m + j];
+    out[at++] = acc[ACC_USED];
+    out[at++] = acc[ACC_BAD];
+}
+
+extern "C" int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, double* out_dev) {
+    if (!out_dev) return fail(FN_ERR_ARG, "out_dev is NULL");
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    rc = launch_eval(h, ts, false);
+    if (rc) return rc;
+    assemble_kernel<<<1, 32, 0, h->stream>>>(h->out_dev, out_dev, h->fam, h->m, h->cst_sum);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double* score, double* d2, int32_t* p) {
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    rc = launch_eval(h, ts, true);
+    if (rc) return rc;
+    if (score) CUDA_TRY(cudaMemcpyAsync(score, h->pg_score, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (d2) CUDA_TRY(cudaMemcpyAsync(d2, h->pg_d2, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (p) CUDA_TRY(cudaMemcpyAsync(p, h->pg_p, h->n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, double* noise_p, double* averages) {
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    rc = launch_eval(h, ts, true);
+    if (rc) return rc;
+    if (!h->noise_p) CUDA_TRY(cudaMalloc(&h->noise_p, h->n * sizeof(double)));
+    const int tb = 128;
+    noise_p_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(h->n, h->pg_d2, h->pg_p, ts.is_t, ts.v, h->noise_p);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (noise_p) CUDA_TRY(cudaMemcpyAsync(noise_p, h->noise_p, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (averages) CUDA_TRY(cudaMemcpyAsync(averages, h->avg, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// coefficients, tests, weights
+// ------------------------------------------------------------------------------------------
+extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, const double* design,
+                       double* coef, double* covar, double* dfpost) {
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    if (!design || c < 1 || c > FN_MAXC) return fail(FN_ERR_UNSUPPORTED, "design has %d columns; 1..%d supported", c, FN_MAXC);
+    const int m = h->m;
+    Design d;
+    if (!d.build(m, c, design)) return fail(FN_ERR_ARG, "coefficient design (%d x %d) is rank deficient", m, c);
+    dfree(h->coef); dfree(h->covar); dfree(h->dfpost); dfree(h->x_coef); dfree(h->rinv_dev);
+    CUDA_TRY(cudaMalloc(&h->coef, (size_t)h->n * c * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->covar, (size_t)h->n * c * c * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->dfpost, (size_t)h->n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->x_coef, (size_t)m * d.width * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->rinv_dev, (size_t)c * c * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(h->x_coef, d.q.data(), (size_t)m * d.width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->rinv_dev, d.rinv.data(), (size_t)c * c * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->coef_c = c;
+    h->coef_is_t = ts.is_t != 0;
+
+    Geom g;
+    const size_t table_bytes = ((size_t)m * d.width + 2 * m) * sizeof(double);
+    rc = choose_geom(h, h->has_aux, h->gs != nullptr, false, table_bytes, g);
+    if (rc) return rc;
+    CoefParams cp;
+    cp.g = geom_params(h, g);
+    cp.g.width = d.width;
+    cp.src.y = h->y; cp.src.aux = h->aux; cp.src.gs = h->gs; cp.src.cst = nullptr; cp.src.status = h->status;
+    cp.src.m = m; cp.src.genes = g.genes;
+    cp.x = h->x_coef; cp.rinv = h->rinv_dev; cp.c = c;
+    cp.kind = h->fam.kind; cp.tail_own = h->fam.tail_own; cp.v3 = h->fam.v3; cp.is_t = ts.is_t;
+    cp.v = ts.v; cp.theta0 = ts.theta0;
+    cp.ta = h->fam.kind != KIND_SCALE1 ? h->tab_dev : nullptr;
+    cp.tb = h->fam.kind != KIND_SCALE1 ? h->tab_dev + m : nullptr;
+    cp.coef = h->coef; cp.covar = h->covar; cp.dfpost = h->dfpost;
+    FN_DISPATCH_WIDTH(d.width, {
+        rc = set_smem(h, coef_kernel<C>, g.smem);
+        if (rc) return rc;
+        coef_kernel<C><<<g.grid, g.threads, g.smem, h->stream>>>(cp);
+    });
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (coef) CUDA_TRY(cudaMemcpyAsync(coef, h->coef, (size_t)h->n * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (covar) CUDA_TRY(cudaMemcpyAsync(covar, h->covar, (size_t)h->n * c * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (dfpost) CUDA_TRY(cudaMemcpyAsync(dfpost, h->dfpost, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov, double* pval) {
+    if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_test needs a preceding fn_coef");
+    const int c = h->coef_c;
+    if (kc < 1 || kc > FN_MAXC || !contrasts) return fail(FN_ERR_UNSUPPORTED, "contrasts has %d columns; 1..%d supported", kc, FN_MAXC);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t nb_con = (size_t)c * kc * sizeof(double);
+    const size_t nb_out = (size_t)h->n * kc * sizeof(double);
+    const size_t nb_cc = ccov ? (size_t)h->n * kc * kc * sizeof(double) : 0;
+    const size_t nb_p = (size_t)h->n * sizeof(double);
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    int rc = ensure_scratch(h, up(nb_con) + up(nb_out) + up(nb_cc) + up(nb_p));
+    if (rc) return rc;
+    char* base = (char*)h->scratch_dev;
+    double* d_con = (double*)base; base += up(nb_con);
+    double* d_out = (double*)base; base += up(nb_out);
+    double* d_cc = ccov ? (double*)base : nullptr; base += up(nb_cc);
+    double* d_p = (double*)base;
+    CUDA_TRY(cudaMemcpyAsync(d_con, contrasts, nb_con, cudaMemcpyHostToDevice, h->stream));
+    TestParams tp;
+    tp.n = h->n; tp.c = c; tp.kc = kc; tp.is_t = h->coef_is_t;
+    tp.coef = h->coef; tp.covar = h->covar; tp.dfpost = h->dfpost; tp.contrasts = d_con;
+    tp.contrasted = d_out; tp.ccov = d_cc; tp.pval = d_p;
+    const int tb = 128;
+    test_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(tp);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (contrasted) CUDA_TRY(cudaMemcpyAsync(contrasted, d_out, nb_out, cudaMemcpyDeviceToHost, h->stream));
+    if (ccov) CUDA_TRY(cudaMemcpyAsync(ccov, d_cc, nb_cc, cudaMemcpyDeviceToHost, h->stream));
+    if (pval) CUDA_TRY(cudaMemcpyAsync(pval, d_p, nb_p, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* weights) {
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    if (!weights) return fail(FN_ERR_ARG, "weights is NULL");
+    const size_t bytes = (size_t)h->n * h->m * sizeof(double);
+    rc = ensure_scratch(h, bytes);
+    if (rc) return rc;
+    WeightParams wp;
+    wp.n = h->n; wp.m = h->m; wp.y = h->y; wp.aux = h->aux; wp.gs = h->gs;
+    wp.kind = h->fam.kind; wp.tail_own = h->fam.tail_own; wp.v3 = h->fam.v3; wp.theta0 = ts.theta0;
+    wp.ta = h->tab_dev; wp.tb = h->tab_dev + h->m;
+    wp.out = (double*)h->scratch_dev;
+    weights_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(wp);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(weights, wp.out, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Benjamini-Hochberg
+// ------------------------------------------------------------------------------------------
+static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work) {
+    const int nblocks = (int)((n + BH_CHUNK - 1) / BH_CHUNK);
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    uint64_t* keys0 = (uint64_t*)work; work += up(n * 8);
+    uint64_t* keys1 = (uint64_t*)work; work += up(n * 8);
+    uint32_t* idx0 = (uint32_t*)work; work += up(n * 4);
+    uint32_t* idx1 = (uint32_t*)work; work += up(n * 4);
+    uint32_t* hist = (uint32_t*)work; work += up((size_t)256 * nblocks * 4);
+    double* chunk_min = (double*)work; work += up((size_t)nblocks * 8);
+    double* carry = (double*)work;
+    bh_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, p_dev, keys0, idx0);
+    ++h->launches;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 8 * pass;
+        bh_hist_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, shift, hist, nblocks);
+        bh_scan_kernel<<<1, 1024, 0, h->stream>>>(hist, (long long)256 * nblocks);
+        bh_scatter_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, keys1, idx1, shift, hist, nblocks);
+        h->launches += 3;
+        std::swap(keys0, keys1);
+        std::swap(idx0, idx1);
+    }
+    bh_chunkmin_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, chunk_min);
+    bh_carry_kernel<<<1, 32, 0, h->stream>>>(nblocks, chunk_min, carry);
+    bh_finish_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, carry, q_dev);
+    h->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static size_t bh_work_bytes(int64_t n) {
+    const size_t nblocks = (n + BH_CHUNK - 1) / BH_CHUNK;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    return 2 * up(n * 8) + 2 * up(n * 4) + up(256 * nblocks * 4) + 2 * up(nblocks * 8);
+}
+
+extern "C" int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    if (n < 0 || n >= (1LL << 32)) return fail(FN_ERR_UNSUPPORTED, "fn_bh: n out of range");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_scratch(h, bh_work_bytes(n));
+    if (rc) return rc;
+    return bh_run(h, n, p_dev, q_dev, (char*)h->scratch_dev);
+}
+
+extern "C" int fn_bh(fn_handle* h, int64_t n, const double* p, double* q) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    if (n < 0 || n >= (1LL << 32)) return fail(FN_ERR_UNSUPPORTED, "fn_bh: n out of range");
+    if (n == 0) return 0;
+    if (!p || !q) return fail(FN_ERR_ARG, "fn_bh: NULL array");
+    CUDA_TRY(cudaSetDevice(h->device));
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    int rc = ensure_scratch(h, 2 * up(n * 8) + bh_work_bytes(n));
+    if (rc) return rc;
+    char* base = (char*)h->scratch_dev;
+    double* p_dev = (double*)base; base += up(n * 8);
+    double* q_dev = (double*)base; base += up(n * 8);
+    CUDA_TRY(cudaMemcpyAsync(p_dev, p, n * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = bh_run(h, n, p_dev, q_dev, base);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(q, q_dev, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}

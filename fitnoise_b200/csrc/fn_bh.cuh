@@ -1,0 +1,162 @@
+// K4: Benjamini-Hochberg q-values on the device (replaces p_adjust.py:3-21, two numpy argsorts).
+//
+//   key_i  = bit pattern of p_i (NaN -> 1.0); non-negative doubles order like their bit patterns
+//   sort   = stable LSD radix sort of (key, index), 8 passes of 8 bits: per-CTA digit histograms,
+//            one scan, stable scatter (warp match + per-warp digit offsets)
+//   v_r    = (p_(r) * n) / (r + 1)  with the reference's operation order (p_adjust.py:14-16),
+//            un-fused multiply and divide, so q is BIT-EXACT given p
+//   q_(r)  = min(1, min_{s >= r} v_s): suffix-min scan (min is exact, any association order)
+//   q[index_(r)] = q_(r)
+// Ties need no care: equal p get equal q whatever their order (cumulative min), as in the reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fn {
+
+#define BH_THREADS 256
+#define BH_ITEMS 8                          // keys per thread per CTA chunk
+#define BH_CHUNK (BH_THREADS * BH_ITEMS)
+
+__global__ void bh_keys_kernel(long long n, const double* p, uint64_t* keys, uint32_t* idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = p[i];
+    if (v != v) v = 1.0;                    // p_adjust.py:7
+    keys[i] = (uint64_t)__double_as_longlong(v);
+    idx[i] = (uint32_t)i;
+}
+
+// hist[d * nblocks + b] = number of keys of CTA b's chunk whose digit is d
+__global__ void __launch_bounds__(BH_THREADS) bh_hist_kernel(long long n, const uint64_t* keys, int shift,
+                                                             uint32_t* hist, int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * BH_CHUNK;
+    for (int it = 0; it < BH_ITEMS; ++it) {
+        const long long i = base + it * BH_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of hist (256 * nblocks entries, digit-major) in place; one CTA
+__global__ void __launch_bounds__(1024) bh_scan_kernel(uint32_t* hist, long long total) {
+    __shared__ uint32_t part[1024];
+    const long long per = (total + blockDim.x - 1) / blockDim.x;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < total ? lo + per : total;
+    uint32_t s = 0;
+    for (long long i = lo; i < hi; ++i) s += hist[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { const uint32_t t = part[i]; part[i] = run; run += t; }
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (long long i = lo; i < hi; ++i) { const uint32_t t = hist[i]; hist[i] = run; run += t; }
+}
+
+// stable scatter of CTA b's chunk using the scanned histogram as per-(digit, CTA) base offsets
+__global__ void __launch_bounds__(BH_THREADS) bh_scatter_kernel(long long n, const uint64_t* keys_in,
+                                                                const uint32_t* idx_in, uint64_t* keys_out,
+                                                                uint32_t* idx_out, int shift,
+                                                                const uint32_t* hist, int nblocks) {
+    __shared__ uint32_t digit_base[256];                    // next free output slot per digit
+    __shared__ uint32_t warp_cnt[BH_THREADS / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    digit_base[threadIdx.x] = hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    const long long base = (long long)blockIdx.x * BH_CHUNK;
+    for (int it = 0; it < BH_ITEMS; ++it) {
+        for (int w = 0; w < BH_THREADS / 32; ++w) warp_cnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        const long long i = base + it * BH_THREADS + threadIdx.x;
+        const bool live = i < n;
+        uint64_t key = 0; uint32_t id = 0; uint32_t d = 0;
+        if (live) { key = keys_in[i]; id = idx_in[i]; d = (uint32_t)((key >> shift) & 0xff); }
+        // lanes with the same digit (dead lanes get a digit of their own: 256)
+        const uint32_t peers = __match_any_sync(0xffffffffu, live ? d : 256u);
+        const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (live && rank_in_warp == 0) warp_cnt[warp][d] = __popc(peers);
+        __syncthreads();
+        // per digit: exclusive scan over warps (thread t owns digit t), advance the digit base
+        uint32_t mine_before = 0;
+        {
+            uint32_t run = 0;
+            const uint32_t t = threadIdx.x;
+            for (int w = 0; w < BH_THREADS / 32; ++w) { const uint32_t c = warp_cnt[w][t]; warp_cnt[w][t] = run; run += c; }
+            mine_before = run;              // total of this round for digit t
+        }
+        __syncthreads();
+        if (live) {
+            const uint32_t pos = digit_base[d] + warp_cnt[warp][d] + rank_in_warp;
+            keys_out[pos] = key;
+            idx_out[pos] = id;
+        }
+        __syncthreads();
+        digit_base[threadIdx.x] += mine_before;
+    }
+}
+
+// v_r = (p_r * n) / (r + 1); per-chunk minimum
+__global__ void __launch_bounds__(BH_THREADS) bh_chunkmin_kernel(long long n, const uint64_t* keys, double* chunk_min) {
+    __shared__ double red[BH_THREADS];
+    const long long base = (long long)blockIdx.x * BH_CHUNK + (long long)threadIdx.x * BH_ITEMS;
+    double mn = INFINITY;
+    for (int k = 0; k < BH_ITEMS; ++k) {
+        const long long r = base + k;
+        if (r < n) {
+            const double p = __longlong_as_double((long long)keys[r]);
+            const double v = __ddiv_rn(__dmul_rn(p, (double)n), (double)(r + 1));
+            mn = fmin(mn, v);
+        }
+    }
+    red[threadIdx.x] = mn;
+    __syncthreads();
+    for (int s = BH_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_min[blockIdx.x] = red[0];
+}
+
+// carry[b] = min over chunks > b (inf for the last); one CTA, sequential in one thread per segment
+__global__ void bh_carry_kernel(int nchunks, const double* chunk_min, double* carry) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double run = INFINITY;
+    for (int b = nchunks - 1; b >= 0; --b) { carry[b] = run; run = fmin(run, chunk_min[b]); }
+}
+
+// q_(r) = min(1, suffix-min), scattered back to gene order
+__global__ void __launch_bounds__(BH_THREADS) bh_finish_kernel(long long n, const uint64_t* keys, const uint32_t* idx,
+                                                               const double* carry, double* q) {
+    __shared__ double tmin[BH_THREADS];
+    const long long base = (long long)blockIdx.x * BH_CHUNK + (long long)threadIdx.x * BH_ITEMS;
+    double v[BH_ITEMS];
+    double mn = INFINITY;
+    for (int k = BH_ITEMS - 1; k >= 0; --k) {
+        const long long r = base + k;
+        double x = INFINITY;
+        if (r < n) {
+            const double p = __longlong_as_double((long long)keys[r]);
+            x = __ddiv_rn(__dmul_rn(p, (double)n), (double)(r + 1));
+        }
+        mn = fmin(mn, x);
+        v[k] = mn;                            // suffix min within the thread's run
+    }
+    tmin[threadIdx.x] = mn;
+    __syncthreads();
+    // min over later threads of the CTA and later chunks
+    double later = carry[blockIdx.x];
+    for (int t = threadIdx.x + 1; t < BH_THREADS; ++t) later = fmin(later, tmin[t]);
+    for (int k = 0; k < BH_ITEMS; ++k) {
+        const long long r = base + k;
+        if (r < n) q[idx[r]] = fmin(1.0, fmin(v[k], later));
+    }
+}
+
+}  // namespace fn

@@ -1,0 +1,713 @@
+// Per-gene REML mathematics of the Fitnoise hot path (SURVEY.md section 8a "Math").
+//
+// What the reference does per gene with a complete QR, an explicit inverse and a determinant of
+// the (k-c)x(k-c) transformed covariance (fitnoise.py:23-50, distributions.py:4-7,135-147,
+// 167-215) is done here with the c x c weighted normal equations only:
+//
+//   w_j = 1/sigma2_j (0 for dropped samples), A = X'WX, b = X'Wy, beta = A^-1 b
+//   d2        = z2' S^-1 z2        = sum_j w_j (y_j - x_j beta)^2 = y'Wy - b'beta
+//   ln det S  = sum_ret ln sigma2_j + ln det A - ln det (X_ret' X_ret)
+//   d(-ll)/d sigma2_j = 1/2 (w_j - w_j^2 x_j'A^-1 x_j) - kappa (w_j r_j)^2
+//
+// Thread mapping (device): a gene is handled by `lpg` adjacent lanes of one warp (lpg a power of
+// two, 1..32); lane l owns samples l, l+lpg, ... of the gene's row, which lives in shared memory
+// (tile staged by fn_tile.cuh).  Lane-partial sums are combined with xor-shuffles, after which
+// every lane of the gene holds the full sums and redundantly does the small c x c algebra.
+// On the host (tests/hostcheck only) lpg = 1 and the shuffles compile away.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "fn_special.cuh"
+
+namespace fn {
+
+enum { KIND_SCALE1 = 0, KIND_SCALE_PS = 1, KIND_PATSEQ = 2 };
+enum { DIST_NORMAL = 0, DIST_T = 1, DIST_T_FIXED = 2 };
+
+// Variance family: sigma2_j = theta_a[j or 0] * U_j + theta_b[j or 0] * T_j   
+//   KIND_SCALE1    U_j = 1/w_j (w = precision weight, or 1), one shared theta_a (na = 1), or
+//                  theta_a == 1 fixed (na = 0: Model_independent)          fitnoise.py:530-535,573-578
+//   KIND_SCALE_PS  U_j = 1/w_j, theta_a per sample (na = m)                 fitnoise.py:609-614
+//   KIND_PATSEQ    U_j = rc_j (* gs if v3), T_j = y_j^2 (tail_own) or gs;   fitnoise.py:671-678,
+//                  rc_j = 1/max(count_j,1), gs = avgtail^2; na, nb in {1, m} 717-724,769-776,825-832,875-882
+struct Family {
+    int kind;
+    int na, nb;        // number of theta_a / theta_b entries: 0, 1 or m
+    int tail_own;      // PATSEQ v1: T_j = y_j^2
+    int v3;            // PATSEQ v3: sigma2_j = (theta_a rc_j + theta_b) * gs
+    int dist;          // DIST_NORMAL, DIST_T (df = theta[0]), DIST_T_FIXED (df = fixed_df)
+    double fixed_df;   // Model_independent: 1e-10  (fitnoise.py:577)
+};
+
+FN_HD bool finite_d(double x) { return fabs(x) < INFINITY; }   // false for NaN too
+
+// ------------------------------------------------------------------------------------------
+// lane cooperation
+// ------------------------------------------------------------------------------------------
+FN_HD double lane_sum(double v, int lpg) {
+#ifdef __CUDA_ARCH__
+    for (int off = lpg >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+#else
+    (void)lpg;
+#endif
+    return v;
+}
+FN_HD int lane_sum_i(int v, int lpg) {
+#ifdef __CUDA_ARCH__
+    for (int off = lpg >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+#else
+    (void)lpg;
+#endif
+    return v;
+}
+FN_HD bool warp_any(bool p) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(0xffffffffu, p);
+#else
+    return p;
+#endif
+}
+
+// Product of many positive doubles kept as mantissa in [1,2) and an integer exponent, so that
+// sum_j ln sigma2_j costs one log per gene instead of one per sample.
+struct LogProd {
+    double mant;
+    int expo;
+    FN_HD void init() { mant = 1.0; expo = 0; }
+    FN_HD void renorm() {
+#ifdef __CUDA_ARCH__
+        long long bits = __double_as_longlong(mant);
+#else
+        long long bits; memcpy(&bits, &mant, 8);
+#endif
+        expo += (int)((bits >> 52) & 0x7ff) - 1023;
+        bits = (bits & ~(0x7ffLL << 52)) | (1023LL << 52);
+#ifdef __CUDA_ARCH__
+        mant = __longlong_as_double(bits);
+#else
+        memcpy(&mant, &bits, 8);
+#endif
+    }
+    // x must be a positive normal double; anything else poisons the product with NaN
+    FN_HD void mul(double x) {
+        mant *= x;
+        if (!(mant >= 2.3e-308 && mant < 1.7e308)) { mant = NAN; return; }
+        renorm();
+    }
+    FN_HD void lane_reduce(int lpg) {
+#ifdef __CUDA_ARCH__
+        for (int off = lpg >> 1; off > 0; off >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, mant, off);
+            const int oe = __shfl_xor_sync(0xffffffffu, expo, off);
+            mant *= om; expo += oe;
+            if (mant == mant) renorm();
+        }
+#else
+        (void)lpg;
+#endif
+    }
+    FN_HD double log_value() const { return log(mant) + 0.6931471805599453094 * (double)expo; }
+};
+
+// ------------------------------------------------------------------------------------------
+// view of one gene's row for one lane
+// ------------------------------------------------------------------------------------------
+struct GeneView {
+    double* y;          // row of y (m doubles); writable for the in-place per-sample gradient
+    double* aux;        // row of the second array (precision weights or rc), or nullptr
+    double gs;          // per-gene scalar (avgtail^2) or 0
+    int m;
+    int lane, lpg;      // this lane's index within the gene, lanes per gene
+    int cnt;            // number of samples this lane owns
+    int skew;           // rotation of the lane-local sample order (shared-memory bank spreading)
+    FN_HD void setup(int m_, int lane_, int lpg_, int skew_) {
+        m = m_; lane = lane_; lpg = lpg_;
+        cnt = (m - lane + lpg - 1) / lpg;
+        if (cnt < 0) cnt = 0;
+        skew = cnt > 0 ? skew_ % cnt : 0;
+    }
+    FN_HD int sample(int i) const {        // i in [0, cnt)
+        int ii = i + skew;
+        if (ii >= cnt) ii -= cnt;
+        return lane + lpg * ii;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// small dense algebra on packed lower-triangular storage: (i,j), j<=i at i(i+1)/2+j
+// ------------------------------------------------------------------------------------------
+template <int C> struct Tri { enum { N = C * (C + 1) / 2 }; };
+#define FN_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+// In-place Cholesky A = L L'.  On return a holds L below the diagonal and 1/L_ii on it;
+// det = prod of pivots (so ln det A = ln det).  Returns false when a pivot is <= rel_tol * A_ii.
+template <int C>
+FN_HD bool chol(double* a, double& det, double rel_tol) {
+    bool ok = true;
+    det = 1.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double s = a[FN_TRI(i, j)];
+#pragma unroll
+            for (int t = 0; t < j; ++t) s -= a[FN_TRI(i, t)] * a[FN_TRI(j, t)];
+            if (j < i) {
+                a[FN_TRI(i, j)] = s * a[FN_TRI(j, j)];
+            } else {
+                const double orig = a[FN_TRI(i, i)];
+                if (!(s > rel_tol * orig) || !(s > 0.0)) { ok = false; s = 1.0; }
+                det *= s;
+                a[FN_TRI(i, i)] = 1.0 / sqrt(s);
+            }
+        }
+    }
+    return ok;
+}
+
+// Solve L L' x = b in place (L as produced by chol()).
+template <int C>
+FN_HD void chol_solve(const double* l, double* x) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        double s = x[i];
+#pragma unroll
+        for (int t = 0; t < i; ++t) s -= l[FN_TRI(i, t)] * x[t];
+        x[i] = s * l[FN_TRI(i, i)];
+    }
+#pragma unroll
+    for (int i = C - 1; i >= 0; --i) {
+        double s = x[i];
+#pragma unroll
+        for (int t = i + 1; t < C; ++t) s -= l[FN_TRI(t, i)] * x[t];
+        x[i] = s * l[FN_TRI(i, i)];
+    }
+}
+
+// h = x' A^-1 x = |L^-1 x|^2
+template <int C>
+FN_HD double leverage(const double* l, const double* x) {
+    double z[C];
+    double h = 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        double s = x[i];
+#pragma unroll
+        for (int t = 0; t < i; ++t) s -= l[FN_TRI(i, t)] * z[t];
+        z[i] = s * l[FN_TRI(i, i)];
+        h += z[i] * z[i];
+    }
+    return h;
+}
+
+// A^-1 (packed lower) from the Cholesky factor.
+template <int C>
+FN_HD void chol_inverse(const double* l, double* ainv) {
+    double li[Tri<C>::N];           // L^-1, lower triangular
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        li[FN_TRI(j, j)] = l[FN_TRI(j, j)];
+#pragma unroll
+        for (int i = j + 1; i < C; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = j; t < i; ++t) s -= l[FN_TRI(i, t)] * li[FN_TRI(t, j)];
+            li[FN_TRI(i, j)] = s * l[FN_TRI(i, i)];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = i; t < C; ++t) s += li[FN_TRI(t, i)] * li[FN_TRI(t, j)];
+            ainv[FN_TRI(i, j)] = s;
+        }
+}
+
+// Weighted normal-equation accumulators for one gene (one lane's share until reduce()).
+template <int C>
+struct Normal {
+    double a[Tri<C>::N];
+    double b[C];
+    double yy;
+    int k;
+    FN_HD void init() {
+#pragma unroll
+        for (int i = 0; i < Tri<C>::N; ++i) a[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) b[i] = 0.0;
+        yy = 0.0; k = 0;
+    }
+    FN_HD void add(double w, double y, const double* x) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const double wx = w * x[i];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) a[FN_TRI(i, j)] += wx * x[j];
+            b[i] += wx * y;
+        }
+        yy += (w * y) * y;
+    }
+    FN_HD void reduce(int lpg) {
+        if (lpg == 1) return;
+#pragma unroll
+        for (int i = 0; i < Tri<C>::N; ++i) a[i] = lane_sum(a[i], lpg);
+#pragma unroll
+        for (int i = 0; i < C; ++i) b[i] = lane_sum(b[i], lpg);
+        yy = lane_sum(yy, lpg);
+        k = lane_sum_i(k, lpg);
+    }
+    // columns c_real..C-1 of the design are zero padding: put 1 on their diagonal so that the
+    // factorisation goes through with det and beta unchanged
+    FN_HD void pad(int c_real) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) if (i >= c_real) a[FN_TRI(i, i)] = 1.0;
+    }
+};
+
+template <int C>
+FN_HD void load_x(const double* X, int j, double* x) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) x[i] = X[j * C + i];
+}
+
+// ------------------------------------------------------------------------------------------
+// per-sample variance model
+// ------------------------------------------------------------------------------------------
+// Per-evaluation tables in shared memory (device) / plain arrays (host), all of length m:
+//   KIND_SCALE_PS: ta[j] = 1/theta_j, tb[j] = ln theta_j
+//   KIND_PATSEQ:   ta[j] = theta_a(j), tb[j] = theta_b(j)
+struct EvalConst {
+    int kind, tail_own, v3;
+    int is_t;             // multivariate t (else normal)
+    double v;             // df
+    double theta0;        // SCALE1 shared variance (1 when na == 0)
+    const double* ta;
+    const double* tb;
+    const double* t0;     // t0[p]: -(log-density terms that depend on (v,p) only)
+    const double* t1;     // t1[p]: their derivative with respect to v (t only)
+};
+
+// (v,p)-only terms of -log density (distributions.py:139-146 t / :44-46 normal), and d/dv.
+FN_HD void density_tables(int is_t, double v, int p, double& t0, double& t1) {
+    if (is_t) {
+        const double hp = 0.5 * (v + p);
+        t0 = -(lgamma(hp) - lgamma(0.5 * v) - (0.5 * p) * log(3.14159265358979323846 * v));
+        t1 = -0.5 * digamma(hp) + 0.5 * digamma(0.5 * v) + 0.5 * p / v;
+    } else {
+        t0 = 0.5 * p * 1.8378770664093454836;      // p/2 ln(2 pi)
+        t1 = 0.0;
+    }
+}
+
+// Weight (1/sigma2) and validity of sample j.  U and T are the partials of sigma2 with respect to
+// theta_a(j) and theta_b(j) (PATSEQ) -- for the SCALE kinds the gradient is formed without them.
+struct SampleVar {
+    double w;        // 1/sigma2, or 0 when dropped
+    double s2;       // sigma2 (PATSEQ only)
+    double U, T;     // PATSEQ only
+    bool valid;
+};
+
+FN_HD SampleVar sample_var(const EvalConst& ec, const GeneView& gv, int j, double y) {
+    SampleVar sv;
+    sv.U = 0.0; sv.T = 0.0; sv.s2 = 1.0;
+    const bool yok = finite_d(y);
+    if (ec.kind == KIND_PATSEQ) {
+        const double rc = gv.aux[j];
+        sv.U = ec.v3 ? rc * gv.gs : rc;
+        sv.T = ec.tail_own ? (yok ? y * y : 0.0) : gv.gs;
+        sv.s2 = ec.ta[j] * sv.U + ec.tb[j] * sv.T;
+        sv.valid = yok && finite_d(sv.s2);          // Mv*.good: distributions.py:31-36
+        sv.w = sv.valid ? 1.0 / sv.s2 : 0.0;
+    } else {
+        // sigma2 = theta / w_prec : finite unless w_prec is 0 or NaN  (aux = 1/weights, fitnoise.py:540)
+        const double wp = gv.aux ? gv.aux[j] : 1.0;
+        sv.valid = yok && (wp != 0.0) && (wp == wp);
+        const double it = (ec.kind == KIND_SCALE_PS) ? ec.ta[j] : 1.0;   // SCALE1 works at theta = 1
+        sv.w = sv.valid ? wp * it : 0.0;
+    }
+    return sv;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: theta-independent preparation of one gene (fitnoise.py:23-35 restated without the QR)
+// ------------------------------------------------------------------------------------------
+struct PrepOut {
+    int k;              // retained samples
+    bool eligible;      // k > c and the retained sub-design has full column rank
+    double cst;         // theta-independent part of ln det S:  -ln det(X_ret'X_ret) [- sum_ret ln w_prec]
+    double average;     // mean(y[retain]) when k > c, else NaN       (fitnoise.py:267)
+    double ysum, yss;   // over finite y: sum and sum of squares about the row mean  (initial variance)
+    int nfinite;
+    int bad_counts;     // PATSEQ: samples with count == 0 but finite y   (fitnoise.py:647)
+    double avg_tail;    // PATSEQ v2/v3: avgtail (not squared)            (fitnoise.py:747,853)
+};
+
+#define FN_RANK_TOL 1e-10
+
+// `counts_raw`: for PATSEQ the aux row still holds RAW counts at prepare time.
+template <int C>
+FN_HD void prepare_gene(const Family& fam, const GeneView& gv, const double* X, int c_real, PrepOut& out) {
+    Normal<C> g;
+    g.init();
+    LogProd lw; lw.init();
+    double ysum = 0.0, csum = 0.0, ycsum = 0.0, ysel = 0.0;
+    int nfin = 0, bad = 0;
+    const bool patseq = fam.kind == KIND_PATSEQ;
+    for (int i = 0; i < gv.cnt; ++i) {
+        const int j = gv.sample(i);
+        const double y = gv.y[j];
+        const bool yok = finite_d(y);
+        double aux = gv.aux ? gv.aux[j] : 1.0;
+        bool valid;
+        if (patseq) {
+            if (aux == 0.0 && yok) ++bad;
+            csum += aux;
+            ycsum += (yok ? y : 0.0) * aux;
+            valid = yok && finite_d(aux);
+        } else {
+            valid = yok && aux != 0.0 && aux == aux;
+            if (valid && gv.aux) lw.mul(fabs(aux));
+        }
+        if (yok) { ysum += y; ++nfin; }
+        if (valid) {
+            double x[C];
+            load_x<C>(X, j, x);
+            g.add(1.0, 0.0, x);
+            ysel += y;
+            ++g.k;
+        }
+    }
+    g.reduce(gv.lpg);
+    lw.lane_reduce(gv.lpg);
+    ysum = lane_sum(ysum, gv.lpg);
+    ysel = lane_sum(ysel, gv.lpg);
+    nfin = lane_sum_i(nfin, gv.lpg);
+    bad = lane_sum_i(bad, gv.lpg);
+    if (patseq) { csum = lane_sum(csum, gv.lpg); ycsum = lane_sum(ycsum, gv.lpg); }
+    // second sweep: squared deviations of the finite y about their mean (numpy.var, fitnoise.py:546)
+    const double mean = nfin > 0 ? ysum / nfin : 0.0;
+    double ss = 0.0;
+    for (int i = 0; i < gv.cnt; ++i) {
+        const double y = gv.y[gv.sample(i)];
+        if (finite_d(y)) { const double d = y - mean; ss += d * d; }
+    }
+    ss = lane_sum(ss, gv.lpg);
+
+    g.pad(c_real);
+    double det;
+    const bool full_rank = chol<C>(g.a, det, FN_RANK_TOL);
+    out.k = g.k;
+    out.eligible = (g.k > c_real) && full_rank;
+    out.cst = -log(det);
+    if (!patseq && gv.aux) out.cst -= lw.log_value();
+    out.average = (g.k > c_real) ? ysel / g.k : NAN;
+    out.ysum = ysum; out.yss = ss; out.nfinite = nfin;
+    out.bad_counts = bad;
+    out.avg_tail = 0.0;
+    if (patseq) {
+        double num = ycsum;
+        if (!fam.v3) num = fmax(1.0, num);
+        out.avg_tail = num / fmax(1.0, csum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: -log likelihood and gradient of one gene
+// ------------------------------------------------------------------------------------------
+struct EvalOut {
+    double value;       // -ll (without the theta-independent cst/2 unless cst was passed)
+    double dv;          // d/d df
+    double ga, gb;      // d/d theta_a, d/d theta_b when they are shared parameters
+    double d2;          // Mahalanobis distance z2'S^-1 z2
+    int p;              // residual df k - c
+    int used;           // 1 when the gene contributed
+};
+
+FN_HD void eval_zero(EvalOut& o) { o.value = 0.0; o.dv = 0.0; o.ga = 0.0; o.gb = 0.0; o.d2 = NAN; o.p = 0; o.used = 0; }
+
+// value, dv and kappa from (p, ln det S, d2)
+FN_HD double finish_density(const EvalConst& ec, int p, double logdet, double d2, double& dv, double& kappa) {
+    if (ec.is_t) {
+        const double v = ec.v;
+        const double l1p = log1p(d2 / v);
+        const double hp = 0.5 * (v + p);
+        kappa = hp / (v + d2);
+        dv = ec.t1[p] + 0.5 * l1p - kappa * d2 / v;
+        return ec.t0[p] + 0.5 * logdet + hp * l1p;
+    }
+    kappa = 0.5;
+    dv = 0.0;
+    return ec.t0[p] + 0.5 * (logdet + d2);
+}
+
+// KIND_SCALE1: sigma2_j = theta0 / w_prec_j.  All sums are taken at theta = 1 and rescaled;
+// the gradient with respect to theta0 is closed-form (no second sweep):
+//   d(-ll)/d theta0 = (p/2 - kappa d2) / theta0.
+template <int C>
+FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
+                       bool eligible, double cst, EvalOut& out) {
+    Normal<C> nm;
+    nm.init();
+    const int cnt = eligible ? gv.cnt : 0;
+    for (int i = 0; i < cnt; ++i) {
+        const int j = gv.sample(i);
+        const double y = gv.y[j];
+        const SampleVar sv = sample_var(ec, gv, j, y);
+        double x[C];
+        load_x<C>(X, j, x);
+        nm.add(sv.w, sv.valid ? y : 0.0, x);
+        nm.k += sv.valid ? 1 : 0;
+    }
+    nm.reduce(gv.lpg);
+    nm.pad(c_real);
+    double det;
+    const bool ok = chol<C>(nm.a, det, 0.0);
+    double beta[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
+    chol_solve<C>(nm.a, beta);
+    double d2 = nm.yy;
+#pragma unroll
+    for (int i = 0; i < C; ++i) d2 -= nm.b[i] * beta[i];
+    // y'Wy - b'beta cancels badly when the fit explains almost everything: redo from residuals
+    if (warp_any(eligible && d2 < 1e-4 * nm.yy)) {
+        double s = 0.0;
+        for (int i = 0; i < cnt; ++i) {
+            const int j = gv.sample(i);
+            const double y = gv.y[j];
+            const SampleVar sv = sample_var(ec, gv, j, y);
+            double x[C];
+            load_x<C>(X, j, x);
+            double r = sv.valid ? y : 0.0;
+#pragma unroll
+            for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
+            s += sv.w * r * r;
+        }
+        s = lane_sum(s, gv.lpg);
+        if (d2 < 1e-4 * nm.yy) d2 = s;
+    }
+    eval_zero(out);
+    if (!eligible) return;
+    const int p = nm.k - c_real;
+    if (!ok || p <= 0) { out.value = NAN; out.used = 1; return; }
+    if (d2 < 0.0) d2 = 0.0;
+    const double it = 1.0 / ec.theta0;
+    d2 *= it;
+    const double logdet = p * log(ec.theta0) + log(det) + cst;
+    double dv, kappa;
+    out.value = finish_density(ec, p, logdet, d2, dv, kappa);
+    out.dv = dv;
+    out.ga = (0.5 * p - kappa * d2) * it;
+    out.d2 = d2; out.p = p; out.used = 1;
+}
+
+// KIND_SCALE_PS / KIND_PATSEQ: general diagonal variance; two more sweeps over the gene's row
+// (residuals, then the per-sample gradient terms).  When a theta block is per-sample
+// (inplace_a / inplace_b) the per-sample gradient contribution is written over the sample's own
+// slot in the y (term a) / aux (term b) tile for the caller to column-sum; otherwise it is
+// accumulated into out.ga / out.gb.
+template <int C, int KIND>
+FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int c_real,
+                        bool eligible, double cst, bool inplace_a, bool inplace_b, EvalOut& out) {
+    Normal<C> nm;
+    nm.init();
+    LogProd lp; lp.init();
+    double slt = 0.0;                  // SCALE_PS: sum_ret ln theta_j
+    const int cnt = eligible ? gv.cnt : 0;
+    for (int i = 0; i < cnt; ++i) {
+        const int j = gv.sample(i);
+        const double y = gv.y[j];
+        const SampleVar sv = sample_var(ec, gv, j, y);
+        double x[C];
+        load_x<C>(X, j, x);
+        nm.add(sv.w, sv.valid ? y : 0.0, x);
+        if (sv.valid) {
+            ++nm.k;
+            if (KIND == KIND_PATSEQ) lp.mul(sv.s2); else slt += ec.tb[j];
+        }
+    }
+    nm.reduce(gv.lpg);
+    if (KIND == KIND_PATSEQ) lp.lane_reduce(gv.lpg); else slt = lane_sum(slt, gv.lpg);
+    nm.pad(c_real);
+    double det;
+    const bool ok = chol<C>(nm.a, det, 0.0);
+    double beta[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
+    chol_solve<C>(nm.a, beta);
+
+    // sweep 2: d2 from residuals
+    double d2 = 0.0;
+    for (int i = 0; i < cnt; ++i) {
+        const int j = gv.sample(i);
+        const double y = gv.y[j];
+        const SampleVar sv = sample_var(ec, gv, j, y);
+        double x[C];
+        load_x<C>(X, j, x);
+        double r = sv.valid ? y : 0.0;
+#pragma unroll
+        for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
+        d2 += sv.w * r * r;
+    }
+    d2 = lane_sum(d2, gv.lpg);
+
+    eval_zero(out);
+    const int p = nm.k - c_real;
+    const bool good = eligible && ok && p > 0;
+    double kappa = 0.5;
+    if (good) {
+        const double lsig = (KIND == KIND_PATSEQ) ? lp.log_value() : slt;
+        const double logdet = lsig + log(det) + cst;
+        double dv;
+        out.value = finish_density(ec, p, logdet, d2, dv, kappa);
+        out.dv = dv; out.d2 = d2; out.p = p; out.used = 1;
+    } else if (eligible) {
+        out.value = NAN; out.used = 1;
+    }
+
+    // sweep 3: gradient.  e~_j = sigma2_j * d(-ll)/d sigma2_j = 1/2 (1 - w_j h_j) - kappa w_j r_j^2
+    double ga = 0.0, gb = 0.0;
+    for (int i = 0; i < gv.cnt; ++i) {
+        const int j = gv.sample(i);
+        const double y = gv.y[j];
+        double ca = 0.0, cb = 0.0;
+        if (good) {
+            const SampleVar sv = sample_var(ec, gv, j, y);
+            if (sv.valid) {
+                double x[C];
+                load_x<C>(X, j, x);
+                double r = y;
+#pragma unroll
+                for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
+                const double h = leverage<C>(nm.a, x);
+                const double et = 0.5 * (1.0 - sv.w * h) - kappa * sv.w * r * r;
+                if (KIND == KIND_PATSEQ) {
+                    const double e = et * sv.w;
+                    ca = sv.U * e; cb = sv.T * e;
+                } else {
+                    ca = et * ec.ta[j];          // d sigma2_j / d theta_j = sigma2_j / theta_j
+                }
+            }
+        }
+        if (inplace_a) gv.y[j] = ca; else ga += ca;
+        if (KIND == KIND_PATSEQ) { if (inplace_b) gv.aux[j] = cb; else gb += cb; }
+    }
+    if (!inplace_a) out.ga = lane_sum(ga, gv.lpg);
+    if (KIND == KIND_PATSEQ && !inplace_b) out.gb = lane_sum(gb, gv.lpg);
+    // every lane of the gene now holds the same totals: only lane 0 may add them to the CTA sums
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: GLS coefficients and their posterior (fit_coef, fitnoise.py:294-347)
+// ------------------------------------------------------------------------------------------
+struct CoefOut {
+    bool ok;            // k >= c and full rank
+    double d2;
+    int p2;             // k - c
+};
+
+// beta (whitened basis) and A^-1 (packed lower, whitened basis).  The caller maps them back through
+// R^-1 of the design's thin QR.  The variance kinds are evaluated at the FITTED theta
+// (fitnoise.py:311-313).
+template <int C>
+FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
+                     double* beta, double* ainv, CoefOut& out) {
+    Normal<C> nm, gm;
+    nm.init(); gm.init();
+    for (int i = 0; i < gv.cnt; ++i) {
+        const int j = gv.sample(i);
+        const double y = gv.y[j];
+        const SampleVar sv = sample_var(ec, gv, j, y);
+        double x[C];
+        load_x<C>(X, j, x);
+        nm.add(sv.w, sv.valid ? y : 0.0, x);
+        if (sv.valid) { gm.add(1.0, 0.0, x); ++nm.k; }
+    }
+    nm.reduce(gv.lpg);
+    gm.reduce(gv.lpg);
+    nm.pad(c_real); gm.pad(c_real);
+    double det;
+    const bool full_rank = chol<C>(gm.a, det, FN_RANK_TOL);
+    const bool okA = chol<C>(nm.a, det, 0.0);
+#pragma unroll
+    for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
+    chol_solve<C>(nm.a, beta);
+    chol_inverse<C>(nm.a, ainv);
+    double d2 = 0.0;
+    for (int i = 0; i < gv.cnt; ++i) {
+        const int j = gv.sample(i);
+        const double y = gv.y[j];
+        const SampleVar sv = sample_var(ec, gv, j, y);
+        double x[C];
+        load_x<C>(X, j, x);
+        double r = sv.valid ? y : 0.0;
+#pragma unroll
+        for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
+        d2 += sv.w * r * r;
+    }
+    d2 = lane_sum(d2, gv.lpg);
+    if (ec.kind == KIND_SCALE1) {             // sums were taken at theta = 1
+        d2 /= ec.theta0;
+#pragma unroll
+        for (int i = 0; i < Tri<C>::N; ++i) ainv[i] *= ec.theta0;
+    }
+    out.p2 = nm.k - c_real;
+    out.ok = (nm.k >= c_real) && full_rank && okA;
+    out.d2 = (out.p2 > 0) ? d2 : 0.0;        // k == c: the fit is exact (conditional on nothing)
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b: contrasts and their test (Model.test, fitnoise.py:368-396; Mv*.p_value distributions.py:52-57,150-155)
+// ------------------------------------------------------------------------------------------
+#define FN_MAXC 8
+
+// coef (c), V (c x c, row-major), df.  contrasts is c x kc row-major.  Writes contrasted (kc),
+// optionally the kc x kc covariance C'VC, and the p-value of contrasted == 0.
+FN_HDN void test_gene(int c, int kc, const double* coef, const double* V, double df, int is_t,
+                      const double* contrasts, double* contrasted, double* ccov, double& pval) {
+    double mean[FN_MAXC], vc[FN_MAXC * FN_MAXC], s[FN_MAXC * FN_MAXC], z[FN_MAXC];
+    for (int a = 0; a < kc; ++a) {
+        double acc = 0.0;
+        for (int i = 0; i < c; ++i) acc += contrasts[i * kc + a] * coef[i];
+        mean[a] = acc;
+        contrasted[a] = acc;
+    }
+    for (int i = 0; i < c; ++i)                 // vc = V C   (c x kc)
+        for (int a = 0; a < kc; ++a) {
+            double acc = 0.0;
+            for (int t = 0; t < c; ++t) acc += V[i * c + t] * contrasts[t * kc + a];
+            vc[i * kc + a] = acc;
+        }
+    for (int a = 0; a < kc; ++a)                // s = C' V C  (kc x kc)
+        for (int b = 0; b < kc; ++b) {
+            double acc = 0.0;
+            for (int i = 0; i < c; ++i) acc += contrasts[i * kc + a] * vc[i * kc + b];
+            s[a * kc + b] = acc;
+            if (ccov) ccov[a * kc + b] = acc;
+        }
+    // q = mean' s^-1 mean through a Cholesky factor of s
+    bool ok = true;
+    for (int a = 0; a < kc; ++a) {
+        for (int b = 0; b <= a; ++b) {
+            double acc = s[a * kc + b];
+            for (int t = 0; t < b; ++t) acc -= s[a * kc + t] * s[b * kc + t];
+            if (b < a) s[a * kc + b] = acc / s[b * kc + b];
+            else { if (!(acc > 0.0)) { ok = false; acc = 1.0; } s[a * kc + a] = sqrt(acc); }
+        }
+    }
+    double q = 0.0;
+    for (int a = 0; a < kc; ++a) {
+        double acc = mean[a];
+        for (int t = 0; t < a; ++t) acc -= s[a * kc + t] * z[t];
+        z[a] = acc / s[a * kc + a];
+        q += z[a] * z[a];
+    }
+    if (!ok) { pval = NAN; return; }
+    pval = is_t ? f_sf(q / kc, (double)kc, df) : chi2_sf(q, (double)kc);
+}
+
+}  // namespace fn

@@ -1,0 +1,440 @@
+// sm_100a kernels of the Fitnoise hot path.  K1 prepare, K2 nll+grad, K3 coef, K3b test,
+// noise p-values, weights, aux transform.  (K4, Benjamini-Hochberg, lives in fn_bh.cuh.)
+//
+// All per-gene kernels share one shape: persistent CTAs, gene tiles staged into shared memory by
+// the TMA engine (fn_tile.cuh), a gene handled by `lpg` adjacent lanes (fn_gene.cuh), CTA sums
+// reduced with shuffles, and a deterministic grid reduction finished by the last CTA to arrive.
+#pragma once
+#include <cuda_runtime.h>
+#include "fn_gene.cuh"
+#include "fn_tile.cuh"
+
+namespace fn {
+
+// accumulator layout of one CTA's partial sums
+enum { ACC_VALUE = 0, ACC_DV = 1, ACC_GA = 2, ACC_GB = 3, ACC_USED = 4, ACC_BAD = 5, ACC_FIXED = 6 };
+
+struct GridReduce {
+    double* partials;        // gridDim.x * nacc
+    unsigned int* ticket;
+    double* out_dev;         // nacc doubles
+    double* out_host;        // mapped pinned, nacc doubles, or nullptr
+    int nacc;
+};
+
+// Sum `nacc` per-CTA values over the grid in a fixed order; the last CTA to arrive does it.
+// `vals` is this CTA's shared array of nacc doubles (already complete, visible after a barrier).
+__device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* vals) {
+    __shared__ int is_last;
+    for (int i = threadIdx.x; i < gr.nacc; i += blockDim.x)
+        gr.partials[(size_t)blockIdx.x * gr.nacc + i] = vals[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(gr.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < gr.nacc; i += blockDim.x) {
+        double s = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) s += gr.partials[(size_t)b * gr.nacc + i];
+        gr.out_dev[i] = s;
+        if (gr.out_host) gr.out_host[i] = s;
+    }
+    if (threadIdx.x == 0) *gr.ticket = 0;
+    __threadfence_system();
+}
+
+// CTA-wide sum of NV thread-local doubles into shared `out[NV]` (deterministic order).
+template <int NV>
+__device__ __forceinline__ void block_sum(double* v, double* out, double* scratch /* 32*NV */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if (lane == 0) scratch[warp * NV + i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < nwarp; ++w) s += scratch[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up common to the per-gene kernels
+// ------------------------------------------------------------------------------------------
+struct GeomParams {
+    long long n;             // genes
+    long long n_tiles;
+    int m;
+    int genes;               // genes per tile  (= blockDim.x / lpg)
+    int lpg;
+    int stages;
+    int width;               // template width C the designs are padded to
+};
+
+// dynamic shared memory: [tables: doubles][stage buffers (128-aligned)]
+__device__ __forceinline__ unsigned char* align128(unsigned char* p) {
+    return (unsigned char*)(((uintptr_t)p + 127) & ~(uintptr_t)127);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 prepare
+// ------------------------------------------------------------------------------------------
+enum { PREP_VARSUM = 0, PREP_VARCNT = 1, PREP_BAD = 2, PREP_CSTSUM = 3, PREP_ELIG = 4, PREP_NACC = 5 };
+
+struct PrepParams {
+    GeomParams g;
+    TileSrc src;             // y, aux = RAW second array, status = control bits
+    Family fam;
+    const double* xn; const double* xc;     // m x width each
+    int c_noise, c_ctrl;
+    uint8_t* status_out;     // n_pad
+    double* cst_out;         // n_pad
+    double* avg_out;         // n_pad
+    double* gs_out;          // n_pad or nullptr (PATSEQ: avgtail^2)
+    GridReduce gr;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bars[FN_MAX_STAGES];
+    __shared__ double red_out[PREP_NACC];
+    __shared__ double red_scratch[32 * PREP_NACC];
+    double* xn = (double*)smem_raw;
+    double* xc = xn + p.g.m * C;
+    unsigned char* stage_base = align128((unsigned char*)(xc + p.g.m * C));
+    for (int i = threadIdx.x; i < p.g.m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
+    TileRing ring;
+    ring.init(bars, stage_base, p.g.stages, p.src);
+
+    const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
+    double acc[PREP_NACC];
+#pragma unroll
+    for (int i = 0; i < PREP_NACC; ++i) acc[i] = 0.0;
+
+    tile_loop(ring, p.g.n_tiles, false, [&](const TileStage& st, long long tile) {
+        const long long gene = tile * p.g.genes + gl;
+        GeneView gv;
+        gv.y = st.y + (size_t)gl * p.g.m;
+        gv.aux = st.aux ? st.aux + (size_t)gl * p.g.m : nullptr;
+        gv.gs = 0.0;
+        gv.setup(p.g.m, lane, p.g.lpg, gl);
+        const bool control = (st.status[gl] & 2) != 0;
+        PrepOut po;
+        prepare_gene<C>(p.fam, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, po);
+        if (lane == 0 && gene < p.g.n) {
+            p.status_out[gene] = (uint8_t)((po.eligible ? 1 : 0) | (control ? 2 : 0));
+            p.cst_out[gene] = po.cst;
+            p.avg_out[gene] = po.average;
+            if (p.gs_out) p.gs_out[gene] = po.avg_tail * po.avg_tail;
+            if (po.nfinite > 0) { acc[PREP_VARSUM] += po.yss / po.nfinite; acc[PREP_VARCNT] += 1.0; }
+            acc[PREP_BAD] += po.bad_counts;
+            if (po.eligible) { acc[PREP_CSTSUM] += po.cst; acc[PREP_ELIG] += 1.0; }
+        }
+    });
+    block_sum<PREP_NACC>(acc, red_out, red_scratch);
+    grid_reduce(p.gr, red_out);
+}
+
+// PATSEQ: raw counts -> rc = 1/max(count, 1)   (fitnoise.py:648,749)
+__global__ void counts_to_rc_kernel(double* aux, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+        aux[i] = 1.0 / fmax(aux[i], 1.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 -log likelihood + gradient
+// ------------------------------------------------------------------------------------------
+struct EvalParams {
+    GeomParams g;
+    TileSrc src;             // y, aux (precision weights / rc), gs, cst (per-gene mode only), status
+    const double* xn; const double* xc;
+    int c_noise, c_ctrl;
+    int kind, tail_own, v3, is_t;
+    double v, theta0;
+    const double* ta; const double* tb;     // device tables of length m (general kinds)
+    int inplace_a, inplace_b;               // per-sample theta blocks
+    double* pg_score; double* pg_d2; int* pg_p;     // per-gene outputs (nullptr in sum mode)
+    GridReduce gr;           // nacc = ACC_FIXED (+ 2m when a block is per-sample)
+};
+
+template <int C, int KIND>
+__global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bars[FN_MAX_STAGES];
+    __shared__ double red_scratch[32 * ACC_FIXED];
+    const int m = p.g.m;
+    // tables: xn, xc (m*C each), ta, tb (m each), t0, t1 (m+1 each), vals (ACC_FIXED + 2m), colscratch (2*blockDim)
+    double* xn = (double*)smem_raw;
+    double* xc = xn + m * C;
+    double* ta = xc + m * C;
+    double* tb = ta + m;
+    double* t0 = tb + m;
+    double* t1 = t0 + (m + 1);
+    double* vals = t1 + (m + 1);
+    double* colscr = vals + (ACC_FIXED + 2 * m);
+    const bool inplace = p.inplace_a || p.inplace_b;
+    unsigned char* stage_base = align128((unsigned char*)(colscr + (inplace ? 2 * blockDim.x : 0)));
+
+    for (int i = threadIdx.x; i < m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        ta[i] = p.ta ? p.ta[i] : 0.0;
+        tb[i] = p.tb ? p.tb[i] : 0.0;
+    }
+    for (int i = threadIdx.x; i <= m; i += blockDim.x) density_tables(p.is_t, p.v, i, t0[i], t1[i]);
+    TileRing ring;
+    ring.init(bars, stage_base, p.g.stages, p.src);      // contains the __syncthreads() for the tables
+
+    EvalConst ec;
+    ec.kind = KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
+    ec.ta = ta; ec.tb = tb; ec.t0 = t0; ec.t1 = t1;
+
+    const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
+    double acc[ACC_FIXED];
+#pragma unroll
+    for (int i = 0; i < ACC_FIXED; ++i) acc[i] = 0.0;
+    // per-sample gradient columns: thread (sub, col) sums column col over genes sub, sub+nsub, ...
+    const int nsub = inplace ? blockDim.x / m : 0;
+    const int col = inplace ? threadIdx.x % m : 0, sub = inplace ? threadIdx.x / m : 0;
+    double col_a = 0.0, col_b = 0.0;
+
+    tile_loop(ring, p.g.n_tiles, inplace, [&](const TileStage& st, long long tile) {
+        const long long gene = tile * p.g.genes + gl;
+        GeneView gv;
+        gv.y = st.y + (size_t)gl * m;
+        gv.aux = st.aux ? st.aux + (size_t)gl * m : nullptr;
+        gv.gs = st.gs ? st.gs[gl] : 0.0;
+        gv.setup(m, lane, p.g.lpg, gl);
+        const uint8_t status = st.status[gl];
+        const bool control = (status & 2) != 0;
+        const bool eligible = (status & 1) != 0;
+        const double cst = st.cst ? st.cst[gl] : 0.0;
+        EvalOut eo;
+        if (KIND == KIND_SCALE1)
+            eval_scale1<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst, eo);
+        else
+            eval_general<C, KIND>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst,
+                                  p.inplace_a != 0, p.inplace_b != 0, eo);
+        if (lane == 0 && gene < p.g.n) {
+            if (eo.used) {
+                if (eo.value == eo.value) {
+                    acc[ACC_VALUE] += eo.value; acc[ACC_DV] += eo.dv;
+                    acc[ACC_GA] += eo.ga; acc[ACC_GB] += eo.gb; acc[ACC_USED] += 1.0;
+                } else {
+                    acc[ACC_BAD] += 1.0;
+                }
+            }
+            if (p.pg_score) {
+                p.pg_score[gene] = eo.used ? eo.value : NAN;
+                p.pg_d2[gene] = eo.d2;
+                p.pg_p[gene] = eo.p;
+            }
+        }
+        if (inplace) {
+            __syncthreads();
+            if (sub < nsub) {
+                for (int g = sub; g < p.g.genes; g += nsub) {
+                    if (p.inplace_a) col_a += st.y[(size_t)g * m + col];
+                    if (p.inplace_b) col_b += st.aux[(size_t)g * m + col];
+                }
+            }
+        }
+    });
+
+    block_sum<ACC_FIXED>(acc, vals, red_scratch);
+    if (inplace) {
+        colscr[threadIdx.x] = col_a;
+        colscr[blockDim.x + threadIdx.x] = col_b;
+        __syncthreads();
+        if (threadIdx.x < m) {
+            double sa = 0.0, sb = 0.0;
+            for (int s = 0; s < nsub; ++s) { sa += colscr[s * m + threadIdx.x]; sb += colscr[blockDim.x + s * m + threadIdx.x]; }
+            vals[ACC_FIXED + threadIdx.x] = sa;
+            vals[ACC_FIXED + m + threadIdx.x] = sb;
+        }
+        __syncthreads();
+    }
+    grid_reduce(p.gr, vals);
+}
+
+// noise p-values from (d2, p): Mvt.p_value F sf (distributions.py:150-155) / Mvnormal chi2 sf (:52-57)
+__global__ void noise_p_kernel(long long n, const double* d2, const int* pdf, int is_t, double v, double* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = d2[i];
+    const int p = pdf[i];
+    if (!(d == d) || p <= 0) { out[i] = NAN; return; }
+    out[i] = is_t ? f_sf(d / p, (double)p, v) : chi2_sf(d, (double)p);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 coefficients
+// ------------------------------------------------------------------------------------------
+struct CoefParams {
+    GeomParams g;
+    TileSrc src;
+    const double* x;         // m x width, whitened coefficient design
+    const double* rinv;      // c x c upper triangular
+    int c;
+    int kind, tail_own, v3, is_t;
+    double v, theta0;
+    const double* ta; const double* tb;
+    double* coef;            // n x c
+    double* covar;           // n x c x c
+    double* dfpost;          // n
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bars[FN_MAX_STAGES];
+    __shared__ double rinv[FN_MAXC * FN_MAXC];
+    const int m = p.g.m, c = p.c;
+    double* x = (double*)smem_raw;
+    double* ta = x + m * C;
+    double* tb = ta + m;
+    unsigned char* stage_base = align128((unsigned char*)(tb + m));
+    for (int i = threadIdx.x; i < m * C; i += blockDim.x) x[i] = p.x[i];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) { ta[i] = p.ta ? p.ta[i] : 0.0; tb[i] = p.tb ? p.tb[i] : 0.0; }
+    for (int i = threadIdx.x; i < c * c; i += blockDim.x) rinv[i] = p.rinv[i];
+    TileRing ring;
+    ring.init(bars, stage_base, p.g.stages, p.src);
+
+    EvalConst ec;
+    ec.kind = p.kind; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
+    ec.ta = ta; ec.tb = tb; ec.t0 = nullptr; ec.t1 = nullptr;
+    const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
+
+    tile_loop(ring, p.g.n_tiles, false, [&](const TileStage& st, long long tile) {
+        const long long gene = tile * p.g.genes + gl;
+        GeneView gv;
+        gv.y = st.y + (size_t)gl * m;
+        gv.aux = st.aux ? st.aux + (size_t)gl * m : nullptr;
+        gv.gs = st.gs ? st.gs[gl] : 0.0;
+        gv.setup(m, lane, p.g.lpg, gl);
+        double beta[C], ainv[Tri<C>::N];
+        CoefOut co;
+        coef_gene<C>(ec, gv, x, c, beta, ainv, co);
+        if (lane != 0 || gene >= p.g.n) return;
+        double* cf = p.coef + gene * c;
+        double* cv = p.covar + gene * c * c;
+        if (!co.ok) {
+            for (int i = 0; i < c; ++i) cf[i] = NAN;
+            for (int i = 0; i < c * c; ++i) cv[i] = NAN;
+            p.dfpost[gene] = NAN;
+            return;
+        }
+        // posterior scale (Mvt.conditional, distributions.py:210-214): (df + d2) / (df + p2)
+        const double s2 = p.is_t ? (p.v + co.d2) / (p.v + co.p2) : 1.0;
+        p.dfpost[gene] = p.is_t ? p.v + co.p2 : NAN;
+        // back to the user's basis: coef = Rinv beta,  V = Rinv Ainv Rinv' s2
+        double tmp[C * C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            if (i < c) {
+                double a = 0.0;
+#pragma unroll
+                for (int t = 0; t < C; ++t) if (t >= i && t < c) a += rinv[i * c + t] * beta[t];
+                cf[i] = a;
+            }
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                double a = 0.0;
+#pragma unroll
+                for (int t = 0; t < C; ++t)
+                    if (t >= i && t < c && i < c && j < c) a += rinv[i * c + t] * ainv[t > j ? FN_TRI(t, j) : FN_TRI(j, t)];
+                tmp[i * C + j] = a;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                if (i < c && j < c) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int t = 0; t < C; ++t) if (t >= j && t < c) a += tmp[i * C + t] * rinv[j * c + t];
+                    cv[i * c + j] = a * s2;
+                }
+            }
+    });
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b contrasts + test: thread per gene over the compact per-gene results
+// ------------------------------------------------------------------------------------------
+struct TestParams {
+    long long n;
+    int c, kc, is_t;
+    const double* coef; const double* covar; const double* dfpost;
+    const double* contrasts;     // c x kc (device)
+    double* contrasted;          // n x kc
+    double* ccov;                // n x kc x kc or nullptr
+    double* pval;                // n
+};
+
+__global__ void test_kernel(const TestParams p) {
+    __shared__ double cm[FN_MAXC * FN_MAXC];
+    for (int i = threadIdx.x; i < p.c * p.kc; i += blockDim.x) cm[i] = p.contrasts[i];
+    __syncthreads();
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n) return;
+    const double* V = p.covar + g * p.c * p.c;
+    double* out = p.contrasted + g * p.kc;
+    if (V[0] != V[0]) {                      // coef_dists[row] is None (fitnoise.py:385)
+        for (int a = 0; a < p.kc; ++a) out[a] = NAN;
+        if (p.ccov) for (int a = 0; a < p.kc * p.kc; ++a) p.ccov[g * p.kc * p.kc + a] = NAN;
+        p.pval[g] = NAN;
+        return;
+    }
+    double pv;
+    test_gene(p.c, p.kc, p.coef + g * p.c, V, p.dfpost[g], p.is_t, cm, out,
+              p.ccov ? p.ccov + g * p.kc * p.kc : nullptr, pv);
+    p.pval[g] = pv;
+}
+
+// ------------------------------------------------------------------------------------------
+// get_weights: 1/sigma2 per observation (fitnoise.py:399-404); inf/NaN exactly where the reference's are
+// ------------------------------------------------------------------------------------------
+struct WeightParams {
+    long long n; int m;
+    const double* y; const double* aux; const double* gs;
+    int kind, tail_own, v3;
+    double theta0;
+    const double* ta; const double* tb;
+    double* out;
+};
+
+__global__ void weights_kernel(const WeightParams p) {
+    const long long total = p.n * p.m;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long g = i / p.m;
+        const int j = (int)(i - g * p.m);
+        double w;
+        if (p.kind == KIND_PATSEQ) {
+            const double rc = p.aux[i];
+            const double gsv = p.gs ? p.gs[g] : 0.0;
+            const double y = p.y[i];
+            const double U = p.v3 ? rc * gsv : rc;
+            const double T = p.tail_own ? (finite_d(y) ? y * y : 0.0) : gsv;
+            w = 1.0 / (p.ta[j] * U + p.tb[j] * T);
+        } else {
+            const double wp = p.aux ? p.aux[i] : 1.0;
+            w = (p.kind == KIND_SCALE_PS) ? wp * p.ta[j] : wp / p.theta0;
+        }
+        p.out[i] = w;
+    }
+}
+
+}  // namespace fn

@@ -1,0 +1,539 @@
+"""Public model layer: ``Dataset``, ``Model`` and the noise-model classes, with the reference's
+names, arguments, result attributes and text formats (reference: fitnoise/fitnoise.py:164-892).
+
+What differs from the reference is where the work happens.  The reference loops over genes in
+Python (fitnoise.py:23-35, 132-133, 259-267, 308-341, 384-389); here each of those loops is one
+CUDA kernel over all genes (csrc/fn_kernels.cuh) reached through the C ABI
+(include/fitnoise_b200.h), and only the hyper-parameter vector theta lives on the host, inside the
+same scipy L-BFGS-B driver loop the reference's Theano path uses (fitnoise.py:143-158).
+
+Noise-model plug-ins keep the reference's interface (``_unpack``, ``_describe_noise``,
+``_get_dist``, composition by mix-in) and add ONE declaration, ``_family(m)``: the variance-family
+descriptor the kernels consume.  A subclass that overrides ``_get_dist`` without a ``_family`` is
+rejected -- there is no per-gene Python/CPU fallback.
+"""
+import sys
+
+import numpy as np
+import scipy.optimize
+
+from . import _native, p_adjust
+from .distributions import Mvnormal, Mvt
+from .env import Withable, as_matrix, as_vector
+from .session import Session
+
+INDEPENDENT_DF = 1e-10      # reference fitnoise.py:577
+
+
+class Dataset(object):
+    """Expression matrix (genes x samples, NaN = missing) plus per-observation context:
+    ``"weights"`` (precision weights) or ``"counts"`` (PAT-Seq read counts).  fitnoise.py:164-167"""
+
+    def __init__(self, y, context={}):
+        self.y = as_matrix(y)
+        self.context = context
+
+
+def as_dataset(dataset):
+    return dataset if isinstance(dataset, Dataset) else Dataset(dataset)
+
+
+class _LazyDists(object):
+    """Sequence of per-gene distribution objects built on indexing.  The reference materialises n
+    Python objects holding m x m / c x c matrices (fitnoise.py:252-255, 301, 380); at 1M genes
+    that is tens of GB, so rows are constructed on demand from the result arrays."""
+    __fn_lazy_sequence__ = True
+
+    def __init__(self, n, make):
+        self._n, self._make = int(n), make
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._make(i)
+
+    def __iter__(self):
+        return (self._make(i) for i in range(self._n))
+
+
+def _optimize(value_grad, initial, bounds, verbose):
+    """The reference's driver loop (fitnoise.py:143-158): L-BFGS-B with analytic gradient and
+    ftol = gtol = 1e-12, restarted from the optimum until it moves by less than 1e-6."""
+    initial = np.asarray(initial, dtype="float64")
+    while True:
+        result = scipy.optimize.minimize(
+            value_grad, initial, method="L-BFGS-B", jac=True, bounds=bounds,
+            options=dict(ftol=1e-12, gtol=1e-12))
+        if verbose:
+            print(result)
+        if np.all(np.abs(result.x - initial) < 1e-6):
+            return result
+        initial = result.x
+
+
+class Model(Withable):
+    """
+        score = mean residual log2 density
+    """
+
+    def __init__(self):
+        pass
+
+    def __repr__(self):
+        if hasattr(self, "param"):
+            result = self._describe_noise(self.param)
+            result += "noise combined p-value = %f\n" % self.noise_combined_p_value
+            result += "noise fit score = %f bits\n" % self.score
+        else:
+            result = "<%s>\n" % self.__class__.__name__
+        return result
+
+    @property
+    def description(self):
+        return repr(self)
+
+    # ---- plug-in interface ---------------------------------------------------------------
+    def _unpack(self, packed):
+        return Withable()
+
+    def _describe_noise(self, param):
+        return ""
+
+    def _model_cost(self, param):
+        return 0.0
+
+    def _family(self, m):
+        """Variance-family descriptor (``_native.Family``) for m samples."""
+        raise NotImplementedError(
+            "%s does not declare a variance family (_family); fitnoise_b200 evaluates noise models "
+            "only through its CUDA kernels and has no per-gene Python fallback" % type(self).__name__)
+
+    _aux_key = None                     # which Dataset.context entry is the second n x m array
+
+    def _initial_bounds(self, m, row_variance_mean):
+        return [], []
+
+    def _aux_row(self, i):
+        """Row i of the reference's ``_aux`` matrix (only for the lazy ``noise_dists`` views)."""
+        return np.zeros(0)
+
+    def _get_dist(self, param, aux):
+        raise NotImplementedError
+
+    # ---- configuration: upload + device-side preparation -----------------------------------
+    def _configured(self):
+        y = self.data.y
+        n, m = y.shape
+        family = self._family(m)
+        aux = None
+        if self._aux_key is not None:
+            if self._aux_key in self.data.context:
+                aux = as_matrix(self.data.context[self._aux_key])
+                assert aux.shape == y.shape
+            elif self._aux_key == "counts":
+                raise KeyError("counts")
+        session = Session(y, aux, family,
+                          self.controls if np.any(self.controls) else None,
+                          self.noise_design, self.control_design,
+                          engine_factory=getattr(self, "_engine_factory", None))
+        if family.kind == _native.KIND_PATSEQ:
+            assert session.n_bad_counts == 0, \
+                "Tail lengths with zero count should be NaN (or NA in R)"
+        initial, bounds = self._initial_bounds(m, session.row_variance_mean)
+        return self._with(_session=session, _initial=list(initial), _bounds=list(bounds))
+
+    # ---- fit_noise (fitnoise.py:207-291) ---------------------------------------------------
+    def fit_noise(self, data, design=None, control_design=None, controls=None, use_theano=True,
+                  verbose=False, force_param=None):
+        """``use_theano`` is accepted for signature compatibility and ignored."""
+        data = as_dataset(data)
+        design = as_matrix(design)                       # design is effectively required (:212)
+
+        n, m = data.y.shape
+        if control_design is None:
+            control_design = np.ones((m, 1))
+        if controls is None:
+            controls = [False] * n
+        control_design = as_matrix(control_design)
+        controls = as_vector(controls, "bool")
+        assert design.shape[0] == m and control_design.shape[0] == m and len(controls) == n
+
+        result = self._with(data=data, noise_design=design, control_design=control_design,
+                            controls=controls)
+        result = result._configured()
+        session = result._session
+        initial = as_vector(result._initial)
+
+        evaluations = [0]
+
+        def value_grad(theta):
+            evaluations[0] += 1
+            if verbose:
+                print(theta, end=" ")
+                sys.stdout.flush()
+            value, grad, used, bad = session.nll_grad(theta)
+            if bad:
+                value = np.inf
+            if verbose:
+                print("->", value)
+            return value, grad
+
+        if force_param is not None:                                   # :38-41
+            force_param = as_vector(force_param)
+            assert len(force_param) == len(initial)
+            fit = Withable()._with(x=force_param, fun=0.0)
+        elif len(initial) == 0:                                       # :52-53
+            fit = Withable()._with(x=np.zeros(0), fun=0.0)
+        else:
+            assert np.all(np.isfinite(initial)), "initial hyper-parameters are not finite"
+            fit = _optimize(value_grad, initial, result._bounds, verbose)
+        param = result._unpack(as_vector(fit.x))
+        if verbose:
+            print("Model cost:", result._model_cost(param))
+
+        noise_p_values, averages = session.noise_stats(fit.x)         # :257-267
+
+        good_p = noise_p_values[np.isfinite(noise_p_values)]          # :270-274
+        if not len(good_p):
+            noise_combined_p_value = 0.0
+        else:
+            noise_combined_p_value = min(1, np.minimum.reduce(good_p) * len(good_p))
+
+        n_controls = int(np.sum(controls))                            # :276-277
+        n_residuals = (n - n_controls) * (m - design.shape[1]) + n_controls * (m - control_design.shape[1])
+        df = n_residuals - len(initial)
+
+        theta = as_vector(fit.x)
+        fitted = result._with(
+            optimization_result=fit,
+            param=param,
+            df=df,
+            deviance=fit.fun * 2.0,
+            score=fit.fun / (np.log(2.0) * df),
+            noise_p_values=noise_p_values,
+            noise_combined_p_value=noise_combined_p_value,
+            averages=averages,
+            _theta=theta,
+            _evaluations=evaluations[0],
+        )
+        fitted.noise_dists = _LazyDists(n, lambda i: fitted._get_dist(param, fitted._aux_row(i)))
+        return fitted
+
+    # ---- fit_coef (fitnoise.py:294-347) ----------------------------------------------------
+    def fit_coef(self, design=None):
+        if design is None:
+            design = self.noise_design
+        design = as_matrix(design)
+        token = object()
+        coef, covar, dfpost = self._session.coef(self._theta, design, token)
+        is_t = self._family(self.data.y.shape[1]).dist != _native.DIST_NORMAL
+
+        def make(i):
+            if covar[i, 0, 0] != covar[i, 0, 0]:
+                return None
+            if is_t:
+                return Mvt(coef[i], covar[i], dfpost[i])
+            return Mvnormal(coef[i], covar[i])
+
+        return self._with(design=design, coef=coef, coef_dists=_LazyDists(len(coef), make),
+                          _coef_covar=covar, _coef_df=dfpost, _coef_token=token)
+
+    # ---- fit (fitnoise.py:350-365) ---------------------------------------------------------
+    def fit(self, data, design=None, noise_design=None, control_design=None, controls=None,
+            use_theano=True, verbose=False, force_param=None):
+        return (self.fit_noise(data=data,
+                               design=noise_design if noise_design is not None else design,
+                               control_design=control_design, controls=controls,
+                               use_theano=use_theano, verbose=verbose, force_param=force_param)
+                .fit_coef(design))
+
+    # ---- test (fitnoise.py:368-396) --------------------------------------------------------
+    def test(self, coef=None, contrasts=None):
+        if coef is not None:
+            assert contrasts is None
+            contrasts = np.zeros((self.design.shape[1], len(coef)))
+            for i in range(len(coef)):
+                contrasts[coef[i], i] = 1.0
+        assert contrasts is not None, "No coefficients or contrasts to test given."
+        contrasts = as_matrix(contrasts)
+        assert contrasts.shape[0] == self.design.shape[1]
+
+        session = self._session
+        if session.coef_token is not self._coef_token:        # another fit_coef ran on this session since
+            session.coef(self._theta, self.design, self._coef_token)
+        contrasted, p_values = session.test(contrasts)
+        q_values = session.bh(p_values)
+
+        covar, mean, dfpost = self._coef_covar, self.coef, self._coef_df
+        is_t = self._family(self.data.y.shape[1]).dist != _native.DIST_NORMAL
+
+        def make(i):
+            if covar[i, 0, 0] != covar[i, 0, 0]:
+                return None
+            base = Mvt(mean[i], covar[i], dfpost[i]) if is_t else Mvnormal(mean[i], covar[i])
+            return base.transformed(contrasts.T)
+
+        return self._with(contrasts=contrasted, contrast_dists=_LazyDists(len(mean), make),
+                          p_values=p_values, q_values=q_values)
+
+    # ---- get_weights (fitnoise.py:399-404) -------------------------------------------------
+    def get_weights(self):
+        """ Weight matrix for limma. """
+        return self._session.weights(self._theta)
+
+
+# ------------------------------------------------------------------------------------------------
+# mix-ins and noise models
+# ------------------------------------------------------------------------------------------------
+
+class Model_t_mixin(Model):
+    """ This mix-in converts an Mv_normal model to an Mvt model (fitnoise.py:407-436). """
+
+    def _unpack(self, pack):
+        df = pack[0]
+        return super(Model_t_mixin, self)._unpack(pack[1:])._with(df=df)
+
+    def _describe_noise(self, param):
+        return "df = %f\n" % param.df + super(Model_t_mixin, self)._describe_noise(param)
+
+    def _get_dist(self, param, aux):
+        inner = super(Model_t_mixin, self)._get_dist(param, aux)
+        assert type(inner) is Mvnormal
+        return Mvt(inner.mean, inner.covar, param.df)
+
+    def _family(self, m):
+        family = super(Model_t_mixin, self)._family(m)
+        assert family.dist == _native.DIST_NORMAL
+        family.dist = _native.DIST_T
+        return family
+
+    def _initial_bounds(self, m, row_variance_mean):
+        initial, bounds = super(Model_t_mixin, self)._initial_bounds(m, row_variance_mean)
+        return [5.0] + list(initial), [(1e-3, 100.0)] + list(bounds)
+
+
+class _Weighted(Model):
+    """aux = 1/weights or ones (fitnoise.py:539-544); the device gets the precision weights."""
+    _aux_key = "weights"
+
+    def _aux_row(self, i):
+        if "weights" in self.data.context:
+            with np.errstate(divide="ignore"):
+                return 1.0 / as_matrix(self.data.context["weights"])[i]
+        return np.ones(self.data.y.shape[1])
+
+
+class Model_normal(_Weighted):
+    def _unpack(self, pack):
+        return Withable()._with(variance=pack[0])
+
+    def _describe_noise(self, param):
+        return "sd = %f\n" % np.sqrt(param.variance)
+
+    def _get_dist(self, param, aux):
+        return Mvnormal(np.zeros(len(aux)), np.diag(param.variance * aux))
+
+    def _family(self, m):
+        return _native.Family(_native.KIND_SCALE1, 1, 0, 0, 0, _native.DIST_NORMAL, 0.0)
+
+    def _initial_bounds(self, m, var):
+        # reference: var = mean(var(y, axis=1)) (fitnoise.py:546); NaN-aware here (divergences)
+        return [var], [(var * 1e-6, var * 1e6)]
+
+
+class Model_t(Model_t_mixin, Model_normal):
+    pass
+
+
+class Model_independent(_Weighted):
+    def _describe_noise(self, param):
+        return ""
+
+    def _get_dist(self, param, aux):
+        return Mvt(np.zeros(len(aux)), np.diag(aux), INDEPENDENT_DF)
+
+    def _family(self, m):
+        return _native.Family(_native.KIND_SCALE1, 0, 0, 0, 0, _native.DIST_T_FIXED, INDEPENDENT_DF)
+
+
+class Model_normal_per_sample(_Weighted):
+    def _unpack(self, pack):
+        return Withable()._with(variances=pack)
+
+    def _describe_noise(self, param):
+        return "sd = [%s]\n" % ", ".join("%f" % item for item in np.sqrt(param.variances))
+
+    def _get_dist(self, param, aux):
+        return Mvnormal(np.zeros(len(aux)), np.diag(param.variances * aux))
+
+    def _family(self, m):
+        return _native.Family(_native.KIND_SCALE_PS, m, 0, 0, 0, _native.DIST_NORMAL, 0.0)
+
+    def _initial_bounds(self, m, var):
+        return [var] * m, [(var * 1e-6, var * 1e6)] * m
+
+
+class Model_t_per_sample(Model_t_mixin, Model_normal_per_sample):
+    pass
+
+
+class _Patseq(Model):
+    """ Differential tail length detection in PAT-Seq: variance = read term / reads + sample term.
+        The device gets the raw counts and derives 1/max(count,1) and the average tail itself. """
+    _aux_key = "counts"
+    _per_sample_a = False
+    _per_sample_b = False
+    _tail_own = False
+    _v3 = False
+    _start = (100.0, 0.01)
+
+    def _family(self, m):
+        return _native.Family(_native.KIND_PATSEQ, m if self._per_sample_a else 1,
+                              m if self._per_sample_b else 1, int(self._tail_own), int(self._v3),
+                              _native.DIST_NORMAL, 0.0)
+
+    def _initial_bounds(self, m, var):
+        na = m if self._per_sample_a else 1
+        nb = m if self._per_sample_b else 1
+        initial = [self._start[0]] * na + [self._start[1]] * nb
+        return initial, [(1e-12, 1e12)] * (na + nb)
+
+    def _unpack(self, pack):
+        na = len(pack) // 2 if self._per_sample_a else 1
+        read = pack[:na] if self._per_sample_a else pack[0]
+        sample = pack[na:] if self._per_sample_b else pack[na]
+        return Withable()._with(read_variance=read, sample_variance=sample)
+
+    def _aux_row(self, i):
+        y = self.data.y[i]
+        counts = as_matrix(self.data.context["counts"])[i]
+        y0 = np.where(np.isfinite(y), y, 0.0)
+        if self._tail_own:
+            return np.concatenate([np.maximum(counts, 1.0), y0])                 # :648-652
+        num = (y0 * counts).sum()
+        if not self._v3:
+            num = max(1.0, num)                                                   # :747 vs :853
+        avg = num / max(1.0, counts.sum())
+        return np.concatenate([np.maximum(counts, 1.0), [avg]])                   # :749-750
+
+    def _get_dist(self, param, aux):
+        if self._tail_own:
+            m = len(aux) // 2
+            count, tail = aux[:m], aux[m:]
+        else:
+            m = len(aux) - 1
+            count, tail = aux[:m], aux[m]
+        if self._v3:
+            s2 = (param.read_variance / count + param.sample_variance) * (tail * tail)
+        else:
+            s2 = param.read_variance / count + param.sample_variance * (tail * tail)
+        return Mvnormal(np.zeros(m), np.diag(s2 * np.ones(m)))
+
+
+class Model_normal_patseq_v1(_Patseq):
+    _tail_own = True
+    _start = (250.0, 0.01)
+
+    def _describe_noise(self, param):
+        return "variance = %f^2 / reads + (%f * tail)^2\n" % (
+            np.sqrt(param.read_variance), np.sqrt(param.sample_variance))
+
+
+class Model_t_v1_patseq(Model_t_mixin, Model_normal_patseq_v1):
+    pass
+
+
+Model_t_patseq_v1 = Model_t_v1_patseq      # the reference's class name is transposed (fitnoise.py:680)
+
+
+class Model_normal_patseq_v1_per_sample(_Patseq):
+    _tail_own = True
+    _per_sample_b = True
+
+    def _describe_noise(self, param):
+        return "variance = %f^2 / reads + (sample_cv * tail)^2\nsample_cv = [%s]\n" % (
+            np.sqrt(param.read_variance),
+            ", ".join("%f" % item for item in np.sqrt(param.sample_variance)))
+
+
+class Model_t_patseq_v1_per_sample(Model_t_mixin, Model_normal_patseq_v1_per_sample):
+    pass
+
+
+class Model_normal_patseq_v2(_Patseq):
+    def _describe_noise(self, param):
+        return "variance = %f^2 / reads + (%f * avgtail)^2\n" % (
+            np.sqrt(param.read_variance), np.sqrt(param.sample_variance))
+
+
+class Model_t_patseq_v2(Model_t_mixin, Model_normal_patseq_v2):
+    pass
+
+
+class Model_normal_patseq_v2_per_sample(_Patseq):
+    _per_sample_a = True
+    _per_sample_b = True
+
+    def _describe_noise(self, param):
+        return ("variance = read_sd^2 / reads + (sample_cv * avgtail)^2\n"
+                "read_sd = [%s]\n"
+                "sample_cv = [%s]\n" % (
+                    ", ".join("%f" % item for item in np.sqrt(param.read_variance)),
+                    ", ".join("%f" % item for item in np.sqrt(param.sample_variance))))
+
+
+class Model_t_patseq_v2_per_sample(Model_t_mixin, Model_normal_patseq_v2_per_sample):
+    pass
+
+
+class Model_normal_patseq_v3(_Patseq):
+    _v3 = True
+    _start = (1.0, 0.01)
+
+    def _describe_noise(self, param):
+        return "variance = (%f^2 / reads + %f^2) * tail^2\n" % (
+            np.sqrt(param.read_variance), np.sqrt(param.sample_variance))
+
+
+class Model_t_patseq_v3(Model_t_mixin, Model_normal_patseq_v3):
+    pass
+
+
+# Bless PATSEQ v2 (fitnoise.py:889-892)
+Model_normal_patseq = Model_normal_patseq_v2
+Model_t_patseq = Model_t_patseq_v2
+Model_normal_patseq_per_sample = Model_normal_patseq_v2_per_sample
+Model_t_patseq_per_sample = Model_t_patseq_v2_per_sample
+
+# Names used by BASELINE.json / the legacy R package (backyard/old_fitnoise.R:599-614)
+Model_t_standard = Model_t
+Model_t_independent = Model_independent
+
+
+class _Unsupported(Model):
+    _why = ""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError(self._why)
+
+
+class Model_normal_factors(_Unsupported):
+    _why = ("the *_factors noise models (full covariance with unknown batch-effect factors, "
+            "fitnoise.py:439-518) are not built yet: they need a rank-n update of the per-gene "
+            "system that the diagonal-variance kernels do not provide (SURVEY 8f, rank 1)")
+
+
+class Model_t_factors(Model_normal_factors):
+    pass
+
+
+class Model_independent_factors(Model_normal_factors):
+    pass

@@ -1,0 +1,105 @@
+"""One fit's device-resident state: this rank's shard of the genes on its GPU plus the collectives
+that make the per-rank results global.  The numerical work is all in the CUDA library
+(``_native.Engine``); this module only shards, reduces and gathers."""
+import os
+
+import numpy as np
+
+from . import _native, parallel
+
+
+class Session(object):
+    """``local`` is this rank's evaluator.  By default a ``_native.Engine`` (CUDA; raises without
+    a GPU).  Tests of the sharding logic on a CPU-only box pass their own stand-in through
+    ``engine_factory`` -- the product never does."""
+
+    def __init__(self, y, aux, family, controls, design_noise, design_ctrl, engine_factory=None):
+        self.rank, self.world = parallel.world()
+        y = np.asarray(y, dtype=np.float64)
+        self.n, self.m = y.shape
+        self.bounds = parallel.shard_bounds(self.n, self.world)
+        self.lo, self.hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        self.family = family
+        self.P = family.theta_length()
+        self._cuda_reduce = None
+        if engine_factory is None:
+            engine_factory = self._cuda_engine
+        self.local = engine_factory()
+        sl = slice(self.lo, self.hi)
+        info = self.local.upload(
+            y[sl], None if aux is None else np.asarray(aux, dtype=np.float64)[sl], family,
+            None if controls is None else np.asarray(controls)[sl], design_noise, design_ctrl)
+        # global preparation summary
+        if self.world == 1:
+            self.n_eligible, self.n_bad_counts = int(info.n_eligible), int(info.n_bad_counts)
+            self.row_variance_mean = float(info.row_variance_mean)
+        else:
+            rows = float(info.n_variance_rows)
+            sums = parallel.allreduce_sum([float(info.n_eligible), float(info.n_bad_counts),
+                                           self._nan0(info.row_variance_mean * rows), rows])
+            self.n_eligible, self.n_bad_counts = int(sums[0]), int(sums[1])
+            self.row_variance_mean = sums[2] / sums[3] if sums[3] > 0 else np.nan
+        self.coef_token = None
+
+    @staticmethod
+    def _nan0(x):
+        return 0.0 if x != x else float(x)
+
+    def _cuda_engine(self):
+        stream = None
+        if self.world > 1:
+            # share torch's current stream so that the all-reduce is ordered after the kernel
+            import torch
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank)))
+            stream = torch.cuda.current_stream().cuda_stream
+            self._cuda_reduce = torch.zeros(self.P + 3, dtype=torch.float64, device="cuda")
+            return _native.Engine(torch.cuda.current_device(), stream)
+        return _native.Engine(int(os.environ.get("LOCAL_RANK", "0")))
+
+    def close(self):
+        if self.local is not None and hasattr(self.local, "close"):
+            self.local.close()
+        self.local = None
+
+    # ---- likelihood -----------------------------------------------------------------------
+    def nll_grad(self, theta):
+        """Global (all ranks) value and gradient of the REML objective at theta."""
+        theta = np.asarray(theta, dtype=np.float64)
+        if self._cuda_reduce is not None:
+            buf = self._cuda_reduce
+            self.local.nll_grad_dev(theta, buf.data_ptr())
+            parallel.allreduce_sum_tensor(buf)
+            out = buf.cpu().numpy()
+            return float(out[0]), out[1:1 + self.P].copy(), int(out[self.P + 1]), int(out[self.P + 2])
+        value, grad, used, bad = self.local.nll_grad(theta)
+        if self.world == 1:
+            return value, grad, used, bad
+        out = parallel.allreduce_sum(np.concatenate([[value], grad, [used, bad]]))
+        return float(out[0]), out[1:1 + self.P], int(out[self.P + 1]), int(out[self.P + 2])
+
+    def per_gene(self, theta):
+        score, d2, p = self.local.per_gene(theta)
+        return (parallel.allgather_rows(score, self.n), parallel.allgather_rows(d2, self.n),
+                parallel.allgather_rows(p, self.n))
+
+    def noise_stats(self, theta):
+        noise_p, averages = self.local.noise_stats(theta)
+        return parallel.allgather_rows(noise_p, self.n), parallel.allgather_rows(averages, self.n)
+
+    # ---- coefficients, tests --------------------------------------------------------------
+    def coef(self, theta, design, token):
+        coef, covar, dfpost = self.local.coef(theta, design)
+        self.coef_token = token
+        return (parallel.allgather_rows(coef, self.n), parallel.allgather_rows(covar, self.n),
+                parallel.allgather_rows(dfpost, self.n))
+
+    def test(self, contrasts):
+        contrasted, _, p = self.local.test(contrasts)
+        return parallel.allgather_rows(contrasted, self.n), parallel.allgather_rows(p, self.n)
+
+    def bh(self, p):
+        # every rank holds the full p vector after the gather and adjusts it on its own GPU
+        return self.local.bh(p)
+
+    def weights(self, theta):
+        return parallel.allgather_rows(self.local.weights(theta), self.n)

@@ -1,0 +1,130 @@
+/* fitnoise_b200 -- C ABI of the B200-native Fitnoise hot path.
+ *
+ * The reference (pfh/fitnoise 2.2) is pure Python and has NO foreign-function interface; this is
+ * the boundary a maintainer would bind from Python with ctypes (see INTEGRATION.md for the stub)
+ * to replace the per-gene Python loops of the reference.  Each entry point names the reference
+ * code it stands in for (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C, no torch/numpy types; every array argument is a HOST pointer unless its name ends
+ *     in _dev; matrices are row-major float64 (numpy C order, env.py:57-65); missing = NaN.
+ *   - every function returns 0 on success, a negative code on failure; fn_last_error() gives the
+ *     message for the calling thread.  There is no CPU fallback: without a CUDA device fn_create
+ *     fails.
+ *   - a handle owns one GPU's shard of the genes (device memory, stream, pinned result buffer).
+ *     One host thread per handle.  Multi-GPU: one handle per process/GPU, genes sharded by the
+ *     caller; the per-evaluation sums of all shards are added by the caller (NCCL allreduce of
+ *     1+P doubles over fn_nll_grad_dev output, see fitnoise_b200/parallel.py).
+ */
+#ifndef FITNOISE_B200_H
+#define FITNOISE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fn_handle fn_handle;
+
+/* Variance family of a noise model: sigma2_j = theta_a(j) * U_j + theta_b(j) * T_j.
+ * Stands in for the plug-in interface Model._get_dist / _unpack (fitnoise.py:198-205, 410-428,
+ * 522-535, 573-578, 599-614, 659-678, 705-724, 757-776, 807-832, 863-882).
+ * theta is ordered as the reference's _initial: [df if dist==FN_DIST_T], theta_a block, theta_b block. */
+enum { FN_KIND_SCALE1 = 0, FN_KIND_SCALE_PS = 1, FN_KIND_PATSEQ = 2 };
+enum { FN_DIST_NORMAL = 0, FN_DIST_T = 1, FN_DIST_T_FIXED = 2 };
+typedef struct fn_family {
+    int32_t kind;       /* FN_KIND_*: SCALE1 sigma2 = theta/w (Model_normal/_t/_independent);
+                           SCALE_PS sigma2_j = theta_j/w_j (Model_*_per_sample);
+                           PATSEQ sigma2_j = theta_a/count_j + theta_b*tail^2 (Model_*_patseq_*) */
+    int32_t na, nb;     /* entries in the theta_a / theta_b blocks: 0, 1 or m */
+    int32_t tail_own;   /* PATSEQ v1: tail = the gene's own y_j; else the count-weighted average tail */
+    int32_t v3;         /* PATSEQ v3: sigma2_j = (theta_a/count_j + theta_b) * avgtail^2 */
+    int32_t dist;       /* FN_DIST_* : Mvnormal, Mvt with df = theta[0], Mvt with fixed df */
+    double fixed_df;    /* Model_independent: 1e-10 (fitnoise.py:577) */
+} fn_family;
+
+/* summary of fn_upload's preparation pass */
+typedef struct fn_prep_info {
+    double row_variance_mean;   /* mean over genes of var(y_row) over finite entries (fitnoise.py:546,627) */
+    double cst_sum;             /* theta-independent part of sum_g ln det S_g over eligible genes */
+    int64_t n_eligible;         /* genes entering the REML sum: k > c and full-rank retained design (fitnoise.py:28) */
+    int64_t n_bad_counts;       /* PATSEQ: observations with count == 0 but finite y (fitnoise.py:647) */
+    int64_t n_variance_rows;    /* genes with >= 1 finite value (the rows averaged in row_variance_mean) */
+} fn_prep_info;
+
+const char* fn_last_error(void);
+int fn_device_count(void);
+const char* fn_version(void);
+
+/* One handle per GPU.  `stream` is a cudaStream_t to launch on (e.g. torch's current stream) or
+ * NULL for a stream owned by the handle. */
+int fn_create(int device, void* stream, fn_handle** out);
+int fn_destroy(fn_handle* h);
+int fn_synchronize(fn_handle* h);
+
+/* Upload a shard of genes and prepare it: replaces Model.fit_noise's set-up and the per-gene prep
+ * loop of _fit_noise (fitnoise.py:211-233, 23-35) and Model_*._configured (fitnoise.py:538-552 ...
+ * 843-861).  y: n x m.  aux: n x m precision WEIGHTS (SCALE kinds; w = 0 or NaN drops the
+ * observation) or read COUNTS (PATSEQ), or NULL.  controls: n bytes (non-zero = control gene,
+ * fitted with design_ctrl) or NULL.  Designs are m x c row-major, c <= 8, full column rank. */
+int fn_upload(fn_handle* h, int64_t n, int32_t m, const double* y, const double* aux,
+              const fn_family* family, const uint8_t* controls,
+              int32_t c_noise, const double* design_noise,
+              int32_t c_ctrl, const double* design_ctrl, fn_prep_info* info);
+/* Same with y/aux/controls already in device memory (n_pad = n rounded up to 1024 rows is NOT
+ * required of the caller; the data is copied device-to-device into the handle's padded buffers). */
+int fn_upload_dev(fn_handle* h, int64_t n, int32_t m, const double* y_dev, const double* aux_dev,
+                  const fn_family* family, const uint8_t* controls_dev,
+                  int32_t c_noise, const double* design_noise,
+                  int32_t c_ctrl, const double* design_ctrl, fn_prep_info* info);
+
+/* One evaluation of the REML objective: sum over this handle's genes of score_row (fitnoise.py:
+ * 44-50) and its gradient (theano.gradient.grad, fitnoise.py:93; accumulation :98-106,125-136).
+ * theta has P = (dist==T) + na + nb entries.  value includes the theta-independent terms.
+ * n_used / n_bad (may be NULL): genes that contributed / that produced a non-finite term. */
+int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double* value, double* grad,
+                int64_t* n_used, int64_t* n_bad);
+/* Asynchronous form for multi-GPU: leaves [value, grad[0..P-1], n_used, n_bad] (P+3 doubles) in
+ * device memory at out_dev on the handle's stream, for the caller to allreduce.  No host sync. */
+int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, double* out_dev);
+
+/* Per-gene score_row, Mahalanobis distance d2 and residual df p at theta (NaN / 0 for genes the
+ * REML prep skips).  Parity/diagnostic entry; any output pointer may be NULL. */
+int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double* score, double* d2, int32_t* p);
+
+/* Tail of Model.fit_noise (fitnoise.py:257-267): noise p-values and row averages. */
+int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, double* noise_p, double* averages);
+
+/* Model.fit_coef (fitnoise.py:294-347): GLS coefficients and their posterior at the fitted theta.
+ * design: m x c.  coef: n x c; covar: n x c x c; dfpost: n (NaN for Mvnormal).  Rows the reference
+ * leaves as None are NaN.  Results also stay on the device for fn_test. Outputs may be NULL. */
+int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, const double* design,
+            double* coef, double* covar, double* dfpost);
+
+/* Model.test (fitnoise.py:368-396): contrasts (c x kc) of the last fn_coef, their p-values.
+ * contrasted: n x kc; ccov: n x kc x kc or NULL; pval: n. */
+int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov, double* pval);
+
+/* p_adjust.fdr (p_adjust.py:3-21): Benjamini-Hochberg q-values; NaN p counts as 1.0. */
+int fn_bh(fn_handle* h, int64_t n, const double* p, double* q);
+/* device-resident form: p_dev, q_dev are device pointers of n doubles */
+int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev);
+
+/* Model.get_weights (fitnoise.py:399-404): 1/sigma2, n x m. */
+int fn_weights(fn_handle* h, const double* theta, int32_t P, double* weights);
+
+/* Tuning knobs for experiments (0 = automatic): lanes per gene, threads per CTA, pipeline stages,
+ * CTAs per SM. */
+int fn_set_tuning(fn_handle* h, int32_t lpg, int32_t threads, int32_t stages, int32_t ctas_per_sm);
+/* How many kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t fn_launch_count(fn_handle* h);
+/* Average device time (ms) of the last fn_nll_grad kernel, measured with CUDA events on the
+ * handle's stream when timing is enabled with fn_set_timing(h, 1). */
+int fn_set_timing(fn_handle* h, int32_t on);
+double fn_last_kernel_ms(fn_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -317,8 +317,13 @@ def tail_p_value(S, z, df):
 # _fit_noise (fitnoise.py:17-160)
 # --------------------------------------------------------------------------------------
 
-def prepare_rows(cfg, designs, theta_for_good=None):
-    """fitnoise.py:23-35.  Returns {row: (retain, tQ2, z2)} for rows with k > c."""
+def prepare_rows(cfg, designs, theta_for_good=None, skip_rank_deficient=False):
+    """fitnoise.py:23-35.  Returns {row: (retain, tQ2, z2)} for rows with k > c.
+
+    ``skip_rank_deficient=True`` is the product's documented divergence: rows whose
+    retained sub-design has k > c but less than full column rank are left out of the REML sum,
+    because the reference's term for them depends on LAPACK's Householder details, not on the
+    mathematics.  Default False = the reference's behaviour."""
     y = cfg.y
     n, m = y.shape
     theta = cfg.initial if theta_for_good is None else theta_for_good
@@ -329,6 +334,8 @@ def prepare_rows(cfg, designs, theta_for_good=None):
         retain = np.arange(m, dtype="int32")[keep]
         c = design.shape[1]
         if len(retain) <= c:
+            continue
+        if skip_rank_deficient and np.linalg.matrix_rank(design[retain]) < c:
             continue
         Q, R = np.linalg.qr(design[retain], mode="complete")     # env.py:200
         tQ2 = Q[:, c:].T
@@ -406,7 +413,8 @@ def optimize_tight(value_grad, initial, bounds, max_rounds=50):
     return res
 
 
-def fit_noise(cfg, design, control_design=None, controls=None, force_param=None, tight=True):
+def fit_noise(cfg, design, control_design=None, controls=None, force_param=None, tight=True,
+              skip_rank_deficient=False):
     """Model.fit_noise, fitnoise.py:207-291.  Returns a dict of the result attributes."""
     y = cfg.y
     n, m = y.shape
@@ -418,7 +426,7 @@ def fit_noise(cfg, design, control_design=None, controls=None, force_param=None,
     control_design = np.asarray(control_design, dtype="float64")
     controls = np.asarray(controls, dtype=bool)
     designs = [control_design if flag else design for flag in controls]      # :233
-    prepared = prepare_rows(cfg, designs)
+    prepared = prepare_rows(cfg, designs, skip_rank_deficient=skip_rank_deficient)
 
     if force_param is not None:                                               # :38-41
         x = np.asarray(force_param, dtype="float64")
@@ -539,11 +547,12 @@ def get_weights(cfg, theta):
 
 def fit_and_test(model, y, design, context=None, coef_idx=None, contrasts=None,
                  control_design=None, controls=None, noise_design=None, force_param=None,
-                 nan_aware=False, tight=True):
+                 nan_aware=False, tight=True, skip_rank_deficient=False):
     """Model.fit + .test end to end (fitnoise.py:350-365, 368-396) as one dict."""
     cfg = Configured(model, y, context, nan_aware=nan_aware)
     nd = design if noise_design is None else noise_design
-    out = fit_noise(cfg, nd, control_design, controls, force_param, tight=tight)
+    out = fit_noise(cfg, nd, control_design, controls, force_param, tight=tight,
+                    skip_rank_deficient=skip_rank_deficient)
     coef, covar, dfs = fit_coef(cfg, out["x"], design)
     out.update(coef=coef, coef_covar=covar, coef_df=dfs)
     if coef_idx is not None or contrasts is not None:

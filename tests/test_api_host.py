@@ -1,0 +1,127 @@
+"""Host-side logic of the package on a CPU-only box: the optimiser driver loop, result attributes,
+lazy views, error behaviour.  The evaluator is the host build of the kernel mathematics
+(tests/hostcheck); the CUDA path runs the same tests in test_gpu_parity.py."""
+import json
+
+import numpy as np
+import pytest
+
+import fitnoise_b200 as fitnoise
+import hostcheck
+from conftest import assert_close, golden_context, golden_fit_kwargs, load_golden
+from helpers import fit_golden
+from oracle import fitnoise_oracle as oracle
+
+OPT_CASES = ["t_twogroup", "t_patseq_v2", "t_controls_opt"]
+
+
+@pytest.mark.parametrize("name", OPT_CASES)
+def test_fitted_hyperparameters_match_oracle(name):
+    """north_star: fitted hyper-parameters within 1e-6 relative at the same optimiser tolerance.
+    The oracle runs the reference's driver loop (fitnoise.py:143-158) on its own score_row."""
+    g = load_golden(name)
+    fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator)
+    ref = oracle.fit_and_test(str(g["model"]), g["y"], g["design"], golden_context(g),
+                              coef_idx=[int(i) for i in g["test_coef"]], nan_aware=True,
+                              skip_rank_deficient=True,
+                              **golden_fit_kwargs(g))
+    x, rx = fitted.optimization_result.x, ref["x"]
+    free = ~(np.isclose(rx, 100.0) | np.isclose(rx, 1e-3))          # df may sit on its bound
+    assert_close(x[free], rx[free], 1e-6, what="theta")
+    assert_close(x[~free], rx[~free], 1e-9, what="theta at bound")
+    assert_close(fitted.optimization_result.fun, ref["fun"], 1e-10, what="fun")
+    assert_close(fitted.deviance, ref["deviance"], 1e-10, what="deviance")
+    assert_close(fitted.score, ref["score"], 1e-10, what="score")
+    # and it is no worse than what the reference's own (loose, numeric-gradient) optimiser found
+    # (comparable only when no row is excluded as rank deficient)
+    from helpers import rank_deficient_rows
+    if not rank_deficient_rows(g):
+        assert fitted.optimization_result.fun <= float(g["ref_opt_fun"]) + 1e-9 * abs(float(g["ref_opt_fun"]))
+    # statistics downstream of theta, against the oracle at ITS theta
+    assert_close(tested.p_values, ref["p_values"], 1e-5, what="p at fitted theta")
+
+
+def test_result_attributes_and_lazy_views():
+    g = load_golden("t_twogroup")
+    fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
+    for name in ("data", "noise_design", "control_design", "controls", "optimization_result", "param",
+                 "df", "deviance", "score", "noise_dists", "noise_p_values", "noise_combined_p_value",
+                 "averages", "design", "coef", "coef_dists", "description"):
+        assert hasattr(fitted, name), name
+    for name in ("contrasts", "contrast_dists", "p_values", "q_values"):
+        assert hasattr(tested, name), name
+    assert fitted.param.df == g["theta"][0] and fitted.param.variance == g["theta"][1]
+    n, m = g["y"].shape
+    assert len(fitted.noise_dists) == n and len(fitted.coef_dists) == n
+    nd = fitted.noise_dists[3]
+    assert isinstance(nd, fitnoise.Mvt) and nd.covar.shape == (m, m) and nd.df == g["theta"][0]
+    cd = fitted.coef_dists[5]
+    assert_close(cd.mean, g["ref_coef"][5], 1e-9)
+    assert_close(cd.covar, g["ref_coef_covar"][5], 1e-9)
+    td = tested.contrast_dists[5]
+    assert_close(td.covar, g["ref_contrast_covar"][5], 1e-9)
+    assert_close(td.p_value(np.zeros(1)), g["ref_p_values"][5], 1e-8)
+    # the R bridge reads attributes through as_jsonic + json.dumps (R/fitnoise.R:75-88)
+    for name in ("coef", "averages", "noise_p_values", "score", "df", "description"):
+        json.dumps(fitnoise.as_jsonic(getattr(fitted, name)))
+    json.dumps(fitnoise.as_jsonic(fitted.param))
+    # fits are immutable records: test() returned a new object
+    assert not hasattr(fitted, "p_values")
+
+
+def test_status_rows_nan_pattern():
+    """Which outputs are NaN for k>c / k==c / k<c / all-missing rows."""
+    g = load_golden("independent_status")
+    fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
+    assert np.array_equal(np.isnan(fitted.coef), np.isnan(g["ref_coef"]))
+    assert np.array_equal(np.isnan(tested.p_values), np.isnan(g["ref_p_values"]))
+    assert fitted.coef_dists[4] is None and fitted.coef_dists[0] is not None
+    assert tested.q_values[4] == 1.0 or np.isnan(g["ref_p_values"][4])
+
+
+def test_errors():
+    y = np.random.default_rng(0).normal(size=(10, 6))
+    design = np.array([[1.0, 0]] * 3 + [[1.0, 1]] * 3)
+    m = fitnoise.Model_t()._with(_engine_factory=hostcheck.HostEvaluator)
+    with pytest.raises(AssertionError):
+        m.fit(y)                                                  # design is required (fitnoise.py:212)
+    with pytest.raises(AssertionError):
+        m.fit(y, design).test()                                   # "No coefficients or contrasts"
+    with pytest.raises(AssertionError):
+        m.fit(y, design, force_param=[1.0])                       # wrong length
+    with pytest.raises(KeyError):
+        fitnoise.Model_t_patseq()._with(_engine_factory=hostcheck.HostEvaluator).fit(y, design)
+    counts = np.ones((10, 6))
+    counts[0, 0] = 0
+    with pytest.raises(AssertionError):                           # zero count with finite tail
+        fitnoise.Model_t_patseq()._with(_engine_factory=hostcheck.HostEvaluator).fit(
+            fitnoise.Dataset(y, {"counts": counts}), design)
+    with pytest.raises(NotImplementedError):
+        fitnoise.Model_t_factors(1)
+    with pytest.raises(NotImplementedError):
+        fitnoise.transform(y)
+
+    class Custom(fitnoise.Model):
+        def _get_dist(self, param, aux):
+            return None
+    with pytest.raises(NotImplementedError):                      # no variance family -> no fallback
+        Custom()._with(_engine_factory=hostcheck.HostEvaluator).fit(y, design)
+
+
+def test_no_cpu_fallback_without_gpu(has_cuda):
+    if has_cuda:
+        pytest.skip("box has a GPU")
+    from fitnoise_b200 import _native
+    y = np.random.default_rng(0).normal(size=(10, 6))
+    design = np.array([[1.0, 0]] * 3 + [[1.0, 1]] * 3)
+    with pytest.raises(_native.NativeError):
+        fitnoise.Model_t().fit(y, design)
+    with pytest.raises(_native.NativeError):
+        fitnoise.fdr([0.1, 0.2])
+
+
+def test_nan_aware_initial_variance():
+    g = load_golden("t_nan_quirk")
+    fitted, _ = fit_golden(g, engine_factory=hostcheck.HostEvaluator)
+    assert np.isfinite(fitted.optimization_result.x).all()
+    assert np.isfinite(fitted.noise_p_values).sum() >= 11

@@ -1,0 +1,71 @@
+"""The kernels' arithmetic (csrc/fn_gene.cuh, fn_special.cuh), compiled for the host by
+tests/hostcheck, against scipy / mpmath and against the golden fixtures.  CPU only -- the same
+checks run against the real CUDA kernels in test_gpu_parity.py."""
+import numpy as np
+import pytest
+import scipy.special
+import scipy.stats
+
+import hostcheck
+from conftest import golden_names, load_golden
+from helpers import check_against_golden, fit_golden
+
+NAMES = [n for n in golden_names() if n != "t_nan_quirk"]
+
+
+def test_digamma():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10 ** rng.uniform(-4, 3, 20000), [5e-11, 0.5, 1, 2, 47.00000000005]])
+    got, ref = hostcheck.digamma(x), scipy.special.digamma(x)
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-12
+
+
+def test_f_sf_against_scipy():
+    rng = np.random.default_rng(1)
+    N = 100000
+    dfn = rng.integers(1, 9, N).astype(float)
+    dfd = np.where(rng.random(N) < 0.3, 1e-10 + rng.integers(0, 100, N),
+                   10 ** rng.uniform(-3, 2.5, N) + rng.integers(0, 100, N))
+    f = 10 ** rng.uniform(-8, 6, N)
+    got, ref = hostcheck.f_sf(f, dfn, dfd), scipy.stats.f.sf(f, dfn, dfd)
+    ok = ref > 1e-300
+    assert np.max(np.abs(got - ref)[ok] / ref[ok]) < 1e-10          # north_star: p-values within 1e-8
+    assert hostcheck.f_sf([0.0], [2.0], [5.0])[0] == 1.0
+    assert hostcheck.f_sf([np.inf], [2.0], [5.0])[0] == 0.0
+    assert np.isnan(hostcheck.f_sf([np.nan], [2.0], [5.0])[0])
+
+
+def test_f_sf_deep_tail_against_mpmath():
+    mpmath = pytest.importorskip("mpmath")
+    mpmath.mp.dps = 60
+    for f, dfn, dfd in [(1e4, 1, 12.5), (3e5, 2, 99.0), (250.0, 1, 94.0000000001), (1e9, 3, 7.25),
+                        (5000.0, 1, 47.3), (80.0, 6, 1e-10 + 94)]:
+        x = mpmath.mpf(dfd) / (mpmath.mpf(dfd) + mpmath.mpf(dfn) * mpmath.mpf(f))
+        ref = mpmath.betainc(mpmath.mpf(dfd) / 2, mpmath.mpf(dfn) / 2, 0, x, regularized=True)
+        got = hostcheck.f_sf([f], [dfn], [dfd])[0]
+        assert abs(got - float(ref)) / float(ref) < 1e-10, (f, dfn, dfd, got, float(ref))
+
+
+def test_chi2_sf_against_scipy():
+    rng = np.random.default_rng(2)
+    N = 100000
+    q = 10 ** rng.uniform(-6, 3.2, N)
+    k = rng.integers(1, 200, N).astype(float)
+    got, ref = hostcheck.chi2_sf(q, k), scipy.stats.chi2.sf(q, k)
+    ok = ref > 1e-300
+    assert np.max(np.abs(got - ref)[ok] / ref[ok]) < 1e-10
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_kernel_math_matches_reference_golden(name):
+    """Model.fit(force_param) + test through the package's host logic and the host build of the
+    kernel mathematics, against the reference's outputs."""
+    g = load_golden(name)
+    fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
+    check_against_golden(g, fitted, tested)
+    score, d2, p = fitted._session.per_gene(g["theta"])
+    ref = g["ref_score_rows"].copy()
+    from helpers import rank_deficient_rows
+    ref[rank_deficient_rows(g)] = np.nan
+    from conftest import assert_close
+    assert_close(score, ref, 1e-9, what="per-gene score_row")
