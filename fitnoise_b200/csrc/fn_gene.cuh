@@ -120,16 +120,42 @@ struct GeneView {
     int lane, lpg;      // this lane's index within the gene, lanes per gene
     int cnt;            // number of samples this lane owns
     int skew;           // rotation of the lane-local sample order (shared-memory bank spreading)
-    FN_HD void setup(int m_, int lane_, int lpg_, int skew_) {
+    int blocked;        // 1: rotate within blocks of 16 samples (m % 16 == 0, lpg <= 16)
+    // `gene_local` = index of the gene within the tile.  Rows of a tile are m doubles apart, so
+    // without a rotation the lanes of a warp that work on different genes would hit the same
+    // shared-memory banks whenever m is a multiple of 16 (8-byte bank pairs).
+    FN_HD void setup(int m_, int lane_, int lpg_, int gene_local) {
         m = m_; lane = lane_; lpg = lpg_;
         cnt = (m - lane + lpg - 1) / lpg;
         if (cnt < 0) cnt = 0;
-        skew = cnt > 0 ? skew_ % cnt : 0;
+        blocked = ((m & 15) == 0 && lpg <= 16) ? 1 : 0;
+        if (blocked) skew = (((m / lpg) & 1) == 0) ? gene_local : 0;
+        else skew = cnt > 0 ? gene_local % cnt : 0;
     }
-    FN_HD int sample(int i) const {        // i in [0, cnt)
-        int ii = i + skew;
-        if (ii >= cnt) ii -= cnt;
-        return lane + lpg * ii;
+    // Visit this lane's samples, each exactly once, in a bank-friendly order; `on` = false visits
+    // nothing.  The order only changes the association of the floating-point sums.
+    //  blocked: step (r, t) -> sample 16 t + ((lane + lpg (skew + r)) mod 16), r < 16/lpg, t < m/16.
+    //           Same trip count for every thread (no divergence); at any step the 16 threads of a
+    //           half-warp read 16 distinct bank pairs, and a warp touches only 16 distinct rows of X.
+    //  else:    lane-local indices skew..cnt-1 then 0..skew-1 as two plain strided loops.
+    template <class F>
+    FN_HD void for_each(bool on, F f) const {
+        if (!on) return;
+        if (blocked) {
+            const int steps = 16 / lpg, nblk = m >> 4;
+            for (int r = 0; r < steps; ++r) {
+                const int jr = (lane + lpg * (skew + r)) & 15;
+#pragma unroll 2
+                for (int t = 0; t < nblk; ++t) f(jr + 16 * t);
+            }
+            return;
+        }
+        int j = lane + lpg * skew;
+#pragma unroll 4
+        for (int ii = skew; ii < cnt; ++ii, j += lpg) f(j);
+        j = lane;
+#pragma unroll 4
+        for (int ii = 0; ii < skew; ++ii, j += lpg) f(j);
     }
 };
 
@@ -284,6 +310,9 @@ struct EvalConst {
     int is_t;             // multivariate t (else normal)
     double v;             // df
     double theta0;        // SCALE1 shared variance (1 when na == 0)
+    double itheta0, ltheta0;   // 1/theta0, ln theta0
+    double iv;            // 1/v
+    FN_HD void finish_setup() { itheta0 = 1.0 / theta0; ltheta0 = log(theta0); iv = is_t ? 1.0 / v : 0.0; }
     const double* ta;
     const double* tb;
     const double* t0;     // t0[p]: -(log-density terms that depend on (v,p) only)
@@ -357,8 +386,7 @@ FN_HD void prepare_gene(const Family& fam, const GeneView& gv, const double* X, 
     double ysum = 0.0, csum = 0.0, ycsum = 0.0, ysel = 0.0;
     int nfin = 0, bad = 0;
     const bool patseq = fam.kind == KIND_PATSEQ;
-    for (int i = 0; i < gv.cnt; ++i) {
-        const int j = gv.sample(i);
+    gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
         const bool yok = finite_d(y);
         double aux = gv.aux ? gv.aux[j] : 1.0;
@@ -380,7 +408,7 @@ FN_HD void prepare_gene(const Family& fam, const GeneView& gv, const double* X, 
             ysel += y;
             ++g.k;
         }
-    }
+    });
     g.reduce(gv.lpg);
     lw.lane_reduce(gv.lpg);
     ysum = lane_sum(ysum, gv.lpg);
@@ -391,10 +419,10 @@ FN_HD void prepare_gene(const Family& fam, const GeneView& gv, const double* X, 
     // second sweep: squared deviations of the finite y about their mean (numpy.var, fitnoise.py:546)
     const double mean = nfin > 0 ? ysum / nfin : 0.0;
     double ss = 0.0;
-    for (int i = 0; i < gv.cnt; ++i) {
-        const double y = gv.y[gv.sample(i)];
+    gv.for_each(true, [&](int j) {
+        const double y = gv.y[j];
         if (finite_d(y)) { const double d = y - mean; ss += d * d; }
-    }
+    });
     ss = lane_sum(ss, gv.lpg);
 
     g.pad(c_real);
@@ -433,10 +461,10 @@ FN_HD void eval_zero(EvalOut& o) { o.value = 0.0; o.dv = 0.0; o.ga = 0.0; o.gb =
 FN_HD double finish_density(const EvalConst& ec, int p, double logdet, double d2, double& dv, double& kappa) {
     if (ec.is_t) {
         const double v = ec.v;
-        const double l1p = log1p(d2 / v);
+        const double l1p = log1p(d2 * ec.iv);
         const double hp = 0.5 * (v + p);
         kappa = hp / (v + d2);
-        dv = ec.t1[p] + 0.5 * l1p - kappa * d2 / v;
+        dv = ec.t1[p] + 0.5 * l1p - kappa * d2 * ec.iv;
         return ec.t0[p] + 0.5 * logdet + hp * l1p;
     }
     kappa = 0.5;
@@ -447,37 +475,72 @@ FN_HD double finish_density(const EvalConst& ec, int p, double logdet, double d2
 // KIND_SCALE1: sigma2_j = theta0 / w_prec_j.  All sums are taken at theta = 1 and rescaled;
 // the gradient with respect to theta0 is closed-form (no second sweep):
 //   d(-ll)/d theta0 = (p/2 - kappa d2) / theta0.
+//
+// X must have ORTHONORMAL columns over the m samples (Design::build whitens every design).  For a
+// gene with no weights and no missing value the normal matrix is then the identity, so the sweep
+// needs only b = X'y and y'y (C+1 FMAs per sample): beta = b, det A = 1, d2 = y'y - |b|^2.  A
+// missing value makes y'y non-finite, which is how incomplete rows are found at no per-sample
+// cost; they (and every weighted gene) take the masked sweep that also builds A.
 template <int C>
 FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
                        bool eligible, double cst, EvalOut& out) {
-    Normal<C> nm;
-    nm.init();
-    const int cnt = eligible ? gv.cnt : 0;
-    for (int i = 0; i < cnt; ++i) {
-        const int j = gv.sample(i);
-        const double y = gv.y[j];
-        const SampleVar sv = sample_var(ec, gv, j, y);
-        double x[C];
-        load_x<C>(X, j, x);
-        nm.add(sv.w, sv.valid ? y : 0.0, x);
-        nm.k += sv.valid ? 1 : 0;
+    const bool has_aux = gv.aux != nullptr;
+    double b[C], beta[C];
+    double yy = 0.0, det = 1.0;
+    int k = gv.m;
+    bool ok = true, complete = false;
+#pragma unroll
+    for (int i = 0; i < C; ++i) b[i] = 0.0;
+    if (!has_aux) {
+        gv.for_each(eligible, [&](int j) {
+            const double y = gv.y[j];
+            double x[C];
+            load_x<C>(X, j, x);
+#pragma unroll
+            for (int i = 0; i < C; ++i) b[i] += x[i] * y;
+            yy += y * y;
+        });
+        if (gv.lpg > 1) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) b[i] = lane_sum(b[i], gv.lpg);
+            yy = lane_sum(yy, gv.lpg);
+        }
+        complete = finite_d(yy);
+#pragma unroll
+        for (int i = 0; i < C; ++i) beta[i] = b[i];
     }
-    nm.reduce(gv.lpg);
-    nm.pad(c_real);
-    double det;
-    const bool ok = chol<C>(nm.a, det, 0.0);
-    double beta[C];
+    if (has_aux || warp_any(eligible && !complete)) {
+        Normal<C> nm;
+        nm.init();
+        gv.for_each(eligible && !complete, [&](int j) {
+            const double y = gv.y[j];
+            const SampleVar sv = sample_var(ec, gv, j, y);
+            double x[C];
+            load_x<C>(X, j, x);
+            nm.add(sv.w, sv.valid ? y : 0.0, x);
+            nm.k += sv.valid ? 1 : 0;
+        });
+        nm.reduce(gv.lpg);
+        nm.pad(c_real);
+        double det2;
+        const bool ok2 = chol<C>(nm.a, det2, 0.0);
+        double beta2[C];
 #pragma unroll
-    for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
-    chol_solve<C>(nm.a, beta);
-    double d2 = nm.yy;
+        for (int i = 0; i < C; ++i) beta2[i] = nm.b[i];
+        chol_solve<C>(nm.a, beta2);
+        if (!complete) {
 #pragma unroll
-    for (int i = 0; i < C; ++i) d2 -= nm.b[i] * beta[i];
+            for (int i = 0; i < C; ++i) { b[i] = nm.b[i]; beta[i] = beta2[i]; }
+            yy = nm.yy; k = nm.k; det = det2; ok = ok2;
+        }
+    }
+    double d2 = yy;
+#pragma unroll
+    for (int i = 0; i < C; ++i) d2 -= b[i] * beta[i];
     // y'Wy - b'beta cancels badly when the fit explains almost everything: redo from residuals
-    if (warp_any(eligible && d2 < 1e-4 * nm.yy)) {
+    if (warp_any(eligible && d2 < 1e-4 * yy)) {
         double s = 0.0;
-        for (int i = 0; i < cnt; ++i) {
-            const int j = gv.sample(i);
+        gv.for_each(eligible && d2 < 1e-4 * yy, [&](int j) {
             const double y = gv.y[j];
             const SampleVar sv = sample_var(ec, gv, j, y);
             double x[C];
@@ -486,22 +549,21 @@ FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X,
 #pragma unroll
             for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
             s += sv.w * r * r;
-        }
+        });
         s = lane_sum(s, gv.lpg);
-        if (d2 < 1e-4 * nm.yy) d2 = s;
+        if (d2 < 1e-4 * yy) d2 = s;
     }
     eval_zero(out);
     if (!eligible) return;
-    const int p = nm.k - c_real;
+    const int p = k - c_real;
     if (!ok || p <= 0) { out.value = NAN; out.used = 1; return; }
     if (d2 < 0.0) d2 = 0.0;
-    const double it = 1.0 / ec.theta0;
-    d2 *= it;
-    const double logdet = p * log(ec.theta0) + log(det) + cst;
+    d2 *= ec.itheta0;
+    const double logdet = p * ec.ltheta0 + (complete ? 0.0 : log(det)) + cst;
     double dv, kappa;
     out.value = finish_density(ec, p, logdet, d2, dv, kappa);
     out.dv = dv;
-    out.ga = (0.5 * p - kappa * d2) * it;
+    out.ga = (0.5 * p - kappa * d2) * ec.itheta0;
     out.d2 = d2; out.p = p; out.used = 1;
 }
 
@@ -517,9 +579,7 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
     nm.init();
     LogProd lp; lp.init();
     double slt = 0.0;                  // SCALE_PS: sum_ret ln theta_j
-    const int cnt = eligible ? gv.cnt : 0;
-    for (int i = 0; i < cnt; ++i) {
-        const int j = gv.sample(i);
+    gv.for_each(eligible, [&](int j) {
         const double y = gv.y[j];
         const SampleVar sv = sample_var(ec, gv, j, y);
         double x[C];
@@ -529,7 +589,7 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
             ++nm.k;
             if (KIND == KIND_PATSEQ) lp.mul(sv.s2); else slt += ec.tb[j];
         }
-    }
+    });
     nm.reduce(gv.lpg);
     if (KIND == KIND_PATSEQ) lp.lane_reduce(gv.lpg); else slt = lane_sum(slt, gv.lpg);
     nm.pad(c_real);
@@ -542,8 +602,7 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
 
     // sweep 2: d2 from residuals
     double d2 = 0.0;
-    for (int i = 0; i < cnt; ++i) {
-        const int j = gv.sample(i);
+    gv.for_each(eligible, [&](int j) {
         const double y = gv.y[j];
         const SampleVar sv = sample_var(ec, gv, j, y);
         double x[C];
@@ -552,7 +611,7 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
 #pragma unroll
         for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
         d2 += sv.w * r * r;
-    }
+    });
     d2 = lane_sum(d2, gv.lpg);
 
     eval_zero(out);
@@ -571,8 +630,7 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
 
     // sweep 3: gradient.  e~_j = sigma2_j * d(-ll)/d sigma2_j = 1/2 (1 - w_j h_j) - kappa w_j r_j^2
     double ga = 0.0, gb = 0.0;
-    for (int i = 0; i < gv.cnt; ++i) {
-        const int j = gv.sample(i);
+    gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
         double ca = 0.0, cb = 0.0;
         if (good) {
@@ -595,7 +653,7 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
         }
         if (inplace_a) gv.y[j] = ca; else ga += ca;
         if (KIND == KIND_PATSEQ) { if (inplace_b) gv.aux[j] = cb; else gb += cb; }
-    }
+    });
     if (!inplace_a) out.ga = lane_sum(ga, gv.lpg);
     if (KIND == KIND_PATSEQ && !inplace_b) out.gb = lane_sum(gb, gv.lpg);
     // every lane of the gene now holds the same totals: only lane 0 may add them to the CTA sums
@@ -618,15 +676,14 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
                      double* beta, double* ainv, CoefOut& out) {
     Normal<C> nm, gm;
     nm.init(); gm.init();
-    for (int i = 0; i < gv.cnt; ++i) {
-        const int j = gv.sample(i);
+    gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
         const SampleVar sv = sample_var(ec, gv, j, y);
         double x[C];
         load_x<C>(X, j, x);
         nm.add(sv.w, sv.valid ? y : 0.0, x);
         if (sv.valid) { gm.add(1.0, 0.0, x); ++nm.k; }
-    }
+    });
     nm.reduce(gv.lpg);
     gm.reduce(gv.lpg);
     nm.pad(c_real); gm.pad(c_real);
@@ -638,8 +695,7 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
     chol_solve<C>(nm.a, beta);
     chol_inverse<C>(nm.a, ainv);
     double d2 = 0.0;
-    for (int i = 0; i < gv.cnt; ++i) {
-        const int j = gv.sample(i);
+    gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
         const SampleVar sv = sample_var(ec, gv, j, y);
         double x[C];
@@ -648,7 +704,7 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
 #pragma unroll
         for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
         d2 += sv.w * r * r;
-    }
+    });
     d2 = lane_sum(d2, gv.lpg);
     if (ec.kind == KIND_SCALE1) {             // sums were taken at theta = 1
         d2 /= ec.theta0;

@@ -80,10 +80,9 @@ struct GeomParams {
     int width;               // template width C the designs are padded to
 };
 
-// dynamic shared memory: [tables: doubles][stage buffers (128-aligned)]
-__device__ __forceinline__ unsigned char* align128(unsigned char* p) {
-    return (unsigned char*)(((uintptr_t)p + 127) & ~(uintptr_t)127);
-}
+// dynamic shared memory of the per-gene kernels: [stage buffers][tables].  The stage area comes
+// first so that every pointer into it is plain arithmetic on the __shared__ symbol (the compiler
+// then emits LDS, not generic loads).
 
 // ------------------------------------------------------------------------------------------
 // K1 prepare
@@ -105,30 +104,31 @@ struct PrepParams {
 
 template <int C>
 __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[FN_MAX_STAGES];
     __shared__ double red_out[PREP_NACC];
     __shared__ double red_scratch[32 * PREP_NACC];
-    double* xn = (double*)smem_raw;
-    double* xc = xn + p.g.m * C;
-    unsigned char* stage_base = align128((unsigned char*)(xc + p.g.m * C));
-    for (int i = threadIdx.x; i < p.g.m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
-    TileRing ring;
-    ring.init(bars, stage_base, p.g.stages, p.src);
+    const int m = p.g.m;
+    const TileLayout L = tile_layout(p.src);
+    tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);
+    double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
+    double* xc = xn + m * C;
+    for (int i = threadIdx.x; i < m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
+    __syncthreads();
 
     const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
+    GeneView gv;
+    gv.setup(m, lane, p.g.lpg, gl);
+    gv.gs = 0.0;
     double acc[PREP_NACC];
 #pragma unroll
     for (int i = 0; i < PREP_NACC; ++i) acc[i] = 0.0;
 
-    tile_loop(ring, p.g.n_tiles, false, [&](const TileStage& st, long long tile) {
+    tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, false, [&](unsigned char* st, long long tile) {
         const long long gene = tile * p.g.genes + gl;
-        GeneView gv;
-        gv.y = st.y + (size_t)gl * p.g.m;
-        gv.aux = st.aux ? st.aux + (size_t)gl * p.g.m : nullptr;
-        gv.gs = 0.0;
-        gv.setup(p.g.m, lane, p.g.lpg, gl);
-        const bool control = (st.status[gl] & 2) != 0;
+        gv.y = (double*)st + (size_t)gl * m;
+        gv.aux = p.src.aux ? (double*)(st + L.aux_off) + (size_t)gl * m : nullptr;
+        const bool control = (st[L.status_off + gl] & 2) != 0;
         PrepOut po;
         prepare_gene<C>(p.fam, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, po);
         if (lane == 0 && gene < p.g.n) {
@@ -170,12 +170,15 @@ struct EvalParams {
 
 template <int C, int KIND>
 __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[FN_MAX_STAGES];
     __shared__ double red_scratch[32 * ACC_FIXED];
     const int m = p.g.m;
-    // tables: xn, xc (m*C each), ta, tb (m each), t0, t1 (m+1 each), vals (ACC_FIXED + 2m), colscratch (2*blockDim)
-    double* xn = (double*)smem_raw;
+    const TileLayout L = tile_layout(p.src);
+    tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);     // first tiles are in flight
+    // tables behind the stage area: xn, xc (m*C each), ta, tb (m each), t0, t1 (m+1 each),
+    // vals (ACC_FIXED + 2m), colscr (2*blockDim when a theta block is per-sample)
+    double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
     double* xc = xn + m * C;
     double* ta = xc + m * C;
     double* tb = ta + m;
@@ -184,7 +187,6 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
     double* vals = t1 + (m + 1);
     double* colscr = vals + (ACC_FIXED + 2 * m);
     const bool inplace = p.inplace_a || p.inplace_b;
-    unsigned char* stage_base = align128((unsigned char*)(colscr + (inplace ? 2 * blockDim.x : 0)));
 
     for (int i = threadIdx.x; i < m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
@@ -192,14 +194,15 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
         tb[i] = p.tb ? p.tb[i] : 0.0;
     }
     for (int i = threadIdx.x; i <= m; i += blockDim.x) density_tables(p.is_t, p.v, i, t0[i], t1[i]);
-    TileRing ring;
-    ring.init(bars, stage_base, p.g.stages, p.src);      // contains the __syncthreads() for the tables
+    __syncthreads();
 
     EvalConst ec;
     ec.kind = KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
-    ec.ta = ta; ec.tb = tb; ec.t0 = t0; ec.t1 = t1;
+    ec.ta = ta; ec.tb = tb; ec.t0 = t0; ec.t1 = t1; ec.finish_setup();
 
     const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
+    GeneView gv;
+    gv.setup(m, lane, p.g.lpg, gl);
     double acc[ACC_FIXED];
 #pragma unroll
     for (int i = 0; i < ACC_FIXED; ++i) acc[i] = 0.0;
@@ -208,17 +211,17 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
     const int col = inplace ? threadIdx.x % m : 0, sub = inplace ? threadIdx.x / m : 0;
     double col_a = 0.0, col_b = 0.0;
 
-    tile_loop(ring, p.g.n_tiles, inplace, [&](const TileStage& st, long long tile) {
+    tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, inplace, [&](unsigned char* st, long long tile) {
         const long long gene = tile * p.g.genes + gl;
-        GeneView gv;
-        gv.y = st.y + (size_t)gl * m;
-        gv.aux = st.aux ? st.aux + (size_t)gl * m : nullptr;
-        gv.gs = st.gs ? st.gs[gl] : 0.0;
-        gv.setup(m, lane, p.g.lpg, gl);
-        const uint8_t status = st.status[gl];
+        double* ys = (double*)st;
+        double* auxs = (double*)(st + L.aux_off);
+        gv.y = ys + (size_t)gl * m;
+        gv.aux = p.src.aux ? auxs + (size_t)gl * m : nullptr;
+        gv.gs = p.src.gs ? ((const double*)(st + L.gs_off))[gl] : 0.0;
+        const uint8_t status = st[L.status_off + gl];
         const bool control = (status & 2) != 0;
         const bool eligible = (status & 1) != 0;
-        const double cst = st.cst ? st.cst[gl] : 0.0;
+        const double cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
         EvalOut eo;
         if (KIND == KIND_SCALE1)
             eval_scale1<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst, eo);
@@ -244,8 +247,8 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
             __syncthreads();
             if (sub < nsub) {
                 for (int g = sub; g < p.g.genes; g += nsub) {
-                    if (p.inplace_a) col_a += st.y[(size_t)g * m + col];
-                    if (p.inplace_b) col_b += st.aux[(size_t)g * m + col];
+                    if (p.inplace_a) col_a += ys[(size_t)g * m + col];
+                    if (p.inplace_b) col_b += auxs[(size_t)g * m + col];
                 }
             }
         }
@@ -296,32 +299,32 @@ struct CoefParams {
 
 template <int C>
 __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[FN_MAX_STAGES];
     __shared__ double rinv[FN_MAXC * FN_MAXC];
     const int m = p.g.m, c = p.c;
-    double* x = (double*)smem_raw;
+    const TileLayout L = tile_layout(p.src);
+    tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);
+    double* x = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
     double* ta = x + m * C;
     double* tb = ta + m;
-    unsigned char* stage_base = align128((unsigned char*)(tb + m));
     for (int i = threadIdx.x; i < m * C; i += blockDim.x) x[i] = p.x[i];
     for (int i = threadIdx.x; i < m; i += blockDim.x) { ta[i] = p.ta ? p.ta[i] : 0.0; tb[i] = p.tb ? p.tb[i] : 0.0; }
     for (int i = threadIdx.x; i < c * c; i += blockDim.x) rinv[i] = p.rinv[i];
-    TileRing ring;
-    ring.init(bars, stage_base, p.g.stages, p.src);
+    __syncthreads();
 
     EvalConst ec;
     ec.kind = p.kind; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
-    ec.ta = ta; ec.tb = tb; ec.t0 = nullptr; ec.t1 = nullptr;
+    ec.ta = ta; ec.tb = tb; ec.t0 = nullptr; ec.t1 = nullptr; ec.finish_setup();
     const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
+    GeneView gv;
+    gv.setup(m, lane, p.g.lpg, gl);
 
-    tile_loop(ring, p.g.n_tiles, false, [&](const TileStage& st, long long tile) {
+    tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, false, [&](unsigned char* st, long long tile) {
         const long long gene = tile * p.g.genes + gl;
-        GeneView gv;
-        gv.y = st.y + (size_t)gl * m;
-        gv.aux = st.aux ? st.aux + (size_t)gl * m : nullptr;
-        gv.gs = st.gs ? st.gs[gl] : 0.0;
-        gv.setup(m, lane, p.g.lpg, gl);
+        gv.y = (double*)st + (size_t)gl * m;
+        gv.aux = p.src.aux ? (double*)(st + L.aux_off) + (size_t)gl * m : nullptr;
+        gv.gs = p.src.gs ? ((const double*)(st + L.gs_off))[gl] : 0.0;
         double beta[C], ainv[Tri<C>::N];
         CoefOut co;
         coef_gene<C>(ec, gv, x, c, beta, ainv, co);

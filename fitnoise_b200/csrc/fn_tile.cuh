@@ -62,12 +62,10 @@ struct TileSrc {
     int genes;               // G, a multiple of 16
 };
 
-struct TileStage {
-    double* y;
-    double* aux;
-    double* gs;
-    double* cst;
-    uint8_t* status;
+// Byte offsets of the arrays inside one stage buffer (uniform over the CTA, computed once).
+struct TileLayout {
+    uint32_t aux_off, gs_off, cst_off, status_off;   // y is at offset 0
+    uint32_t stage_bytes, tx_bytes, row_bytes;
 };
 
 __host__ __device__ inline size_t tile_stage_bytes(int genes, int m, bool aux, bool gs, bool cst) {
@@ -75,76 +73,67 @@ __host__ __device__ inline size_t tile_stage_bytes(int genes, int m, bool aux, b
     return (b + 127) & ~(size_t)127;
 }
 
-struct TileRing {
-    uint64_t* bars;          // FN_MAX_STAGES mbarriers (shared)
-    unsigned char* base;     // stage buffers (shared, 128-byte aligned)
-    size_t stage_bytes;
-    int stages;
-    TileSrc src;
-    uint32_t tx_bytes;
+__device__ __forceinline__ TileLayout tile_layout(const TileSrc& s) {
+    TileLayout L;
+    L.row_bytes = (uint32_t)s.genes * s.m * 8;
+    uint32_t at = L.row_bytes;
+    L.aux_off = at; if (s.aux) at += L.row_bytes;
+    L.gs_off = at; if (s.gs) at += (uint32_t)s.genes * 8;
+    L.cst_off = at; if (s.cst) at += (uint32_t)s.genes * 8;
+    L.status_off = at; at += (uint32_t)s.genes;
+    L.tx_bytes = at;
+    L.stage_bytes = (at + 127u) & ~127u;
+    return L;
+}
 
-    __device__ void init(uint64_t* bars_, unsigned char* base_, int stages_, const TileSrc& s) {
-        bars = bars_; base = base_; stages = stages_; src = s;
-        stage_bytes = tile_stage_bytes(s.genes, s.m, s.aux != nullptr, s.gs != nullptr, s.cst != nullptr);
-        const uint32_t row = (uint32_t)s.genes * s.m * 8;
-        tx_bytes = row * (s.aux ? 2 : 1) + (uint32_t)s.genes * 8 * ((s.gs ? 1 : 0) + (s.cst ? 1 : 0)) + s.genes;
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-    }
-    __device__ TileStage stage(int slot) const {
-        TileStage t;
-        unsigned char* p = base + (size_t)slot * stage_bytes;
-        const size_t row = (size_t)src.genes * src.m * 8;
-        t.y = (double*)p; p += row;
-        t.aux = nullptr; t.gs = nullptr; t.cst = nullptr;
-        if (src.aux) { t.aux = (double*)p; p += row; }
-        if (src.gs) { t.gs = (double*)p; p += (size_t)src.genes * 8; }
-        if (src.cst) { t.cst = (double*)p; p += (size_t)src.genes * 8; }
-        t.status = (uint8_t*)p;
-        return t;
-    }
-    // called by ONE thread: start the copies of `tile` into `slot`
-    __device__ void issue(int slot, long long tile) const {
-        const TileStage t = stage(slot);
-        uint64_t* bar = &bars[slot];
-        const long long g0 = tile * src.genes;
-        const uint32_t row = (uint32_t)src.genes * src.m * 8;
-        mbar_expect_tx(bar, tx_bytes);
-        bulk_g2s(t.y, src.y + g0 * src.m, row, bar);
-        if (src.aux) bulk_g2s(t.aux, src.aux + g0 * src.m, row, bar);
-        if (src.gs) bulk_g2s(t.gs, src.gs + g0, (uint32_t)src.genes * 8, bar);
-        if (src.cst) bulk_g2s(t.cst, src.cst + g0, (uint32_t)src.genes * 8, bar);
-        bulk_g2s(t.status, src.status + g0, (uint32_t)src.genes, bar);
-    }
-};
+// called by ONE thread: arm the stage's barrier and start the copies of `tile` into it
+__device__ __forceinline__ void tile_issue(const TileSrc& src, const TileLayout& L, unsigned char* stage,
+                                           uint64_t* bar, long long tile) {
+    const long long g0 = tile * src.genes;
+    mbar_expect_tx(bar, L.tx_bytes);
+    bulk_g2s(stage, src.y + g0 * src.m, L.row_bytes, bar);
+    if (src.aux) bulk_g2s(stage + L.aux_off, src.aux + g0 * src.m, L.row_bytes, bar);
+    if (src.gs) bulk_g2s(stage + L.gs_off, src.gs + g0, (uint32_t)src.genes * 8, bar);
+    if (src.cst) bulk_g2s(stage + L.cst_off, src.cst + g0, (uint32_t)src.genes * 8, bar);
+    bulk_g2s(stage + L.status_off, src.status + g0, (uint32_t)src.genes, bar);
+}
 
-// Persistent tile loop.  `body(stage, tile)` is run by every thread of the CTA for each tile;
-// it may write the stage's shared memory (in-place gradient terms).  `wrote_smem` tells the ring
-// to fence those generic-proxy writes before the slot is refilled by the TMA engine.
-template <class Body>
-__device__ __forceinline__ void tile_loop(TileRing& ring, long long n_tiles, bool wrote_smem, Body body) {
-    const long long first = blockIdx.x, step = gridDim.x;
-    const int S = ring.stages;
+// Initialise the barriers and start the first stages-1 copies (call once, all threads; the
+// caller's next __syncthreads() publishes the barrier initialisation).
+__device__ __forceinline__ void tile_prologue(unsigned char* smem, uint64_t* bars, int stages, const TileSrc& src,
+                                              const TileLayout& L, long long n_tiles) {
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S - 1; ++s) {
-            const long long t = first + (long long)s * step;
-            if (t < n_tiles) ring.issue(s, t);
+        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+        for (int s = 0; s < stages - 1; ++s) {
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < n_tiles) tile_issue(src, L, smem + (size_t)s * L.stage_bytes, &bars[s], t);
         }
     }
-    long long it = 0;
-    for (long long tile = first; tile < n_tiles; tile += step, ++it) {
-        const int slot = (int)(it % S);
+}
+
+// Persistent tile loop.  `body(stage, tile)` is run by every thread of the CTA for each tile with
+// `stage` pointing at the tile's buffer in shared memory; it may write that buffer (in-place
+// gradient terms), in which case `wrote_smem` makes the ring fence those generic-proxy writes
+// before the TMA engine refills the slot.  `smem` must be the CTA's dynamic shared memory base so
+// that the compiler keeps the shared address space (LDS, not generic LD) for the body's loads.
+template <class Body>
+__device__ __forceinline__ void tile_loop(unsigned char* smem, uint64_t* bars, int stages, const TileSrc& src,
+                                          const TileLayout& L, long long n_tiles, bool wrote_smem, Body body) {
+    const long long step = gridDim.x;
+    int slot = 0, pre = stages - 1;       // pre: slot consumed in the previous iteration
+    uint32_t parity = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += step) {
         if (threadIdx.x == 0) {
-            const long long ahead = tile + (long long)(S - 1) * step;
-            if (ahead < n_tiles) ring.issue((int)((it + S - 1) % S), ahead);   // slot freed last iteration
+            const long long ahead = tile + (long long)(stages - 1) * step;
+            if (ahead < n_tiles) tile_issue(src, L, smem + (size_t)pre * L.stage_bytes, &bars[pre], ahead);
         }
-        mbar_wait(&ring.bars[slot], (uint32_t)((it / S) & 1));
-        body(ring.stage(slot), tile);
+        mbar_wait(&bars[slot], parity);
+        body(smem + (size_t)slot * L.stage_bytes, tile);
         if (wrote_smem) fence_proxy_async();
         __syncthreads();
+        pre = slot;
+        if (++slot == stages) { slot = 0; parity ^= 1u; }
     }
 }
 

@@ -75,7 +75,7 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
     for (int p = 0; p <= m; ++p) density_tables(is_t, v, p, t0[p], t1[p]);
     EvalConst ec;
     ec.kind = fam->kind; ec.tail_own = fam->tail_own; ec.v3 = fam->v3; ec.is_t = is_t; ec.v = v;
-    ec.theta0 = theta0; ec.ta = ta.data(); ec.tb = tb.data(); ec.t0 = t0.data(); ec.t1 = t1.data();
+    ec.theta0 = theta0; ec.ta = ta.data(); ec.tb = tb.data(); ec.t0 = t0.data(); ec.t1 = t1.data(); ec.finish_setup();
 
     Prepared pr;
     FN_DISPATCH_WIDTH(width, prepare_all<C>(*fam, n, m, y, aux_raw, controls, dn, dc, pr));
@@ -123,7 +123,7 @@ int hc_coef(const Family* fam, long n, int m, const double* y, const double* aux
     if (!unpack_theta(*fam, m, theta, v, is_t, theta0, ta, tb)) return -4;
     EvalConst ec;
     ec.kind = fam->kind; ec.tail_own = fam->tail_own; ec.v3 = fam->v3; ec.is_t = is_t; ec.v = v;
-    ec.theta0 = theta0; ec.ta = ta.data(); ec.tb = tb.data(); ec.t0 = nullptr; ec.t1 = nullptr;
+    ec.theta0 = theta0; ec.ta = ta.data(); ec.tb = tb.data(); ec.t0 = nullptr; ec.t1 = nullptr; ec.finish_setup();
     Prepared pr;
     Design dummy = d;
     FN_DISPATCH_WIDTH(d.width, prepare_all<C>(*fam, n, m, y, aux_raw, nullptr, d, dummy, pr));

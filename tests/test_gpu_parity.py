@@ -1,0 +1,228 @@
+"""Parity of the CUDA path (through the C ABI, libfitnoise_b200.so) with the reference's own
+outputs (tests/golden) and with the oracle on seeded inputs.  Needs a B200: ``-m gpu``.
+
+Tolerances (north_star): per-gene log-likelihood, coefficients and statistics 1e-9 relative;
+p-values 1e-8 relative; fitted hyper-parameters 1e-6 relative; BH bit-exact given p.
+"""
+import numpy as np
+import pytest
+
+import fitnoise_b200 as fitnoise
+from conftest import assert_close, golden_context, golden_fit_kwargs, golden_names, load_golden
+from fitnoise_b200 import _native
+from helpers import check_against_golden, fit_golden, rank_deficient_rows, synthetic
+from oracle import fitnoise_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+NAMES = [n for n in golden_names() if n != "t_nan_quirk"]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = _native.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_forced_param(name):
+    """fit(force_param) + test on the GPU against the reference's outputs."""
+    g = load_golden(name)
+    fitted, tested = fit_golden(g, force_param=g["theta"])
+    check_against_golden(g, fitted, tested)
+    score, d2, p = fitted._session.per_gene(g["theta"])
+    ref = g["ref_score_rows"].copy()
+    ref[rank_deficient_rows(g)] = np.nan
+    assert_close(score, ref, 1e-9, what="per-gene score_row")
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_value_and_gradient(name):
+    """Summed objective and its gradient against the oracle (matrix-calculus gradient on the
+    reference's own S, cross-checked against central differences in test_oracle_golden.py)."""
+    g = load_golden(name)
+    theta = g["theta"]
+    if len(theta) == 0:
+        pytest.skip("no hyper-parameters")
+    fitted, _ = fit_golden(g, force_param=theta)
+    value, grad, used, bad = fitted._session.nll_grad(theta)
+    cfg = oracle.Configured(str(g["model"]), g["y"], golden_context(g))
+    kw = golden_fit_kwargs(g)
+    out = oracle.fit_noise(cfg, g.get("noise_design", g["design"]), kw.get("control_design"),
+                           kw.get("controls"), force_param=theta, skip_rank_deficient=True)
+    ov, og = oracle.total_score_grad(cfg, out["prepared"], theta)
+    assert used == len(out["prepared"]) and bad == 0
+    assert_close(value, ov, 1e-11, what="objective")
+    assert_close(grad, og, 1e-8, atol=1e-9 * abs(ov), what="gradient")
+
+
+@pytest.mark.parametrize("lpg,threads", [(1, 128), (2, 128), (4, 256), (8, 256), (16, 256)])
+def test_lane_mappings_agree(lpg, threads):
+    """Every lanes-per-gene mapping of the tile kernels gives the same per-gene numbers."""
+    g = load_golden("t_patseq_v2_per_sample")
+    fam_model = getattr(fitnoise, str(g["model"]))()
+    e = _native.Engine(0)
+    try:
+        m = g["y"].shape[1]
+        fam = fam_model._family(m)
+        e.set_tuning(lpg=0, threads=0)
+        e.upload(g["y"], g["counts"], fam, None, g["design"])
+        base = e.per_gene(g["theta"])
+        bv, bg, _, _ = e.nll_grad(g["theta"])
+        e.set_tuning(lpg=lpg, threads=threads)
+        e.upload(g["y"], g["counts"], fam, None, g["design"])
+        got = e.per_gene(g["theta"])
+        v, gr, _, _ = e.nll_grad(g["theta"])
+    finally:
+        e.close()
+    assert_close(got[0], base[0], 1e-12, what="score")
+    assert_close(got[1], base[1], 1e-11, what="d2")
+    assert np.array_equal(got[2], base[2])
+    assert_close(v, bv, 1e-12)
+    assert_close(gr, bg, 1e-9, atol=1e-12 * abs(bv))
+
+
+@pytest.mark.parametrize("name", ["t_twogroup", "t_patseq_v2", "t_controls_opt"])
+def test_fitted_hyperparameters(name):
+    g = load_golden(name)
+    fitted, tested = fit_golden(g)
+    ref = oracle.fit_and_test(str(g["model"]), g["y"], g["design"], golden_context(g),
+                              coef_idx=[int(i) for i in g["test_coef"]], nan_aware=True,
+                              skip_rank_deficient=True, **golden_fit_kwargs(g))
+    x, rx = fitted.optimization_result.x, ref["x"]
+    free = ~(np.isclose(rx, 100.0) | np.isclose(rx, 1e-3))
+    assert_close(x[free], rx[free], 1e-6, what="theta")
+    assert_close(fitted.optimization_result.fun, ref["fun"], 1e-10, what="fun")
+    assert_close(tested.p_values, ref["p_values"], 1e-5, what="p at fitted theta")
+
+
+@pytest.mark.parametrize("lpg,threads", [(1, 128), (2, 256), (4, 256), (8, 128), (16, 256)])
+@pytest.mark.parametrize("model", ["Model_t", "Model_t_per_sample", "Model_normal_patseq"])
+def test_blocked_order_lane_mappings(model, lpg, threads):
+    """m = 32 (a multiple of 16: blocked, bank-rotated sample order) under every lane mapping,
+    against the oracle."""
+    rng = np.random.default_rng(11)
+    n, m = 300, 32
+    design = np.stack([np.ones(m), (np.arange(m) >= 16) * 1.0, rng.normal(size=m)], axis=1)
+    y = rng.normal(size=(n, m)) * 1.3 + 20.0
+    context, aux = {}, None
+    if model == "Model_normal_patseq":
+        aux = rng.poisson(20.0, size=(n, m)).astype(float)
+        aux[rng.random((n, m)) < 0.1] = 0
+        y[aux == 0] = np.nan
+        context = {"counts": aux}
+        theta = np.array([300.0, 0.004])
+    elif model == "Model_t_per_sample":
+        theta = np.array([7.0] + list(rng.uniform(0.5, 2.0, size=m)))
+    else:
+        y[3, 5] = np.nan
+        theta = np.array([7.0, 1.5])
+    fam = getattr(fitnoise, model)()._family(m)
+    e = _native.Engine(0)
+    try:
+        e.set_tuning(lpg=lpg, threads=threads)
+        e.upload(y, aux, fam, None, design)
+        score, d2, p = e.per_gene(theta)
+        value, grad, used, bad = e.nll_grad(theta)
+    finally:
+        e.close()
+    rows = np.arange(0, n, 6)
+    cfg = oracle.Configured(model, y[rows], {k: v[rows] for k, v in context.items()}, nan_aware=True)
+    prep = oracle.prepare_rows(cfg, [design] * len(rows), skip_rank_deficient=True)
+    want = np.full(len(rows), np.nan)
+    for r, item in prep.items():
+        want[r] = oracle.score_row(cfg, theta, r, *item)
+    assert_close(score[rows], want, 1e-9, what="score")
+    assert_close(np.nansum(score), value, 1e-12, what="sum of scores")
+    assert bad == 0
+
+
+@pytest.mark.parametrize("config,n", [(1, 400), (2, 300), (3, 300), (4, 150), (5, 60)])
+def test_synthetic_configs_against_oracle(config, n):
+    """The five BASELINE.json shapes at a size the oracle finishes in seconds."""
+    s = synthetic(config, n=n)
+    model = getattr(fitnoise, s["model"])()
+    kw = {k: s[k] for k in ("controls", "control_design") if k in s}
+    init = model._family(s["y"].shape[1])
+    cfg = oracle.Configured(s["model"], s["y"], s["context"], nan_aware=True)
+    theta = cfg.initial.copy()
+    if len(theta) and config == 3:
+        theta = np.array([12.0, 700.0, 0.003])
+    fitted = model.fit(fitnoise.Dataset(s["y"], s["context"]), s["design"], force_param=theta, **kw)
+    tested = fitted.test(**s["test"])
+    t = s["test"]
+    ref = oracle.fit_and_test(s["model"], s["y"], s["design"], s["context"], coef_idx=t.get("coef"),
+                              contrasts=t.get("contrasts"), force_param=theta, nan_aware=True,
+                              skip_rank_deficient=True, **kw)
+    assert_close(fitted.noise_p_values, ref["noise_p_values"], 1e-8, what="noise p")
+    assert_close(fitted.averages, ref["averages"], 1e-12, what="averages")
+    assert_close(fitted.coef, ref["coef"], 1e-9, atol=1e-10, what="coef")
+    assert_close(fitted._coef_covar, ref["coef_covar"], 1e-9, atol=1e-13, what="covar")
+    assert_close(tested.p_values, ref["p_values"], 1e-8, what="p")
+    assert np.array_equal(tested.q_values, oracle.fdr(tested.p_values)), "BH not bit-exact"
+    if len(theta):
+        value, grad, used, bad = fitted._session.nll_grad(theta)
+        ov, og = oracle.total_score_grad(ref["cfg"], ref["prepared"], theta)
+        assert_close(value, ov, 1e-11, what="objective")
+        assert_close(grad, og, 1e-8, atol=1e-9 * abs(ov), what="gradient")
+
+
+def test_bh_bit_exact(engine):
+    rng = np.random.default_rng(7)
+    g = load_golden("fdr")
+    for i in "1234":
+        assert np.array_equal(engine.bh(g["p" + i]), g["ref_q" + i]), "golden fdr vector %s" % i
+    for n in (1, 2, 255, 256, 257, 2048, 2049, 100003, 1000000):
+        p = rng.random(n) ** rng.choice([1, 3, 8])
+        if n > 10:
+            p[rng.integers(0, n, n // 50 + 1)] = np.nan
+            p[rng.integers(0, n, n // 20 + 1)] = p[0]              # ties
+            p[1] = 0.0
+            p[2] = 1.0
+        q = engine.bh(p)
+        assert np.array_equal(q, oracle.fdr(p)), "n = %d" % n
+    assert np.array_equal(fitnoise.fdr([0.01, np.nan, 0.04, 0.03]), oracle.fdr([0.01, np.nan, 0.04, 0.03]))
+
+
+def test_full_size_properties():
+    """BASELINE.json's largest shape (1M x 96 would take the oracle days): size-independent
+    properties at 200k x 96 -- the oracle on a slice, invariances on the whole."""
+    n, m = 200000, 96
+    rng = np.random.default_rng(5)
+    design = np.array([[1.0, 0.0]] * 48 + [[1.0, 1.0]] * 48)
+    y = rng.normal(size=(n, m)) * np.sqrt(10.0 / rng.chisquare(10.0, size=(n, 1)))
+    fam = fitnoise.Model_t()._family(m)
+    theta = np.array([8.0, 1.2])
+    e = _native.Engine(0)
+    try:
+        e.upload(y, None, fam, None, design)
+        v_all, g_all, used, bad = e.nll_grad(theta)
+        score, d2, p = e.per_gene(theta)
+        assert used == n and bad == 0
+        # 1. the sum of the per-gene scores is the objective
+        assert_close(score.sum(), v_all, 1e-12, what="sum of per-gene scores")
+        # 2. the oracle on a slice of 40 genes
+        rows = np.arange(0, n, n // 40)[:40]
+        cfg = oracle.Configured("Model_t", y[rows])
+        prep = oracle.prepare_rows(cfg, [design] * len(rows))
+        ref = np.array([oracle.score_row(cfg, theta, r, *prep[r]) for r in range(len(rows))])
+        assert_close(score[rows], ref, 1e-9, what="per-gene score vs oracle")
+        # 3. additivity over gene shards (what multi-GPU sharding relies on)
+        half = n // 2
+        e.upload(y[:half], None, fam, None, design)
+        v1, g1, _, _ = e.nll_grad(theta)
+        e.upload(y[half:], None, fam, None, design)
+        v2, g2, _, _ = e.nll_grad(theta)
+        assert_close(v1 + v2, v_all, 1e-12, what="shard additivity (value)")
+        assert_close(g1 + g2, g_all, 1e-9, atol=1e-12 * abs(v_all), what="shard additivity (gradient)")
+        # 4. invariance to a change of basis of the design and to adding a fitted effect
+        e.upload(y + design @ np.array([3.0, -2.0]), None, fam, None, design @ np.array([[2.0, 1.0], [0.0, -3.0]]))
+        v3, g3, _, _ = e.nll_grad(theta)
+        assert_close(v3, v_all, 1e-10, what="invariance to design basis / fitted shift")
+        # 5. scaling y by s moves the variance parameter by s^2
+        e.upload(2.0 * y, None, fam, None, design)
+        v4, _, _, _ = e.nll_grad(np.array([8.0, 4.8]))
+        assert_close(v4, v_all + n * (m - 2) * np.log(2.0), 1e-11, what="scale equivariance")
+    finally:
+        e.close()

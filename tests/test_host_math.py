@@ -69,3 +69,40 @@ def test_kernel_math_matches_reference_golden(name):
     ref[rank_deficient_rows(g)] = np.nan
     from conftest import assert_close
     assert_close(score, ref, 1e-9, what="per-gene score_row")
+
+
+@pytest.mark.parametrize("model", ["Model_t", "Model_t_per_sample", "Model_t_patseq"])
+def test_blocked_sample_order(model):
+    """m a multiple of 16 takes the kernels' blocked (bank-rotated) sample order."""
+    from oracle import fitnoise_oracle as oracle
+    from conftest import assert_close
+    import fitnoise_b200 as fitnoise
+    rng = np.random.default_rng(11)
+    n, m = 40, 32
+    design = np.stack([np.ones(m), (np.arange(m) >= 16) * 1.0, rng.normal(size=m)], axis=1)
+    y = rng.normal(size=(n, m)) * 1.3 + 20.0
+    context = {}
+    if model == "Model_t_patseq":
+        counts = rng.poisson(20.0, size=(n, m)).astype(float)
+        counts[rng.random((n, m)) < 0.1] = 0
+        y[counts == 0] = np.nan
+        context = {"counts": counts}
+        theta = [9.0, 300.0, 0.004]
+    elif model == "Model_t_per_sample":
+        theta = [7.0] + list(rng.uniform(0.5, 2.0, size=m))
+    else:
+        y[3, 5] = np.nan
+        theta = [7.0, 1.5]
+    fitted = getattr(fitnoise, model)()._with(_engine_factory=hostcheck.HostEvaluator).fit(
+        fitnoise.Dataset(y, context), design, force_param=theta)
+    ref = oracle.fit_and_test(model, y, design, context, coef_idx=[1], force_param=theta, nan_aware=True)
+    score, d2, p = fitted._session.per_gene(theta)
+    want = np.full(n, np.nan)
+    for row, item in ref["prepared"].items():
+        want[row] = oracle.score_row(ref["cfg"], np.asarray(theta), row, *item)
+    assert_close(score, want, 1e-9, what="score")
+    value, grad, used, bad = fitted._session.nll_grad(theta)
+    ov, og = oracle.total_score_grad(ref["cfg"], ref["prepared"], np.asarray(theta))
+    assert_close(value, ov, 1e-11)
+    assert_close(grad, og, 1e-8, atol=1e-9 * abs(ov))
+    assert_close(fitted.coef, ref["coef"], 1e-9, atol=1e-10)
