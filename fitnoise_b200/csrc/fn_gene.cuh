@@ -121,6 +121,7 @@ struct GeneView {
     int cnt;            // number of samples this lane owns
     int skew;           // rotation of the lane-local sample order (shared-memory bank spreading)
     int blocked;        // 1: rotate within blocks of 16 samples (m % 16 == 0, lpg <= 16)
+    int steps, nblk;    // blocked order: 16/lpg rotation steps, m/16 blocks
     // `gene_local` = index of the gene within the tile.  Rows of a tile are m doubles apart, so
     // without a rotation the lanes of a warp that work on different genes would hit the same
     // shared-memory banks whenever m is a multiple of 16 (8-byte bank pairs).
@@ -129,6 +130,8 @@ struct GeneView {
         cnt = (m - lane + lpg - 1) / lpg;
         if (cnt < 0) cnt = 0;
         blocked = ((m & 15) == 0 && lpg <= 16) ? 1 : 0;
+        steps = blocked ? 16 / lpg : 0;
+        nblk = m >> 4;
         if (blocked) skew = (((m / lpg) & 1) == 0) ? gene_local : 0;
         else skew = cnt > 0 ? gene_local % cnt : 0;
     }
@@ -142,7 +145,6 @@ struct GeneView {
     FN_HD void for_each(bool on, F f) const {
         if (!on) return;
         if (blocked) {
-            const int steps = 16 / lpg, nblk = m >> 4;
             for (int r = 0; r < steps; ++r) {
                 const int jr = (lane + lpg * (skew + r)) & 15;
 #pragma unroll 2
@@ -156,6 +158,33 @@ struct GeneView {
         j = lane;
 #pragma unroll 4
         for (int ii = 0; ii < skew; ++ii, j += lpg) f(j);
+    }
+    // The same visit for the one sweep that is hot at large m: the block loop is fully unrolled
+    // for the common m/16, so that a rotation step issues all its shared-memory loads (constant
+    // offsets from one base address) before the FMAs that consume them.
+    template <int NB, class F>
+    FN_HD void blocked_unrolled(F f) const {
+        for (int r = 0; r < steps; ++r) {
+            const int jr = (lane + lpg * (skew + r)) & 15;
+#pragma unroll
+            for (int t = 0; t < NB; ++t) f(jr + 16 * t);
+        }
+    }
+    template <class F>
+    FN_HD void for_each_hot(bool on, F f) const {
+        if (!on) return;
+        if (blocked) {
+            switch (nblk) {
+                case 1: blocked_unrolled<1>(f); return;
+                case 2: blocked_unrolled<2>(f); return;
+                case 3: blocked_unrolled<3>(f); return;
+                case 4: blocked_unrolled<4>(f); return;
+                case 6: blocked_unrolled<6>(f); return;
+                case 8: blocked_unrolled<8>(f); return;
+                default: break;
+            }
+        }
+        for_each(true, f);
     }
 };
 
@@ -481,9 +510,17 @@ FN_HD double finish_density(const EvalConst& ec, int p, double logdet, double d2
 // needs only b = X'y and y'y (C+1 FMAs per sample): beta = b, det A = 1, d2 = y'y - |b|^2.  A
 // missing value makes y'y non-finite, which is how incomplete rows are found at no per-sample
 // cost; they (and every weighted gene) take the masked sweep that also builds A.
+struct Scale1Mid {
+    double d2;          // Mahalanobis distance at theta = 1
+    double logdet_a;    // ln det(X'WX) at theta = 1 (0 for a complete unweighted gene)
+    int p;              // residual df
+    int state;          // 0: gene not in the REML sum, 1: usable, 2: failed (non-finite)
+};
+
+// First half: everything that needs the gene's row (sums, solve, d2).  Cheap in the common case.
 template <int C>
-FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
-                       bool eligible, double cst, EvalOut& out) {
+FN_HD void scale1_sweep(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
+                        bool eligible, Scale1Mid& mid) {
     const bool has_aux = gv.aux != nullptr;
     double b[C], beta[C];
     double yy = 0.0, det = 1.0;
@@ -492,7 +529,7 @@ FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X,
 #pragma unroll
     for (int i = 0; i < C; ++i) b[i] = 0.0;
     if (!has_aux) {
-        gv.for_each(eligible, [&](int j) {
+        gv.for_each_hot(eligible, [&](int j) {
             const double y = gv.y[j];
             double x[C];
             load_x<C>(X, j, x);
@@ -553,18 +590,34 @@ FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X,
         s = lane_sum(s, gv.lpg);
         if (d2 < 1e-4 * yy) d2 = s;
     }
+    mid.p = k - c_real;
+    mid.d2 = d2 < 0.0 ? 0.0 : d2;
+    mid.logdet_a = complete ? 0.0 : log(det);
+    mid.state = !eligible ? 0 : ((ok && mid.p > 0 && d2 == d2) ? 1 : 2);
+}
+
+// Second half: the density and its derivatives from (p, d2); needs no data.
+FN_HD void scale1_finish(const EvalConst& ec, const Scale1Mid& mid, double cst, EvalOut& out) {
     eval_zero(out);
-    if (!eligible) return;
-    const int p = k - c_real;
-    if (!ok || p <= 0) { out.value = NAN; out.used = 1; return; }
-    if (d2 < 0.0) d2 = 0.0;
-    d2 *= ec.itheta0;
-    const double logdet = p * ec.ltheta0 + (complete ? 0.0 : log(det)) + cst;
+    if (mid.state == 0) return;
+    out.used = 1;
+    if (mid.state == 2) { out.value = NAN; return; }
+    const int p = mid.p;
+    const double d2 = mid.d2 * ec.itheta0;
+    const double logdet = p * ec.ltheta0 + mid.logdet_a + cst;
     double dv, kappa;
     out.value = finish_density(ec, p, logdet, d2, dv, kappa);
     out.dv = dv;
     out.ga = (0.5 * p - kappa * d2) * ec.itheta0;
-    out.d2 = d2; out.p = p; out.used = 1;
+    out.d2 = d2; out.p = p;
+}
+
+template <int C>
+FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
+                       bool eligible, double cst, EvalOut& out) {
+    Scale1Mid mid;
+    scale1_sweep<C>(ec, gv, X, c_real, eligible, mid);
+    scale1_finish(ec, mid, cst, out);
 }
 
 // KIND_SCALE_PS / KIND_PATSEQ: general diagonal variance; two more sweeps over the gene's row

@@ -211,6 +211,58 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
     const int col = inplace ? threadIdx.x % m : 0, sub = inplace ? threadIdx.x / m : 0;
     double col_a = 0.0, col_b = 0.0;
 
+    // accumulate one finished gene into the thread's partial sums / the per-gene outputs
+    auto account = [&](const EvalOut& eo, long long gene) {
+        if (gene >= p.g.n) return;
+        if (eo.used) {
+            if (eo.value == eo.value) {
+                acc[ACC_VALUE] += eo.value; acc[ACC_DV] += eo.dv;
+                acc[ACC_GA] += eo.ga; acc[ACC_GB] += eo.gb; acc[ACC_USED] += 1.0;
+            } else {
+                acc[ACC_BAD] += 1.0;
+            }
+        }
+        if (p.pg_score) {
+            p.pg_score[gene] = eo.used ? eo.value : NAN;
+            p.pg_d2[gene] = eo.d2;
+            p.pg_p[gene] = eo.p;
+        }
+    };
+
+    if constexpr (KIND == KIND_SCALE1) {
+        // The lpg lanes of a gene all end the sweep holding the same (p, d2).  Instead of every
+        // lane running the density tail (log1p, divisions) for the same gene, lane l keeps the
+        // gene of every lpg-th tile and the tail runs once per lpg tiles with all 32 lanes of a
+        // warp working on different genes.
+        Scale1Mid pend;
+        pend.state = 0; pend.d2 = 0.0; pend.logdet_a = 0.0; pend.p = 0;
+        double pend_cst = 0.0;
+        long long pend_gene = -1;
+        int sel = 0;
+        auto finalize = [&]() {
+            if (pend_gene >= 0) {
+                EvalOut eo;
+                scale1_finish(ec, pend, pend_cst, eo);
+                account(eo, pend_gene);
+                pend_gene = -1;
+            }
+        };
+        tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, false, [&](unsigned char* st, long long tile) {
+            gv.y = (double*)st + gl * m;
+            gv.aux = p.src.aux ? (double*)(st + L.aux_off) + gl * m : nullptr;
+            const uint8_t status = st[L.status_off + gl];
+            const bool control = (status & 2) != 0;
+            Scale1Mid mid;
+            scale1_sweep<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, (status & 1) != 0, mid);
+            if (lane == sel) {
+                pend = mid;
+                pend_cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
+                pend_gene = tile * p.g.genes + gl;
+            }
+            if (++sel == p.g.lpg) { sel = 0; finalize(); }
+        });
+        finalize();
+    } else {
     tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, inplace, [&](unsigned char* st, long long tile) {
         const long long gene = tile * p.g.genes + gl;
         double* ys = (double*)st;
@@ -223,26 +275,9 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
         const bool eligible = (status & 1) != 0;
         const double cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
         EvalOut eo;
-        if (KIND == KIND_SCALE1)
-            eval_scale1<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst, eo);
-        else
-            eval_general<C, KIND>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst,
-                                  p.inplace_a != 0, p.inplace_b != 0, eo);
-        if (lane == 0 && gene < p.g.n) {
-            if (eo.used) {
-                if (eo.value == eo.value) {
-                    acc[ACC_VALUE] += eo.value; acc[ACC_DV] += eo.dv;
-                    acc[ACC_GA] += eo.ga; acc[ACC_GB] += eo.gb; acc[ACC_USED] += 1.0;
-                } else {
-                    acc[ACC_BAD] += 1.0;
-                }
-            }
-            if (p.pg_score) {
-                p.pg_score[gene] = eo.used ? eo.value : NAN;
-                p.pg_d2[gene] = eo.d2;
-                p.pg_p[gene] = eo.p;
-            }
-        }
+        eval_general<C, KIND>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst,
+                              p.inplace_a != 0, p.inplace_b != 0, eo);
+        if (lane == 0) account(eo, gene);
         if (inplace) {
             __syncthreads();
             if (sub < nsub) {
@@ -253,6 +288,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
             }
         }
     });
+    }
 
     block_sum<ACC_FIXED>(acc, vals, red_scratch);
     if (inplace) {

@@ -35,7 +35,7 @@ with torch.cuda.stream(stream):
     base = None
     rows = []
     arrays = 2 if weights else 1
-    for threads, lpg, stages, ctas in itertools.product((128, 256), (1, 2, 4, 8, 16), (2, 3, 4), (1, 2, 3, 4)):
+    for threads, lpg, stages, ctas in itertools.product((128, 256), (1, 2, 4, 8), (1, 2, 3, 4), (1, 2, 3, 4)):
         genes = threads // lpg
         if genes % 16:
             continue
