@@ -46,14 +46,18 @@ class Session(object):
         return 0.0 if x != x else float(x)
 
     def _cuda_engine(self):
-        stream = None
         if self.world > 1:
-            # share torch's current stream so that the all-reduce is ordered after the kernel
+            # One torch stream carries the kernels AND the collectives, so that the all-reduce is
+            # ordered after the kernel that produced its input (the handle would otherwise launch on
+            # a private non-blocking stream that the NCCL stream knows nothing about).
             import torch
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank)))
-            stream = torch.cuda.current_stream().cuda_stream
-            self._cuda_reduce = torch.zeros(self.P + 3, dtype=torch.float64, device="cuda")
-            return _native.Engine(torch.cuda.current_device(), stream)
+            self._torch = torch
+            self._stream = torch.cuda.Stream()
+            with torch.cuda.stream(self._stream):
+                self._cuda_reduce = torch.zeros(self.P + 3, dtype=torch.float64, device="cuda")
+            self._stream.synchronize()
+            return _native.Engine(torch.cuda.current_device(), self._stream.cuda_stream)
         return _native.Engine(int(os.environ.get("LOCAL_RANK", "0")))
 
     def close(self):
@@ -67,9 +71,10 @@ class Session(object):
         theta = np.asarray(theta, dtype=np.float64)
         if self._cuda_reduce is not None:
             buf = self._cuda_reduce
-            self.local.nll_grad_dev(theta, buf.data_ptr())
-            parallel.allreduce_sum_tensor(buf)
-            out = buf.cpu().numpy()
+            with self._torch.cuda.stream(self._stream):
+                self.local.nll_grad_dev(theta, buf.data_ptr())
+                parallel.allreduce_sum_tensor(buf)
+                out = buf.cpu().numpy()
             return float(out[0]), out[1:1 + self.P].copy(), int(out[self.P + 1]), int(out[self.P + 2])
         value, grad, used, bad = self.local.nll_grad(theta)
         if self.world == 1:

@@ -1,0 +1,93 @@
+"""The N > 1 path on CPU: two ranks over gloo, genes sharded, sums all-reduced, per-gene results
+all-gathered.  Each rank's local evaluator is the host build of the kernel mathematics
+(tests/hostcheck) -- the CUDA evaluator takes its place on a GPU box (bench.py --gpus N)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+from conftest import ROOT, assert_close, golden_context, golden_fit_kwargs, golden_test_kwargs, load_golden
+
+CASES = ["t_twogroup", "t_patseq_v2", "t_per_sample_controls"]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run_case(name, forced):
+    import fitnoise_b200 as fitnoise
+    import hostcheck
+    g = load_golden(name)
+    model = getattr(fitnoise, str(g["model"]))()._with(_engine_factory=hostcheck.HostEvaluator)
+    kw = golden_fit_kwargs(g)
+    if forced:
+        kw["force_param"] = g["theta"]
+    fitted = model.fit(fitnoise.Dataset(g["y"], golden_context(g)), design=g["design"], **kw)
+    tested = fitted.test(**golden_test_kwargs(g))
+    value, grad, used, bad = fitted._session.nll_grad(g["theta"])
+    return dict(x=np.asarray(fitted.optimization_result.x), value=value, grad=grad, used=used,
+                noise_p=fitted.noise_p_values, averages=fitted.averages, coef=fitted.coef,
+                covar=fitted._coef_covar, p=tested.p_values, q=tested.q_values, weights=fitted.get_weights(),
+                combined=fitted.noise_combined_p_value, description=fitted.description,
+                shard=(fitted._session.lo, fitted._session.hi, fitted._session.world))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        results = {}
+        for name in CASES:
+            results[name + ":forced"] = _run_case(name, True)
+        results["t_twogroup:fit"] = _run_case("t_twogroup", False)
+        np.save(os.path.join(out_dir, "rank%d.npy" % rank), results, allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_match_one(tmp_path):
+    single = {name + ":forced": _run_case(name, True) for name in CASES}
+    single["t_twogroup:fit"] = _run_case("t_twogroup", False)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ranks = [np.load(os.path.join(str(tmp_path), "rank%d.npy" % r), allow_pickle=True).item() for r in range(2)]
+    for key, one in single.items():
+        for r in range(2):
+            two = ranks[r][key]
+            n = len(one["noise_p"])
+            assert two["shard"][2] == 2 and two["shard"][1] - two["shard"][0] in (n // 2, n - n // 2)
+            assert two["used"] == one["used"]
+            assert_close(two["value"], one["value"], 1e-13, what=key + " value")
+            assert_close(two["grad"], one["grad"], 1e-10, atol=1e-13 * abs(one["value"]), what=key + " grad")
+            # per-gene results are computed by the owning rank and gathered: identical
+            for field in ("noise_p", "averages", "coef", "covar", "p", "q", "weights"):
+                if key.endswith(":forced"):
+                    assert np.array_equal(two[field], one[field], equal_nan=True), "%s %s" % (key, field)
+                else:       # theta itself differs in the last digits between 1 and 2 ranks
+                    assert_close(two[field], one[field], 1e-7, what="%s %s" % (key, field))
+            assert_close(two["combined"], one["combined"], 1e-7)
+            assert_close(two["x"], one["x"], 1e-9, what=key + " theta")
+        assert ranks[0][key]["description"] == ranks[1][key]["description"]
+
+
+def test_shard_bounds():
+    from fitnoise_b200 import parallel
+    for n, w in [(10, 1), (10, 3), (7, 8), (1000001, 8), (0, 2)]:
+        b = parallel.shard_bounds(n, w)
+        assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+        sizes = np.diff(b)
+        assert sizes.min() >= 0 and sizes.max() - sizes.min() <= 1

@@ -1,0 +1,57 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU, NCCL): the sharded fit through the public
+API gives the single-GPU result.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import fitnoise_b200 as fitnoise  # noqa: E402
+from helpers import synthetic  # noqa: E402
+
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+ok = True
+cases = [(1, 20000), (3, 5000), (4, 3001)]
+single = {}
+for config, n in cases:                 # before the process group exists: plain single-GPU fits
+    s = synthetic(config, n=n)
+    kw = {k: s[k] for k in ("controls", "control_design") if k in s}
+    f = getattr(fitnoise, s["model"])().fit(fitnoise.Dataset(s["y"], s["context"]), s["design"], **kw)
+    t = f.test(**s["test"])
+    single[config] = (f.optimization_result.x.copy(), f.optimization_result.fun, t.p_values.copy(), t.q_values.copy(),
+                      f.noise_p_values.copy())
+    f._session.close()
+
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+for config, n in cases:
+    s = synthetic(config, n=n)
+    kw = {k: s[k] for k in ("controls", "control_design") if k in s}
+    f = getattr(fitnoise, s["model"])().fit(fitnoise.Dataset(s["y"], s["context"]), s["design"], **kw)
+    t = f.test(**s["test"])
+    x1, fun1, p1, q1, np1 = single[config]
+    dx = np.max(np.abs(f.optimization_result.x - x1) / np.abs(x1))
+    dfun = abs(f.optimization_result.fun - fun1) / abs(fun1)
+    dp = np.nanmax(np.abs(t.p_values - p1) / np.maximum(p1, 1e-300))
+    dnp = np.nanmax(np.abs(f.noise_p_values - np1) / np.maximum(np1, 1e-300))
+    same_nan = np.array_equal(np.isnan(t.p_values), np.isnan(p1))
+    good = dx < 1e-7 and dfun < 1e-12 and dp < 1e-5 and same_nan
+    ok &= bool(good)
+    print("rank %d config %d world %d shard [%d,%d): dtheta %.2e dfun %.2e dp %.2e dnoise_p %.2e nan-pattern %s -> %s" % (
+        rank, config, f._session.world, f._session.lo, f._session.hi, dx, dfun, dp, dnp, same_nan, "OK" if good else "FAIL"),
+        flush=True)
+    f._session.close()
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
