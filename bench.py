@@ -225,8 +225,17 @@ def run_gpu(args):
         engine.set_timing(True)
         reduce_buf = torch.zeros(P + 3, dtype=torch.float64, device=dev)
 
+        # N > 1: the all-reduce of the P+3 sums is fused into the kernel epilogue (peer stores over
+        # NVLink into IPC-mapped mailboxes); FN_REDUCE=nccl times kernel + ncclAllReduce instead.
+        reduce_mode = os.environ.get("FN_REDUCE", "fused") if world > 1 else "none"
+        if reduce_mode == "fused":
+            handles = [None] * world
+            dist.all_gather_object(handles, engine.comm_mailbox(world, 8 + 2 * m))
+            engine.comm_connect(rank, world, b"".join(handles))
+            dist.barrier()
+
         def step():
-            if world > 1:
+            if reduce_mode == "nccl":
                 engine.nll_grad_dev(THETA, reduce_buf.data_ptr())
                 dist.all_reduce(reduce_buf)
                 return reduce_buf.cpu().numpy()
@@ -280,11 +289,17 @@ def run_gpu(args):
         ms_per_step = elapsed_ms / args.steps
         value = n * world / (ms_per_step / 1000.0)
 
-        # kernel-only duration for the roofline (N>1: one extra timed pass without the collective)
+        # kernel-only duration for the roofline (N>1: the kernel's own events, same call count on every rank)
         if world > 1:
             for _ in range(5):
-                engine.nll_grad(THETA)
-                kernel_ms.append(engine.last_kernel_ms())
+                step_out = step()
+                if reduce_mode != "nccl":
+                    kernel_ms.append(engine.last_kernel_ms())
+            if reduce_mode == "nccl":
+                engine.comm_disconnect()
+                for _ in range(5):
+                    engine.nll_grad(THETA)
+                    kernel_ms.append(engine.last_kernel_ms())
         kms = float(np.mean(kernel_ms))
         alg_bytes = n * (8 * m + 1)
         peak, peak_src = measured_peak()
@@ -299,12 +314,7 @@ def run_gpu(args):
         ev0.record(stream)
         for _ in range(e2e_steps):
             engine.upload(y_np, None, fam, None, design)
-            if world > 1:
-                engine.nll_grad_dev(THETA, reduce_buf.data_ptr())
-                dist.all_reduce(reduce_buf)
-                res = reduce_buf.cpu().numpy()
-            else:
-                res = engine.nll_grad(THETA)
+            res = step()
         ev1.record(stream)
         barrier()
         e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
@@ -356,7 +366,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "genes_total": n * world, "samples": m, "design_columns": 2,
                        "theta_len": P, "l2": "inputs (768 MB per GPU) larger than L2; no flush needed",
-                       "parallelism": "genes sharded, %d rank(s), all-reduce of %d doubles per step" % (world, P + 3)},
+                       "parallelism": "genes sharded, %d rank(s), all-reduce of %d doubles per step (%s)" % (world, P + 3, reduce_mode)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "gene-evals/s", "h2d_bytes_per_step": int(n * m * 8),
                     "d2h_bytes_per_step": int((P + 3) * 8), "ms_per_step": e2e_ms},

@@ -24,7 +24,7 @@ EXPORTS = [
     "fn_last_error", "fn_device_count", "fn_version", "fn_create", "fn_destroy", "fn_synchronize",
     "fn_upload", "fn_upload_dev", "fn_nll_grad", "fn_nll_grad_dev", "fn_per_gene", "fn_noise_stats",
     "fn_coef", "fn_test", "fn_bh", "fn_bh_dev", "fn_weights", "fn_set_tuning", "fn_launch_count",
-    "fn_set_timing", "fn_last_kernel_ms",
+    "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
 ]
 
 
@@ -94,6 +94,9 @@ def load_library():
     lib.fn_weights.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p]
     lib.fn_set_tuning.argtypes = [ctypes.c_void_p] + [ctypes.c_int32] * 4
     lib.fn_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.fn_comm_mailbox.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    lib.fn_comm_connect.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+    lib.fn_comm_disconnect.argtypes = [ctypes.c_void_p]
     _LIB = lib
     return lib
 
@@ -236,6 +239,21 @@ class Engine(object):
         out = np.empty((self.n, self.m))
         self._check(self._lib.fn_weights(self._h, _dp(theta), len(theta), _dp(out)))
         return out
+
+    # ---- fused multi-GPU exchange ---------------------------------------------------------
+    def comm_mailbox(self, world, max_values):
+        """Allocate this rank's mailbox; returns its 64-byte CUDA IPC handle."""
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._lib.fn_comm_mailbox(self._h, world, max_values, buf))
+        return buf.raw
+
+    def comm_connect(self, rank, world, handles):
+        """handles: the ranks' IPC handles concatenated in rank order (world x 64 bytes)."""
+        assert len(handles) == 64 * world
+        self._check(self._lib.fn_comm_connect(self._h, rank, world, ctypes.c_char_p(handles)))
+
+    def comm_disconnect(self):
+        self._check(self._lib.fn_comm_disconnect(self._h))
 
     # ---- instrumentation ------------------------------------------------------------------
     def synchronize(self):

@@ -92,6 +92,13 @@ struct fn_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     std::map<const void*, size_t> smem_set;
+
+    unsigned long long host_seq = 0;   // completion-flag sequence of the pinned result buffer
+    // fused multi-GPU exchange (fn_comm_*): mailboxes mapped with CUDA IPC
+    int comm_world = 0, comm_rank = 0, comm_slot = 0;
+    unsigned long long comm_seq = 0;
+    double* comm_own = nullptr;
+    double* comm_peer[FN_MAX_RANKS] = {nullptr};
 };
 
 template <class T>
@@ -153,10 +160,13 @@ extern "C" int fn_create(int device, void* stream, fn_handle** out) {
     return 0;
 }
 
+extern "C" int fn_comm_disconnect(fn_handle* h);
+
 extern "C" int fn_destroy(fn_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    fn_comm_disconnect(h);
     release_data(h);
     dfree(h->partials); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
     if (h->out_host) cudaFreeHost(h->out_host);
@@ -251,6 +261,7 @@ static int ensure_reduce(fn_handle* h, int grid, int nacc) {
         const size_t cap = (size_t)nacc + 64;
         CUDA_TRY(cudaMalloc(&h->out_dev, cap * sizeof(double)));
         CUDA_TRY(cudaHostAlloc(&h->out_host, cap * sizeof(double), cudaHostAllocMapped));
+        memset(h->out_host, 0, cap * sizeof(double));
         CUDA_TRY(cudaHostGetDevicePointer(&h->out_host_devptr, h->out_host, 0));
         h->out_cap = cap;
     }
@@ -264,6 +275,44 @@ static int ensure_scratch(fn_handle* h, size_t bytes) {
         h->scratch_cap = bytes;
     }
     return 0;
+}
+
+// Wait for the kernel that carries `seq` to publish its totals in the pinned result buffer.  The
+// last CTA stores the flag after the values (system-scope fence in between), so spinning on host
+// memory sees the result a PCIe write after the kernel finishes -- several microseconds sooner than
+// cudaStreamSynchronize returns.  Falls back to the stream's status to notice a failed launch.
+static int wait_result(fn_handle* h, unsigned long long seq, int nacc) {
+    volatile unsigned long long* flag = (volatile unsigned long long*)&h->out_host[nacc];
+    unsigned long long spins = 0;
+    while (*flag != seq) {
+        if ((++spins & 0x3fff) == 0) {
+            cudaError_t e = cudaStreamQuery(h->stream);
+            if (e == cudaSuccess) {
+                if (*flag == seq) break;
+                return fail(FN_ERR_CUDA, "kernel finished without publishing its result");
+            }
+            if (e != cudaErrorNotReady) return fail(FN_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    return 0;
+}
+
+static void fill_reduce(fn_handle* h, GridReduce& gr, int nacc, int add_index, double add_value, bool exchange) {
+    gr.partials = h->partials; gr.ticket = h->ticket; gr.out_dev = h->out_dev;
+    gr.out_host = h->out_host_devptr; gr.nacc = nacc;
+    gr.add_index = add_index; gr.add_value = add_value;
+    gr.host_seq = ++h->host_seq;
+    gr.comm.world = 0; gr.comm.rank = 0; gr.comm.slot_doubles = 0; gr.comm.seq = 0; gr.comm.timeout_ns = 0;
+    for (int r = 0; r < FN_MAX_RANKS; ++r) gr.comm.mailbox[r] = nullptr;
+    if (exchange && h->comm_world > 1) {
+        gr.comm.world = h->comm_world; gr.comm.rank = h->comm_rank; gr.comm.slot_doubles = h->comm_slot;
+        gr.comm.seq = ++h->comm_seq;
+        gr.comm.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+        for (int r = 0; r < h->comm_world; ++r) gr.comm.mailbox[r] = h->comm_peer[r];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -370,8 +419,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     pp.fam = fam;
     pp.xn = h->xn; pp.xc = h->xc; pp.c_noise = c_noise; pp.c_ctrl = c_ctrl;
     pp.status_out = h->status; pp.cst_out = h->cst; pp.avg_out = h->avg; pp.gs_out = h->gs;
-    pp.gr.partials = h->partials; pp.gr.ticket = h->ticket; pp.gr.out_dev = h->out_dev;
-    pp.gr.out_host = h->out_host_devptr; pp.gr.nacc = PREP_NACC;
+    fill_reduce(h, pp.gr, PREP_NACC, -1, 0.0, false);
     FN_DISPATCH_WIDTH(width, {
         rc = set_smem(h, prepare_kernel<C>, g.smem);
         if (rc) return rc;
@@ -444,7 +492,7 @@ static int eval_nacc(const fn_handle* h) {
     return ACC_FIXED + ((ia || ib) ? 2 * h->m : 0);
 }
 
-static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene) {
+static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool exchange) {
     const int m = h->m;
     const bool ia = h->fam.na == m && h->fam.kind != KIND_SCALE1, ib = h->fam.nb == m;
     const bool inplace = ia || ib;
@@ -476,8 +524,7 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene) {
     ep.pg_score = per_gene ? h->pg_score : nullptr;
     ep.pg_d2 = per_gene ? h->pg_d2 : nullptr;
     ep.pg_p = per_gene ? h->pg_p : nullptr;
-    ep.gr.partials = h->partials; ep.gr.ticket = h->ticket; ep.gr.out_dev = h->out_dev;
-    ep.gr.out_host = h->out_host_devptr; ep.gr.nacc = nacc;
+    fill_reduce(h, ep.gr, nacc, per_gene ? -1 : ACC_VALUE, per_gene ? 0.0 : 0.5 * h->cst_sum, exchange);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     FN_DISPATCH_WIDTH(h->width, {
         if (h->fam.kind == KIND_SCALE1) {
@@ -505,7 +552,7 @@ static void assemble(const fn_handle* h, const double* acc, double* out) {
     const Family& f = h->fam;
     const int m = h->m;
     int at = 0;
-    out[at++] = acc[ACC_VALUE] + 0.5 * h->cst_sum * (acc[ACC_USED] > 0 ? 1.0 : 0.0);
+    out[at++] = acc[ACC_VALUE];
     if (f.dist == DIST_T) out[at++] = acc[ACC_DV];
     if (f.na == 1) out[at++] = acc[ACC_GA];
     else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + j];
@@ -520,9 +567,11 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
-    rc = launch_eval(h, ts, false);
+    rc = launch_eval(h, ts, false, true);
     if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->timing) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    rc = wait_result(h, h->host_seq, eval_nacc(h));
+    if (rc) return rc;
     if (h->timing) {
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -541,7 +590,7 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
 __global__ void assemble_kernel(const double* acc, double* out, Family f, int m, double cst_sum) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int at = 0;
-    out[at++] = acc[ACC_VALUE] + 0.5 * cst_sum * (acc[ACC_USED] > 0 ? 1.0 : 0.0);
+    out[at++] = acc[ACC_VALUE];
     if (f.dist == DIST_T) out[at++] = acc[ACC_DV];
     if (f.na == 1) out[at++] = acc[ACC_GA];
     else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + j];
@@ -556,7 +605,7 @@ extern "C" int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, dou
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
-    rc = launch_eval(h, ts, false);
+    rc = launch_eval(h, ts, false, false);
     if (rc) return rc;
     assemble_kernel<<<1, 32, 0, h->stream>>>(h->out_dev, out_dev, h->fam, h->m, h->cst_sum);
     ++h->launches;
@@ -568,7 +617,7 @@ extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double*
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
-    rc = launch_eval(h, ts, true);
+    rc = launch_eval(h, ts, true, false);
     if (rc) return rc;
     if (score) CUDA_TRY(cudaMemcpyAsync(score, h->pg_score, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (d2) CUDA_TRY(cudaMemcpyAsync(d2, h->pg_d2, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -581,7 +630,7 @@ extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, doub
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
-    rc = launch_eval(h, ts, true);
+    rc = launch_eval(h, ts, true, false);
     if (rc) return rc;
     if (!h->noise_p) CUDA_TRY(cudaMalloc(&h->noise_p, h->n * sizeof(double)));
     const int tb = 128;
@@ -765,5 +814,54 @@ extern "C" int fn_bh(fn_handle* h, int64_t n, const double* p, double* q) {
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(q, q_dev, n * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused multi-GPU exchange: mailboxes shared between the ranks' processes with CUDA IPC
+// ------------------------------------------------------------------------------------------
+extern "C" int fn_comm_mailbox(fn_handle* h, int32_t world, int32_t max_values, void* ipc_handle_out) {
+    if (!h || !ipc_handle_out) return fail(FN_ERR_ARG, "fn_comm_mailbox: NULL argument");
+    if (world < 2 || world > FN_MAX_RANKS) return fail(FN_ERR_ARG, "fn_comm_mailbox: world must be 2..%d", FN_MAX_RANKS);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->comm_own) { cudaFree(h->comm_own); h->comm_own = nullptr; }
+    h->comm_slot = ((max_values + 1 + 15) / 16) * 16;
+    const size_t bytes = (size_t)2 * world * h->comm_slot * sizeof(double);
+    CUDA_TRY(cudaMalloc(&h->comm_own, bytes));
+    CUDA_TRY(cudaMemset(h->comm_own, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t handle;
+    CUDA_TRY(cudaIpcGetMemHandle(&handle, h->comm_own));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    memcpy(ipc_handle_out, &handle, sizeof handle);
+    h->comm_world = 0;          // not connected yet
+    return 0;
+}
+
+extern "C" int fn_comm_connect(fn_handle* h, int32_t rank, int32_t world, const void* ipc_handles) {
+    if (!h || !ipc_handles || !h->comm_own) return fail(FN_ERR_STATE, "fn_comm_connect: call fn_comm_mailbox first");
+    if (world < 2 || world > FN_MAX_RANKS || rank < 0 || rank >= world) return fail(FN_ERR_ARG, "fn_comm_connect: bad rank/world");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->comm_peer[r] = h->comm_own; continue; }
+        cudaIpcMemHandle_t handle;
+        memcpy(&handle, (const char*)ipc_handles + (size_t)r * sizeof handle, sizeof handle);
+        void* ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess));
+        h->comm_peer[r] = (double*)ptr;
+    }
+    h->comm_rank = rank; h->comm_world = world; h->comm_seq = 0;
+    return 0;
+}
+
+extern "C" int fn_comm_disconnect(fn_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < h->comm_world; ++r)
+        if (r != h->comm_rank && h->comm_peer[r]) cudaIpcCloseMemHandle(h->comm_peer[r]);
+    for (int r = 0; r < FN_MAX_RANKS; ++r) h->comm_peer[r] = nullptr;
+    h->comm_world = 0;
+    if (h->comm_own) { cudaFree(h->comm_own); h->comm_own = nullptr; }
     return 0;
 }

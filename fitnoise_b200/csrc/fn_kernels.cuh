@@ -14,20 +14,50 @@ namespace fn {
 // accumulator layout of one CTA's partial sums
 enum { ACC_VALUE = 0, ACC_DV = 1, ACC_GA = 2, ACC_GB = 3, ACC_USED = 4, ACC_BAD = 5, ACC_FIXED = 6 };
 
+#define FN_MAX_RANKS 16
+
+// Cross-GPU exchange fused into the kernel epilogue (multi-GPU, one process per GPU).
+// Every rank owns a mailbox in its device memory: [parity 2][sender world][slot] doubles, slot[0] is
+// the sender's sequence flag and slot[1..] its values.  All ranks' mailboxes are mapped into every
+// process with CUDA IPC, so the last CTA of rank r stores its sums straight into every peer's
+// mailbox over NVLink (st.global on the peer mapping), publishes them with a system-scope fence and
+// a flag, waits for the other ranks' flags in its OWN mailbox, and adds the slots in rank order
+// (so every rank computes bit-identical totals).  No NCCL call, no extra launch, no host round trip.
+struct PeerComm {
+    int world, rank;                       // world <= 1: no exchange
+    int slot_doubles;                      // capacity of a slot (flag + values)
+    unsigned long long seq;                // evaluation number, identical on every rank, >= 1
+    unsigned long long timeout_ns;         // give up waiting for a peer after this long
+    double* mailbox[FN_MAX_RANKS];         // mailbox[r]: rank r's mailbox as mapped in this process
+};
+
 struct GridReduce {
     double* partials;        // gridDim.x * nacc
     unsigned int* ticket;
     double* out_dev;         // nacc doubles
-    double* out_host;        // mapped pinned, nacc doubles, or nullptr
+    double* out_host;        // mapped pinned: nacc values then the completion flag, or nullptr
     int nacc;
+    int add_index;           // out[add_index] += add_value (theta-independent part of the objective)
+    double add_value;
+    unsigned long long host_seq;   // written to out_host[nacc] (as an integer) when the values are there
+    PeerComm comm;
 };
 
-// Sum `nacc` per-CTA values over the grid in a fixed order; the last CTA to arrive does it.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Sum `nacc` per-CTA values over the grid in a fixed order; the last CTA to arrive does it, then
+// (multi-GPU) exchanges the sums with the peer GPUs, and finally hands the totals to the host.
 // `vals` is this CTA's shared array of nacc doubles (already complete, visible after a barrier).
 __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* vals) {
     __shared__ int is_last;
-    for (int i = threadIdx.x; i < gr.nacc; i += blockDim.x)
-        gr.partials[(size_t)blockIdx.x * gr.nacc + i] = vals[i];
+    __shared__ double gsum[256];
+    const int T = blockDim.x, nacc = gr.nacc;
+    for (int i = threadIdx.x; i < nacc; i += T)
+        gr.partials[(size_t)blockIdx.x * nacc + i] = vals[i];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -37,13 +67,84 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int i = threadIdx.x; i < gr.nacc; i += blockDim.x) {
-        double s = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) s += gr.partials[(size_t)b * gr.nacc + i];
-        gr.out_dev[i] = s;
-        if (gr.out_host) gr.out_host[i] = s;
+    const unsigned int G = gridDim.x;
+    if (nacc <= T) {
+        // thread (slice, i) adds blocks slice, slice+S, ... of component i; then the slices are added
+        const int S = T / nacc, i = threadIdx.x % nacc, slice = threadIdx.x / nacc;
+        if (slice < S) {
+            double s = 0.0;
+            for (unsigned int b = slice; b < G; b += S) s += __ldcg(&gr.partials[(size_t)b * nacc + i]);
+            gsum[slice * nacc + i] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < nacc) {
+            double s = 0.0;
+            for (int q = 0; q < S; ++q) s += gsum[q * nacc + threadIdx.x];
+            if (threadIdx.x == gr.add_index) s += gr.add_value;
+            gr.out_dev[threadIdx.x] = s;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nacc; i += T) {
+            double s = 0.0;
+            for (unsigned int b = 0; b < G; ++b) s += __ldcg(&gr.partials[(size_t)b * nacc + i]);
+            if (i == gr.add_index) s += gr.add_value;
+            gr.out_dev[i] = s;
+        }
     }
     if (threadIdx.x == 0) *gr.ticket = 0;
+    __syncthreads();
+
+    const PeerComm& pc = gr.comm;
+    bool failed = false;
+    if (pc.world > 1) {
+        const int parity = (int)(pc.seq & 1ull);
+        const size_t slot_of_me = ((size_t)parity * pc.world + pc.rank) * pc.slot_doubles;
+        for (int i = threadIdx.x; i < nacc; i += T) {
+            const double v = gr.out_dev[i];
+            for (int r = 0; r < pc.world; ++r) pc.mailbox[r][slot_of_me + 1 + i] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < pc.world) {
+            volatile unsigned long long* flag = (volatile unsigned long long*)&pc.mailbox[threadIdx.x][slot_of_me];
+            *flag = pc.seq;
+        }
+        __threadfence_system();
+        // wait for every sender's flag in my own mailbox
+        __shared__ int peer_failed;
+        if (threadIdx.x == 0) peer_failed = 0;
+        __syncthreads();
+        if (threadIdx.x < pc.world) {
+            const size_t slot = ((size_t)parity * pc.world + threadIdx.x) * pc.slot_doubles;
+            volatile unsigned long long* flag = (volatile unsigned long long*)&pc.mailbox[pc.rank][slot];
+            const unsigned long long t0 = global_ns();
+            while (*flag != pc.seq) {
+                if (global_ns() - t0 > pc.timeout_ns) { peer_failed = 1; break; }
+                __nanosleep(100);
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        failed = peer_failed != 0;
+        for (int i = threadIdx.x; i < nacc; i += T) {
+            double s = 0.0;
+            for (int r = 0; r < pc.world; ++r) {
+                const size_t slot = ((size_t)parity * pc.world + r) * pc.slot_doubles;
+                s += __ldcg(&pc.mailbox[pc.rank][slot + 1 + i]);
+            }
+            gr.out_dev[i] = failed ? NAN : s;
+        }
+        __syncthreads();
+    }
+    if (gr.out_host) {
+        for (int i = threadIdx.x; i < nacc; i += T) gr.out_host[i] = gr.out_dev[i];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            volatile unsigned long long* flag = (volatile unsigned long long*)&gr.out_host[nacc];
+            *flag = gr.host_seq;
+        }
+    }
     __threadfence_system();
 }
 

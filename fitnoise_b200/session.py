@@ -40,6 +40,21 @@ class Session(object):
             self.n_eligible, self.n_bad_counts = int(sums[0]), int(sums[1])
             self.row_variance_mean = sums[2] / sums[3] if sums[3] > 0 else np.nan
         self.coef_token = None
+        self._fused = False
+        if self._cuda_reduce is not None and os.environ.get("FN_REDUCE", "fused") == "fused":
+            self._connect_fused()
+
+    def _connect_fused(self):
+        """Exchange the ranks' mailbox handles (CUDA IPC) so that the nll+grad kernel itself adds the
+        sums of all GPUs over NVLink (csrc/fn_kernels.cuh grid_reduce); FN_REDUCE=nccl keeps the
+        kernel + ncclAllReduce path instead."""
+        import torch.distributed as dist
+        handle = self.local.comm_mailbox(self.world, 8 + 2 * self.m)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        self.local.comm_connect(self.rank, self.world, b"".join(handles))
+        dist.barrier()
+        self._fused = True
 
     @staticmethod
     def _nan0(x):
@@ -69,6 +84,8 @@ class Session(object):
     def nll_grad(self, theta):
         """Global (all ranks) value and gradient of the REML objective at theta."""
         theta = np.asarray(theta, dtype=np.float64)
+        if self._fused:
+            return self.local.nll_grad(theta)        # the kernel epilogue already added all ranks
         if self._cuda_reduce is not None:
             buf = self._cuda_reduce
             with self._torch.cuda.stream(self._stream):

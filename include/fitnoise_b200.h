@@ -114,6 +114,18 @@ int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev);
 /* Model.get_weights (fitnoise.py:399-404): 1/sigma2, n x m. */
 int fn_weights(fn_handle* h, const double* theta, int32_t P, double* weights);
 
+/* Fused multi-GPU all-reduce (one process per GPU on one NVLink/NVSwitch box).  After these two
+ * calls fn_nll_grad returns the sums over ALL ranks: the last CTA of each rank's kernel stores its
+ * sums into every peer's mailbox (device memory mapped with CUDA IPC, plain stores over NVLink),
+ * waits for the peers' flags and adds the slots in rank order -- compute, collective and hand-over
+ * to the host in one kernel.  Every rank must then call fn_nll_grad the same number of times.
+ *   fn_comm_mailbox  allocates this rank's mailbox for `world` senders of up to max_values doubles
+ *                    and returns its 64-byte CUDA IPC handle for the caller to all-gather;
+ *   fn_comm_connect  takes the world x 64 bytes of gathered handles (rank order). */
+int fn_comm_mailbox(fn_handle* h, int32_t world, int32_t max_values, void* ipc_handle_out);
+int fn_comm_connect(fn_handle* h, int32_t rank, int32_t world, const void* ipc_handles);
+int fn_comm_disconnect(fn_handle* h);
+
 /* Tuning knobs for experiments (0 = automatic): lanes per gene, threads per CTA, pipeline stages,
  * CTAs per SM. */
 int fn_set_tuning(fn_handle* h, int32_t lpg, int32_t threads, int32_t stages, int32_t ctas_per_sm);
