@@ -25,6 +25,7 @@ EXPORTS = [
     "fn_upload", "fn_upload_dev", "fn_nll_grad", "fn_nll_grad_dev", "fn_per_gene", "fn_noise_stats",
     "fn_coef", "fn_test", "fn_bh", "fn_bh_dev", "fn_weights", "fn_set_tuning", "fn_launch_count",
     "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
+    "fn_test_bh", "fn_coef_fetch",
 ]
 
 
@@ -89,6 +90,8 @@ def load_library():
     lib.fn_coef.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p,
                             c_double_p, c_double_p, c_double_p]
     lib.fn_test.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.fn_test_bh.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.fn_coef_fetch.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
     lib.fn_bh.argtypes = [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p]
     lib.fn_bh_dev.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
     lib.fn_weights.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p]
@@ -206,15 +209,33 @@ class Engine(object):
 
     # ---- coefficients and tests -----------------------------------------------------------
     def coef(self, theta, design, want_covar=True):
+        """GLS coefficients.  With want_covar=False the covariances and posterior df stay on the
+        device (fetch them later with coef_fetch); returns (coef, covar|None, dfpost|None)."""
         theta = _f64(theta).reshape(-1)
         design = _f64(design)
         c = design.shape[1]
         coef = np.empty((self.n, c))
         covar = np.empty((self.n, c, c)) if want_covar else None
-        dfpost = np.empty(self.n)
+        dfpost = np.empty(self.n) if want_covar else None
         self._check(self._lib.fn_coef(self._h, _dp(theta), len(theta), c, _dp(design), _dp(coef),
                                       _dp(covar), _dp(dfpost)))
+        self._coef_c = c
         return coef, covar, dfpost
+
+    def coef_fetch(self):
+        """Covariances (n x c x c) and posterior df (n) of the last coef()."""
+        c = self._coef_c
+        covar, dfpost = np.empty((self.n, c, c)), np.empty(self.n)
+        self._check(self._lib.fn_coef_fetch(self._h, None, _dp(covar), _dp(dfpost)))
+        return covar, dfpost
+
+    def test_bh(self, contrasts):
+        """test() and the BH adjustment of its p-values in one call (p stays on the device)."""
+        contrasts = _f64(contrasts)
+        kc = contrasts.shape[1]
+        contrasted, p, q = np.empty((self.n, kc)), np.empty(self.n), np.empty(self.n)
+        self._check(self._lib.fn_test_bh(self._h, kc, _dp(contrasts), _dp(contrasted), _dp(p), _dp(q)))
+        return contrasted, p, q
 
     def test(self, contrasts, want_covar=False):
         contrasts = _f64(contrasts)
@@ -270,6 +291,23 @@ class Engine(object):
 
     def launch_count(self):
         return int(self._lib.fn_launch_count(self._h))
+
+
+_POOL = {}
+
+
+def acquire_engine(device):
+    """An idle engine of this device from the process-wide pool, or a new one.  Creating a handle
+    (stream, events, pinned buffers) and destroying it costs tens of milliseconds; fits reuse them."""
+    free = _POOL.setdefault(int(device), [])
+    if free:
+        return free.pop()
+    return Engine(int(device))
+
+
+def release_engine(engine):
+    if engine is not None and getattr(engine, "_h", None):
+        _POOL.setdefault(engine.device, []).append(engine)
 
 
 _DEFAULT = {}

@@ -6,7 +6,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <map>
+#include <mutex>
+#include <utility>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/fitnoise_b200.h"
@@ -48,6 +51,12 @@ struct Geom {
     long long n_tiles;
 };
 
+// grow-only device allocation: re-uploading data of the same shape costs no cudaMalloc/cudaFree
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
 struct fn_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -63,9 +72,18 @@ struct fn_handle {
     int width = 0;
     double cst_sum = 0.0;
 
+    // active arrays (point into the buffers below, or nullptr when the model does not use them)
     double *y = nullptr, *aux = nullptr, *gs = nullptr, *cst = nullptr, *avg = nullptr;
     uint8_t* status = nullptr;
     double *xn = nullptr, *xc = nullptr;
+    DevBuf b_y, b_aux, b_gs, b_cst, b_avg, b_status, b_xn, b_xc, b_tab, b_pg_score, b_pg_d2, b_pg_p, b_noise_p,
+        b_coef, b_covar, b_dfpost, b_xcoef, b_rinv;
+    size_t tab_host_cap = 0;
+    // pinned staging for uploads from pageable host memory
+    static const int kStageWorkers = 8;
+    void* stage_buf[2 * kStageWorkers] = {nullptr};
+    cudaEvent_t stage_ev[2 * kStageWorkers] = {nullptr};
+    size_t stage_bytes = 0;
 
     double* partials = nullptr;
     size_t partials_cap = 0;
@@ -91,7 +109,6 @@ struct fn_handle {
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
-    std::map<const void*, size_t> smem_set;
 
     unsigned long long host_seq = 0;   // completion-flag sequence of the pinned result buffer
     // fused multi-GPU exchange (fn_comm_*): mailboxes mapped with CUDA IPC
@@ -107,14 +124,40 @@ static void dfree(T*& p) {
     p = nullptr;
 }
 
+static cudaError_t ensure_buf(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
+    if (e == cudaSuccess) b.cap = bytes ? bytes : 16;
+    return e;
+}
+
+// forget the uploaded data (buffers stay allocated for the next upload)
 static void release_data(fn_handle* h) {
-    dfree(h->y); dfree(h->aux); dfree(h->gs); dfree(h->cst); dfree(h->avg); dfree(h->status);
-    dfree(h->xn); dfree(h->xc); dfree(h->tab_dev);
-    dfree(h->pg_score); dfree(h->pg_d2); dfree(h->noise_p); dfree(h->pg_p);
-    dfree(h->coef); dfree(h->covar); dfree(h->dfpost); dfree(h->x_coef); dfree(h->rinv_dev);
-    if (h->tab_host) { cudaFreeHost(h->tab_host); h->tab_host = nullptr; }
+    h->y = h->aux = h->gs = h->cst = h->avg = nullptr;
+    h->status = nullptr;
+    h->xn = h->xc = nullptr;
+    h->tab_dev = nullptr;
+    h->pg_score = h->pg_d2 = h->noise_p = nullptr;
+    h->pg_p = nullptr;
+    h->coef = h->covar = h->dfpost = h->x_coef = h->rinv_dev = nullptr;
     h->loaded = false;
     h->coef_c = 0;
+}
+
+static void free_buffers(fn_handle* h) {
+    release_data(h);
+    DevBuf* all[] = {&h->b_y, &h->b_aux, &h->b_gs, &h->b_cst, &h->b_avg, &h->b_status, &h->b_xn, &h->b_xc, &h->b_tab,
+                     &h->b_pg_score, &h->b_pg_d2, &h->b_pg_p, &h->b_noise_p, &h->b_coef, &h->b_covar, &h->b_dfpost,
+                     &h->b_xcoef, &h->b_rinv};
+    for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    if (h->tab_host) { cudaFreeHost(h->tab_host); h->tab_host = nullptr; h->tab_host_cap = 0; }
+    for (int i = 0; i < 2 * fn_handle::kStageWorkers; ++i) {
+        if (h->stage_buf[i]) { cudaFreeHost(h->stage_buf[i]); h->stage_buf[i] = nullptr; }
+        if (h->stage_ev[i]) { cudaEventDestroy(h->stage_ev[i]); h->stage_ev[i] = nullptr; }
+    }
+    h->stage_bytes = 0;
 }
 
 extern "C" const char* fn_last_error(void) { return g_error.c_str(); }
@@ -167,7 +210,7 @@ extern "C" int fn_destroy(fn_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     fn_comm_disconnect(h);
-    release_data(h);
+    free_buffers(h);
     dfree(h->partials); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
     if (h->out_host) cudaFreeHost(h->out_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -238,13 +281,20 @@ static GeomParams geom_params(const fn_handle* h, const Geom& g) {
     return gp;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function in the device's
+// context, shared by every handle: remember the largest value set per (device, kernel) and only
+// ever raise it.
+static std::mutex g_smem_mutex;
+static std::map<std::pair<int, const void*>, size_t> g_smem_set;
+
 template <class K>
 static int set_smem(fn_handle* h, K kernel, size_t bytes) {
-    const void* key = (const void*)kernel;
-    auto it = h->smem_set.find(key);
-    if (it != h->smem_set.end() && it->second >= bytes) return 0;
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
+    const std::pair<int, const void*> key(h->device, (const void*)kernel);
+    auto it = g_smem_set.find(key);
+    if (it != g_smem_set.end() && it->second >= bytes) return 0;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    h->smem_set[key] = bytes;
+    g_smem_set[key] = bytes;
     return 0;
 }
 
@@ -324,6 +374,49 @@ __global__ void controls_to_status_kernel(long long n, long long n_pad, const ui
     status[i] = (i < n && controls && controls[i]) ? 2 : 0;
 }
 
+// Host -> device copy of a large array.  From pinned memory: one cudaMemcpyAsync.  From pageable
+// memory (a plain numpy array) the runtime's own staging runs at the speed of ONE memcpy thread
+// (~10 GB/s); here kStageWorkers threads each copy every kStageWorkers-th 8 MB chunk into their own
+// pair of pinned buffers and queue the DMA, so the host copies and the PCIe transfers overlap.
+static int copy_h2d(fn_handle* h, void* dst, const void* src, size_t bytes) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, src);
+    if (e != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
+    const size_t chunk = 8u << 20;
+    if (attr.type != cudaMemoryTypeUnregistered || bytes < 4 * chunk) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    const int W = fn_handle::kStageWorkers;
+    if (h->stage_bytes != chunk) {
+        for (int i = 0; i < 2 * W; ++i) {
+            CUDA_TRY(cudaHostAlloc(&h->stage_buf[i], chunk, cudaHostAllocDefault));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+        }
+        h->stage_bytes = chunk;
+    }
+    const size_t nchunks = (bytes + chunk - 1) / chunk;
+    std::vector<std::thread> workers;
+    std::vector<int> status(W, 0);
+    for (int w = 0; w < W; ++w) {
+        workers.emplace_back([=, &status]() {
+            if (cudaSetDevice(h->device) != cudaSuccess) { status[w] = 1; return; }
+            int turn = 0;
+            for (size_t c = w; c < nchunks; c += W, turn ^= 1) {
+                const int slot = 2 * w + turn;
+                const size_t off = c * chunk, len = (off + chunk <= bytes) ? chunk : bytes - off;
+                if (c >= (size_t)(2 * W) && cudaEventSynchronize(h->stage_ev[slot]) != cudaSuccess) { status[w] = 1; return; }
+                memcpy(h->stage_buf[slot], (const char*)src + off, len);
+                if (cudaMemcpyAsync((char*)dst + off, h->stage_buf[slot], len, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                    cudaEventRecord(h->stage_ev[slot], h->stream) != cudaSuccess) { status[w] = 1; return; }
+            }
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int w = 0; w < W; ++w) if (status[w]) return fail(FN_ERR_CUDA, "staged host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, const double* aux,
                          const fn_family* family, const uint8_t* controls, int32_t c_noise,
                          const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
@@ -364,22 +457,28 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     h->n_pad = (n + FN_ROW_PAD - 1) / FN_ROW_PAD * FN_ROW_PAD;
     const size_t rows = (size_t)h->n_pad * m * sizeof(double);
     const size_t used = (size_t)n * m * sizeof(double);
-    CUDA_TRY(cudaMalloc(&h->y, rows));
+    CUDA_TRY(ensure_buf(h->b_y, rows));
+    h->y = (double*)h->b_y.p;
     CUDA_TRY(cudaMemsetAsync((char*)h->y + used, 0xFF, rows - used, h->stream));       // NaN padding rows
-    CUDA_TRY(cudaMemcpyAsync(h->y, y, used, kind, h->stream));
+    if (kind == cudaMemcpyHostToDevice) { int rcc = copy_h2d(h, h->y, y, used); if (rcc) return rcc; }
+    else CUDA_TRY(cudaMemcpyAsync(h->y, y, used, kind, h->stream));
     if (aux) {
-        CUDA_TRY(cudaMalloc(&h->aux, rows));
+        CUDA_TRY(ensure_buf(h->b_aux, rows));
+        h->aux = (double*)h->b_aux.p;
         CUDA_TRY(cudaMemsetAsync((char*)h->aux + used, 0xFF, rows - used, h->stream));
-        CUDA_TRY(cudaMemcpyAsync(h->aux, aux, used, kind, h->stream));
+        if (kind == cudaMemcpyHostToDevice) { int rcc = copy_h2d(h, h->aux, aux, used); if (rcc) return rcc; }
+        else CUDA_TRY(cudaMemcpyAsync(h->aux, aux, used, kind, h->stream));
     }
-    CUDA_TRY(cudaMalloc(&h->status, h->n_pad));
-    CUDA_TRY(cudaMalloc(&h->cst, h->n_pad * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->avg, h->n_pad * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_status, h->n_pad));
+    CUDA_TRY(ensure_buf(h->b_cst, h->n_pad * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_avg, h->n_pad * sizeof(double)));
+    h->status = (uint8_t*)h->b_status.p; h->cst = (double*)h->b_cst.p; h->avg = (double*)h->b_avg.p;
     CUDA_TRY(cudaMemsetAsync(h->cst, 0, h->n_pad * sizeof(double), h->stream));
     const bool patseq = fam.kind == KIND_PATSEQ;
     const bool want_gs = patseq && (!fam.tail_own || fam.v3);
     if (want_gs) {
-        CUDA_TRY(cudaMalloc(&h->gs, h->n_pad * sizeof(double)));
+        CUDA_TRY(ensure_buf(h->b_gs, h->n_pad * sizeof(double)));
+        h->gs = (double*)h->b_gs.p;
         CUDA_TRY(cudaMemsetAsync(h->gs, 0, h->n_pad * sizeof(double), h->stream));
     }
     {
@@ -398,12 +497,18 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
         controls_to_status_kernel<<<(unsigned)((h->n_pad + tb - 1) / tb), tb, 0, h->stream>>>(n, h->n_pad, ctl_dev, h->status);
         ++h->launches;
     }
-    CUDA_TRY(cudaMalloc(&h->xn, (size_t)m * width * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->xc, (size_t)m * width * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_xn, (size_t)m * width * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_xc, (size_t)m * width * sizeof(double)));
+    h->xn = (double*)h->b_xn.p; h->xc = (double*)h->b_xc.p;
     CUDA_TRY(cudaMemcpyAsync(h->xn, dn.q.data(), (size_t)m * width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->xc, dc.q.data(), (size_t)m * width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMalloc(&h->tab_dev, 2 * (size_t)m * sizeof(double)));
-    CUDA_TRY(cudaHostAlloc(&h->tab_host, 2 * (size_t)m * sizeof(double), cudaHostAllocDefault));
+    CUDA_TRY(ensure_buf(h->b_tab, 2 * (size_t)m * sizeof(double)));
+    h->tab_dev = (double*)h->b_tab.p;
+    if (h->tab_host_cap < 2 * (size_t)m * sizeof(double)) {
+        if (h->tab_host) cudaFreeHost(h->tab_host);
+        CUDA_TRY(cudaHostAlloc(&h->tab_host, 2 * (size_t)m * sizeof(double), cudaHostAllocDefault));
+        h->tab_host_cap = 2 * (size_t)m * sizeof(double);
+    }
 
     // K1
     Geom g;
@@ -507,9 +612,10 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     rc = ensure_reduce(h, g.grid, nacc);
     if (rc) return rc;
     if (per_gene && !h->pg_score) {
-        CUDA_TRY(cudaMalloc(&h->pg_score, h->n * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->pg_d2, h->n * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->pg_p, h->n * sizeof(int)));
+        CUDA_TRY(ensure_buf(h->b_pg_score, h->n * sizeof(double)));
+        CUDA_TRY(ensure_buf(h->b_pg_d2, h->n * sizeof(double)));
+        CUDA_TRY(ensure_buf(h->b_pg_p, h->n * sizeof(int)));
+        h->pg_score = (double*)h->b_pg_score.p; h->pg_d2 = (double*)h->b_pg_d2.p; h->pg_p = (int*)h->b_pg_p.p;
     }
     EvalParams ep;
     ep.g = geom_params(h, g);
@@ -632,7 +738,10 @@ extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, doub
     if (rc) return rc;
     rc = launch_eval(h, ts, true, false);
     if (rc) return rc;
-    if (!h->noise_p) CUDA_TRY(cudaMalloc(&h->noise_p, h->n * sizeof(double)));
+    if (!h->noise_p) {
+        CUDA_TRY(ensure_buf(h->b_noise_p, h->n * sizeof(double)));
+        h->noise_p = (double*)h->b_noise_p.p;
+    }
     const int tb = 128;
     noise_p_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(h->n, h->pg_d2, h->pg_p, ts.is_t, ts.v, h->noise_p);
     ++h->launches;
@@ -655,12 +764,13 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     const int m = h->m;
     Design d;
     if (!d.build(m, c, design)) return fail(FN_ERR_ARG, "coefficient design (%d x %d) is rank deficient", m, c);
-    dfree(h->coef); dfree(h->covar); dfree(h->dfpost); dfree(h->x_coef); dfree(h->rinv_dev);
-    CUDA_TRY(cudaMalloc(&h->coef, (size_t)h->n * c * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->covar, (size_t)h->n * c * c * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->dfpost, (size_t)h->n * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->x_coef, (size_t)m * d.width * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->rinv_dev, (size_t)c * c * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_coef, (size_t)h->n * c * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_covar, (size_t)h->n * c * c * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_dfpost, (size_t)h->n * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_xcoef, (size_t)m * d.width * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_rinv, (size_t)c * c * sizeof(double)));
+    h->coef = (double*)h->b_coef.p; h->covar = (double*)h->b_covar.p; h->dfpost = (double*)h->b_dfpost.p;
+    h->x_coef = (double*)h->b_xcoef.p; h->rinv_dev = (double*)h->b_rinv.p;
     CUDA_TRY(cudaMemcpyAsync(h->x_coef, d.q.data(), (size_t)m * d.width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->rinv_dev, d.rinv.data(), (size_t)c * c * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     h->coef_c = c;
@@ -695,7 +805,11 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     return 0;
 }
 
-extern "C" int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov, double* pval) {
+static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work);
+static size_t bh_work_bytes(int64_t n);
+
+static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov,
+                     double* pval, double* qval) {
     if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_test needs a preceding fn_coef");
     const int c = h->coef_c;
     if (kc < 1 || kc > FN_MAXC || !contrasts) return fail(FN_ERR_UNSUPPORTED, "contrasts has %d columns; 1..%d supported", kc, FN_MAXC);
@@ -704,14 +818,16 @@ extern "C" int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double
     const size_t nb_out = (size_t)h->n * kc * sizeof(double);
     const size_t nb_cc = ccov ? (size_t)h->n * kc * kc * sizeof(double) : 0;
     const size_t nb_p = (size_t)h->n * sizeof(double);
+    const size_t nb_bh = qval ? nb_p + 256 + bh_work_bytes(h->n) : 0;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    int rc = ensure_scratch(h, up(nb_con) + up(nb_out) + up(nb_cc) + up(nb_p));
+    int rc = ensure_scratch(h, up(nb_con) + up(nb_out) + up(nb_cc) + up(nb_p) + up(nb_bh));
     if (rc) return rc;
     char* base = (char*)h->scratch_dev;
     double* d_con = (double*)base; base += up(nb_con);
     double* d_out = (double*)base; base += up(nb_out);
     double* d_cc = ccov ? (double*)base : nullptr; base += up(nb_cc);
-    double* d_p = (double*)base;
+    double* d_p = (double*)base; base += up(nb_p);
+    double* d_q = (double*)base; base += up(nb_p);
     CUDA_TRY(cudaMemcpyAsync(d_con, contrasts, nb_con, cudaMemcpyHostToDevice, h->stream));
     TestParams tp;
     tp.n = h->n; tp.c = c; tp.kc = kc; tp.is_t = h->coef_is_t;
@@ -724,6 +840,31 @@ extern "C" int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double
     if (contrasted) CUDA_TRY(cudaMemcpyAsync(contrasted, d_out, nb_out, cudaMemcpyDeviceToHost, h->stream));
     if (ccov) CUDA_TRY(cudaMemcpyAsync(ccov, d_cc, nb_cc, cudaMemcpyDeviceToHost, h->stream));
     if (pval) CUDA_TRY(cudaMemcpyAsync(pval, d_p, nb_p, cudaMemcpyDeviceToHost, h->stream));
+    if (qval) {
+        rc = bh_run(h, h->n, d_p, d_q, base);          // p never leaves the device between test and BH
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(qval, d_q, nb_p, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov, double* pval) {
+    return test_core(h, kc, contrasts, contrasted, ccov, pval, nullptr);
+}
+
+extern "C" int fn_test_bh(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* pval, double* qval) {
+    if (!qval) return fail(FN_ERR_ARG, "fn_test_bh: qval is NULL");
+    return test_core(h, kc, contrasts, contrasted, nullptr, pval, qval);
+}
+
+extern "C" int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* dfpost) {
+    if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_coef_fetch needs a preceding fn_coef");
+    const int c = h->coef_c;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (coef) CUDA_TRY(cudaMemcpyAsync(coef, h->coef, (size_t)h->n * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (covar) CUDA_TRY(cudaMemcpyAsync(covar, h->covar, (size_t)h->n * c * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (dfpost) CUDA_TRY(cudaMemcpyAsync(dfpost, h->dfpost, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -761,20 +902,25 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
     uint32_t* idx1 = (uint32_t*)work; work += up(n * 4);
     uint32_t* hist = (uint32_t*)work; work += up((size_t)256 * nblocks * 4);
     double* chunk_min = (double*)work; work += up((size_t)nblocks * 8);
-    double* carry = (double*)work;
+    double* carry = (double*)work; work += up((size_t)nblocks * 8);
+    uint32_t* seg = (uint32_t*)work;
+    const long long hist_total = (long long)256 * nblocks;
+    const int nseg = (int)((hist_total + BH_SEG - 1) / BH_SEG);
     bh_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, p_dev, keys0, idx0);
     ++h->launches;
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = 8 * pass;
         bh_hist_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, shift, hist, nblocks);
-        bh_scan_kernel<<<1, 1024, 0, h->stream>>>(hist, (long long)256 * nblocks);
+        bh_segsum_kernel<<<nseg, BH_THREADS, 0, h->stream>>>(hist, hist_total, seg);
+        bh_segscan_kernel<<<1, 1024, 0, h->stream>>>(seg, nseg);
+        bh_segapply_kernel<<<nseg, BH_THREADS, 0, h->stream>>>(hist, hist_total, seg);
         bh_scatter_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, keys1, idx1, shift, hist, nblocks);
-        h->launches += 3;
+        h->launches += 5;
         std::swap(keys0, keys1);
         std::swap(idx0, idx1);
     }
     bh_chunkmin_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, chunk_min);
-    bh_carry_kernel<<<1, 32, 0, h->stream>>>(nblocks, chunk_min, carry);
+    bh_carry_kernel<<<(nblocks + 127) / 128, 128, 0, h->stream>>>(nblocks, chunk_min, carry);
     bh_finish_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, carry, q_dev);
     h->launches += 3;
     CUDA_TRY(cudaGetLastError());
@@ -784,7 +930,8 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
 static size_t bh_work_bytes(int64_t n) {
     const size_t nblocks = (n + BH_CHUNK - 1) / BH_CHUNK;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return 2 * up(n * 8) + 2 * up(n * 4) + up(256 * nblocks * 4) + 2 * up(nblocks * 8);
+    const size_t nseg = (256 * nblocks + BH_SEG - 1) / BH_SEG;
+    return 2 * up(n * 8) + 2 * up(n * 4) + up(256 * nblocks * 4) + 2 * up(nblocks * 8) + up(nseg * 4);
 }
 
 extern "C" int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev) {

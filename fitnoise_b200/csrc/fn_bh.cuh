@@ -42,23 +42,87 @@ __global__ void __launch_bounds__(BH_THREADS) bh_hist_kernel(long long n, const 
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of hist (256 * nblocks entries, digit-major) in place; one CTA
-__global__ void __launch_bounds__(1024) bh_scan_kernel(uint32_t* hist, long long total) {
-    __shared__ uint32_t part[1024];
-    const long long per = (total + blockDim.x - 1) / blockDim.x;
-    const long long lo = (long long)threadIdx.x * per;
-    const long long hi = lo + per < total ? lo + per : total;
-    uint32_t s = 0;
-    for (long long i = lo; i < hi; ++i) s += hist[i];
-    part[threadIdx.x] = s;
+// Exclusive scan of hist (256 * nblocks entries, digit-major) in place, in three small launches:
+// per-segment sums, a one-CTA scan of the segment sums, per-segment scan with the segment's offset.
+#define BH_SEG (BH_THREADS * BH_ITEMS)
+
+__device__ __forceinline__ uint32_t bh_block_exclusive_scan(uint32_t v, uint32_t* warp_tot /* shared, >= 32 */, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < (int)blockDim.x; ++i) { const uint32_t t = part[i]; part[i] = run; run += t; }
+    if (warp == 0) {
+        uint32_t w = lane < nwarp ? warp_tot[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, off);
+            if (lane >= off) winc += t;
+        }
+        warp_tot[lane] = winc - w;                 // exclusive offset of each warp
+        if (lane == 31) warp_tot[32] = winc;       // block total
     }
     __syncthreads();
-    uint32_t run = part[threadIdx.x];
-    for (long long i = lo; i < hi; ++i) { const uint32_t t = hist[i]; hist[i] = run; run += t; }
+    total = warp_tot[32];
+    return warp_tot[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(BH_THREADS) bh_segsum_kernel(const uint32_t* hist, long long total, uint32_t* seg_sum) {
+    __shared__ uint32_t red[BH_THREADS];
+    const long long base = (long long)blockIdx.x * BH_SEG;
+    uint32_t s = 0;
+    for (int k = 0; k < BH_ITEMS; ++k) {
+        const long long i = base + k * BH_THREADS + threadIdx.x;
+        if (i < total) s += hist[i];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = BH_THREADS / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg_sum[blockIdx.x] = red[0];
+}
+
+// one CTA of 1024 threads: exclusive scan of up to 1024 * k segment sums
+__global__ void __launch_bounds__(1024) bh_segscan_kernel(uint32_t* seg_sum, int nseg) {
+    __shared__ uint32_t warp_tot[33];
+    uint32_t carry = 0;
+    for (int base = 0; base < nseg; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nseg ? seg_sum[i] : 0;
+        uint32_t total;
+        const uint32_t ex = bh_block_exclusive_scan(v, warp_tot, total);
+        if (i < nseg) seg_sum[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BH_THREADS) bh_segapply_kernel(uint32_t* hist, long long total, const uint32_t* seg_off) {
+    __shared__ uint32_t warp_tot[33];
+    const long long base = (long long)blockIdx.x * BH_SEG + (long long)threadIdx.x * BH_ITEMS;
+    uint32_t v[BH_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < BH_ITEMS; ++k) {
+        const long long i = base + k;
+        v[k] = i < total ? hist[i] : 0;
+        s += v[k];
+    }
+    uint32_t block_total;
+    uint32_t run = seg_off[blockIdx.x] + bh_block_exclusive_scan(s, warp_tot, block_total);
+#pragma unroll
+    for (int k = 0; k < BH_ITEMS; ++k) {
+        const long long i = base + k;
+        if (i < total) hist[i] = run;
+        run += v[k];
+    }
 }
 
 // stable scatter of CTA b's chunk using the scanned histogram as per-(digit, CTA) base offsets
@@ -124,11 +188,13 @@ __global__ void __launch_bounds__(BH_THREADS) bh_chunkmin_kernel(long long n, co
     if (threadIdx.x == 0) chunk_min[blockIdx.x] = red[0];
 }
 
-// carry[b] = min over chunks > b (inf for the last); one CTA, sequential in one thread per segment
+// carry[b] = min over chunks > b (inf for the last); thread b scans the later chunk minima
 __global__ void bh_carry_kernel(int nchunks, const double* chunk_min, double* carry) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nchunks) return;
     double run = INFINITY;
-    for (int b = nchunks - 1; b >= 0; --b) { carry[b] = run; run = fmin(run, chunk_min[b]); }
+    for (int i = b + 1; i < nchunks; ++i) run = fmin(run, chunk_min[i]);
+    carry[b] = run;
 }
 
 // q_(r) = min(1, suffix-min), scattered back to gene order

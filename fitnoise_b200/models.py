@@ -64,6 +64,18 @@ class _LazyDists(object):
         return (self._make(i) for i in range(self._n))
 
 
+class _Lazy(object):
+    """A value computed on first use."""
+
+    def __init__(self, compute):
+        self._compute, self._value = compute, None
+
+    def get(self):
+        if self._compute is not None:
+            self._value, self._compute = self._compute(), None
+        return self._value
+
+
 def _optimize(value_grad, initial, bounds, verbose):
     """The reference's driver loop (fitnoise.py:143-158): L-BFGS-B with analytic gradient and
     ftol = gtol = 1e-12, restarted from the optimum until it moves by less than 1e-6."""
@@ -161,7 +173,7 @@ class Model(Withable):
         if control_design is None:
             control_design = np.ones((m, 1))
         if controls is None:
-            controls = [False] * n
+            controls = np.zeros(n, dtype="bool")          # the reference builds [False]*n (:217)
         control_design = as_matrix(control_design)
         controls = as_vector(controls, "bool")
         assert design.shape[0] == m and control_design.shape[0] == m and len(controls) == n
@@ -224,7 +236,8 @@ class Model(Withable):
             _theta=theta,
             _evaluations=evaluations[0],
         )
-        fitted.noise_dists = _LazyDists(n, lambda i: fitted._get_dist(param, fitted._aux_row(i)))
+        # (closes over `result`, not `fitted`: no reference cycle through the fit result)
+        fitted.noise_dists = _LazyDists(n, lambda i: result._get_dist(param, result._aux_row(i)))
         return fitted
 
     # ---- fit_coef (fitnoise.py:294-347) ----------------------------------------------------
@@ -233,10 +246,14 @@ class Model(Withable):
             design = self.noise_design
         design = as_matrix(design)
         token = object()
-        coef, covar, dfpost = self._session.coef(self._theta, design, token)
+        session, theta = self._session, self._theta
+        coef = session.coef(theta, design, token)
         is_t = self._family(self.data.y.shape[1]).dist != _native.DIST_NORMAL
+        # the c x c posterior covariances (and df) are fetched from the GPU only if somebody looks
+        posterior = _Lazy(lambda: session.coef_covar(theta, design, token))
 
         def make(i):
+            covar, dfpost = posterior.get()
             if covar[i, 0, 0] != covar[i, 0, 0]:
                 return None
             if is_t:
@@ -244,7 +261,15 @@ class Model(Withable):
             return Mvnormal(coef[i], covar[i])
 
         return self._with(design=design, coef=coef, coef_dists=_LazyDists(len(coef), make),
-                          _coef_covar=covar, _coef_df=dfpost, _coef_token=token)
+                          _coef_posterior=posterior, _coef_token=token)
+
+    @property
+    def _coef_covar(self):
+        return self._coef_posterior.get()[0]
+
+    @property
+    def _coef_df(self):
+        return self._coef_posterior.get()[1]
 
     # ---- fit (fitnoise.py:350-365) ---------------------------------------------------------
     def fit(self, data, design=None, noise_design=None, control_design=None, controls=None,
@@ -269,13 +294,13 @@ class Model(Withable):
         session = self._session
         if session.coef_token is not self._coef_token:        # another fit_coef ran on this session since
             session.coef(self._theta, self.design, self._coef_token)
-        contrasted, p_values = session.test(contrasts)
-        q_values = session.bh(p_values)
+        contrasted, p_values, q_values = session.test(contrasts)
 
-        covar, mean, dfpost = self._coef_covar, self.coef, self._coef_df
+        posterior, mean = self._coef_posterior, self.coef
         is_t = self._family(self.data.y.shape[1]).dist != _native.DIST_NORMAL
 
         def make(i):
+            covar, dfpost = posterior.get()
             if covar[i, 0, 0] != covar[i, 0, 0]:
                 return None
             base = Mvt(mean[i], covar[i], dfpost[i]) if is_t else Mvnormal(mean[i], covar[i])

@@ -2,10 +2,18 @@
 that make the per-rank results global.  The numerical work is all in the CUDA library
 (``_native.Engine``); this module only shards, reduces and gathers."""
 import os
+import weakref
 
 import numpy as np
 
 from . import _native, parallel
+
+
+def _give_back(engine, pooled):
+    if pooled:
+        _native.release_engine(engine)
+    elif hasattr(engine, "close"):
+        engine.close()
 
 
 class Session(object):
@@ -24,7 +32,12 @@ class Session(object):
         self._cuda_reduce = None
         if engine_factory is None:
             engine_factory = self._cuda_engine
+        self._pooled = False
         self.local = engine_factory()
+        # Return the engine when this session goes away.  weakref.finalize keeps the engine
+        # reachable until then, so that a garbage-collected cycle containing the session can never
+        # run the engine's own finaliser first.
+        self._finalizer = weakref.finalize(self, _give_back, self.local, self._pooled)
         sl = slice(self.lo, self.hi)
         info = self.local.upload(
             y[sl], None if aux is None else np.asarray(aux, dtype=np.float64)[sl], family,
@@ -73,12 +86,13 @@ class Session(object):
                 self._cuda_reduce = torch.zeros(self.P + 3, dtype=torch.float64, device="cuda")
             self._stream.synchronize()
             return _native.Engine(torch.cuda.current_device(), self._stream.cuda_stream)
-        return _native.Engine(int(os.environ.get("LOCAL_RANK", "0")))
+        self._pooled = True
+        return _native.acquire_engine(int(os.environ.get("LOCAL_RANK", "0")))
 
     def close(self):
-        if self.local is not None and hasattr(self.local, "close"):
-            self.local.close()
+        """Give the GPU state back: pooled engines are kept (with their buffers) for the next fit."""
         self.local = None
+        self._finalizer()
 
     # ---- likelihood -----------------------------------------------------------------------
     def nll_grad(self, theta):
@@ -110,14 +124,24 @@ class Session(object):
 
     # ---- coefficients, tests --------------------------------------------------------------
     def coef(self, theta, design, token):
-        coef, covar, dfpost = self.local.coef(theta, design)
+        """Coefficients now; their covariances and posterior df stay on the GPU until asked for."""
+        coef, _, _ = self.local.coef(theta, design, want_covar=False)
         self.coef_token = token
-        return (parallel.allgather_rows(coef, self.n), parallel.allgather_rows(covar, self.n),
-                parallel.allgather_rows(dfpost, self.n))
+        return parallel.allgather_rows(coef, self.n)
+
+    def coef_covar(self, theta, design, token):
+        if self.coef_token is not token:              # another fit_coef ran on this session since
+            self.coef(theta, design, token)
+        covar, dfpost = self.local.coef_fetch()
+        return parallel.allgather_rows(covar, self.n), parallel.allgather_rows(dfpost, self.n)
 
     def test(self, contrasts):
+        """contrasted, p_values, q_values (BH over ALL genes)."""
+        if self.world == 1:
+            return self.local.test_bh(contrasts)      # p never leaves the device before the adjustment
         contrasted, _, p = self.local.test(contrasts)
-        return parallel.allgather_rows(contrasted, self.n), parallel.allgather_rows(p, self.n)
+        contrasted, p = parallel.allgather_rows(contrasted, self.n), parallel.allgather_rows(p, self.n)
+        return contrasted, p, self.bh(p)
 
     def bh(self, p):
         # every rank holds the full p vector after the gather and adjusts it on its own GPU

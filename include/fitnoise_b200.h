@@ -106,6 +106,14 @@ int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, const doubl
  * contrasted: n x kc; ccov: n x kc x kc or NULL; pval: n. */
 int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov, double* pval);
 
+/* fn_test followed by Benjamini-Hochberg over this handle's genes without p leaving the device
+ * (Model.test computes q_values right after p_values, fitnoise.py:395). */
+int fn_test_bh(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* pval, double* qval);
+
+/* Copy the device-resident results of the last fn_coef to the host (any pointer may be NULL): lets a
+ * caller take `coef` at once and the c x c covariances only if somebody asks for coef_dists. */
+int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* dfpost);
+
 /* p_adjust.fdr (p_adjust.py:3-21): Benjamini-Hochberg q-values; NaN p counts as 1.0. */
 int fn_bh(fn_handle* h, int64_t n, const double* p, double* q);
 /* device-resident form: p_dev, q_dev are device pointers of n doubles */

@@ -153,7 +153,16 @@ class HostEvaluator(object):
         if rc != 0:
             raise RuntimeError("hc_coef failed with %d" % rc)
         self._coef = (coef, covar, dfp, int(self.family.dist != 0))
+        if not want_covar:
+            return coef, None, None
         return coef, covar, dfp
+
+    def coef_fetch(self):
+        return self._coef[1], self._coef[2]
+
+    def test_bh(self, contrasts):
+        con, _, p = self.test(contrasts)
+        return con, p, self.bh(p)
 
     def test(self, contrasts, want_covar=False):
         coef, covar, dfp, is_t = self._coef

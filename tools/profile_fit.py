@@ -1,0 +1,41 @@
+"""cProfile of a warm fit + test through the public API (host-side overheads).
+
+    python tools/profile_fit.py <config> [model]
+"""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import fitnoise_b200 as fitnoise  # noqa: E402
+from helpers import synthetic  # noqa: E402
+
+config = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+s = synthetic(config)
+model = sys.argv[2] if len(sys.argv) > 2 else s["model"]
+kw = {k: s[k] for k in ("controls", "control_design") if k in s}
+data = fitnoise.Dataset(s["y"], s["context"])
+
+
+def run():
+    fitted = getattr(fitnoise, model)().fit(data, s["design"], **kw)
+    tested = fitted.test(**s["test"])
+    fitted._session.close()
+    return tested
+
+
+run()
+for _ in range(3):
+    t0 = time.perf_counter()
+    run()
+    print("warm fit+test: %.2f ms" % ((time.perf_counter() - t0) * 1000))
+pr = cProfile.Profile()
+pr.enable()
+run()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
