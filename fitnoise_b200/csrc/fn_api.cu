@@ -106,7 +106,7 @@ struct fn_handle {
 
     int tune_lpg = 0, tune_threads = 0, tune_stages = 0, tune_ctas = 0;
     int64_t launches = 0;
-    bool timing = false;
+    bool timing = false, timing_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
 
@@ -235,17 +235,27 @@ extern "C" int fn_set_tuning(fn_handle* h, int32_t lpg, int32_t threads, int32_t
 }
 extern "C" int64_t fn_launch_count(fn_handle* h) { return h ? h->launches : 0; }
 extern "C" int fn_set_timing(fn_handle* h, int32_t on) { if (!h) return FN_ERR_ARG; h->timing = on != 0; return 0; }
-extern "C" double fn_last_kernel_ms(fn_handle* h) { return h ? h->last_ms : 0.0; }
+extern "C" double fn_last_kernel_ms(fn_handle* h) {
+    if (!h) return 0.0;
+    if (h->timing_pending) {                    // events of the last timed evaluation kernel
+        float ms = 0;
+        if (cudaEventSynchronize(h->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess)
+            h->last_ms = ms;
+        h->timing_pending = false;
+    }
+    return h->last_ms;
+}
 
 // ------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------
-static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_bytes, Geom& g) {
+static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_bytes, Geom& g, int min_threads = 0) {
     const int m = h->m;
     int ctas = h->tune_ctas > 0 ? h->tune_ctas : 2;
     int threads = h->tune_threads > 0 ? h->tune_threads : 256;
     // small problems: more, smaller CTAs so that every SM gets work
     if (h->tune_threads == 0 && h->n < (int64_t)h->sm_count * 256) threads = 128;
+    if (threads < min_threads) threads = 256;      // per-sample column sums need one thread per sample
     const size_t budget = (h->smem_optin - 2048) / ctas;       // per CTA
     const size_t stage_target = 50 * 1024;
     int lpg = h->tune_lpg > 0 ? h->tune_lpg : 1;
@@ -605,7 +615,7 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     int threads_for_cols = 0;
     (void)threads_for_cols;
     const size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
-    int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g);
+    int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0);
     if (rc) return rc;
     if (inplace && m > g.threads) return fail(FN_ERR_UNSUPPORTED, "per-sample variance models need m <= threads per CTA (%d)", g.threads);
     const int nacc = eval_nacc(h);
@@ -647,7 +657,7 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
             eval_kernel<C, KIND_PATSEQ><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
         }
     });
-    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    if (h->timing) { CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->timing_pending = true; }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -675,14 +685,8 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
     if (rc) return rc;
     rc = launch_eval(h, ts, false, true);
     if (rc) return rc;
-    if (h->timing) CUDA_TRY(cudaStreamSynchronize(h->stream));
     rc = wait_result(h, h->host_seq, eval_nacc(h));
     if (rc) return rc;
-    if (h->timing) {
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        h->last_ms = ms;
-    }
     std::vector<double> out(P + 3);
     assemble(h, h->out_host, out.data());
     if (value) *value = out[0];

@@ -226,3 +226,113 @@ def test_full_size_properties():
         assert_close(v4, v_all + n * (m - 2) * np.log(2.0), 1e-11, what="scale equivariance")
     finally:
         e.close()
+
+
+def _random_case(rng, n, m, c, model):
+    design = np.concatenate([np.ones((m, 1)), rng.normal(size=(m, c - 1))], axis=1) if c > 1 else np.ones((m, 1))
+    y = rng.normal(size=(n, m)) * 1.5 + 10.0
+    y[rng.random((n, m)) < 0.05] = np.nan
+    aux = None
+    fam = getattr(fitnoise, model)()._family(m)
+    P = fam.theta_length()
+    if fam.kind == _native.KIND_PATSEQ:
+        aux = rng.poisson(15.0, size=(n, m)).astype(float)
+        aux[np.isnan(y)] = 0
+        y[aux == 0] = np.nan
+        theta = np.concatenate([[9.0] if fam.dist == 1 else [], rng.uniform(100, 300, fam.na), rng.uniform(1e-3, 5e-3, fam.nb)])
+    else:
+        if rng.random() < 0.5:
+            aux = np.exp(rng.normal(0, 0.4, size=(n, m)))
+            aux[rng.random((n, m)) < 0.02] = 0.0
+        theta = np.concatenate([[9.0] if fam.dist == 1 else [], rng.uniform(0.5, 2.5, fam.na)])
+    assert len(theta) == P
+    return y, aux, fam, design, theta
+
+
+SHAPES = [(1, 3, 1), (17, 1, 1), (5, 2, 2), (300, 5, 3), (1025, 7, 4), (333, 16, 5), (257, 33, 6),
+          (200, 48, 8), (64, 100, 2), (40, 250, 3), (2049, 12, 7)]
+SHAPE_MODELS = ["Model_t", "Model_normal", "Model_independent", "Model_t_per_sample", "Model_t_patseq",
+                "Model_t_v1_patseq", "Model_normal_patseq_v3", "Model_t_patseq_per_sample",
+                "Model_t_patseq_v1_per_sample"]
+
+
+@pytest.mark.parametrize("model", SHAPE_MODELS)
+def test_shapes_against_host_build(model):
+    """Every kernel over odd shapes (n = 1 ... 2049, m = 1 ... 250, c = 1 ... 8, ~5 % missing, zero
+    weights): the CUDA result against the host build of the same arithmetic (tests/hostcheck),
+    which test_host_math.py pins to the reference goldens."""
+    import hostcheck
+    rng = np.random.default_rng(abs(hash(model)) % 1000)
+    for n, m, c in SHAPES:
+        if c >= m and m > 1:
+            c = m - 1
+        if c > m:
+            c = m
+        y, aux, fam, design, theta = _random_case(rng, n, m, c, model)
+        coef_design = design
+        host = hostcheck.HostEvaluator()
+        host.upload(y, aux, fam, None, design)
+        e = _native.Engine(0)
+        try:
+            info = e.upload(y, aux, fam, None, design)
+            hs, hd, hp = host.per_gene(theta)
+            gs, gd, gp = e.per_gene(theta)
+            what = "%s n=%d m=%d c=%d" % (model, n, m, c)
+            assert_close(gs, hs, 1e-10, what=what + " score")
+            assert np.array_equal(gp, hp), what
+            hv, hg, hu, _ = host.nll_grad(theta)
+            gv, gg, gu, gb = e.nll_grad(theta)
+            assert gu == hu and gb == 0, what
+            if hu:
+                assert_close(gv, hv, 1e-11, what=what + " value")
+                assert_close(gg, hg, 1e-8, atol=1e-10 * max(abs(hv), 1.0), what=what + " grad")
+            hn, ha = host.noise_stats(theta)
+            gn, ga = e.noise_stats(theta)
+            assert_close(gn, hn, 1e-9, what=what + " noise p")
+            assert_close(ga, ha, 1e-12, what=what + " averages")
+            hc, hcov, hdf = host.coef(theta, coef_design)
+            gc, gcov, gdf = e.coef(theta, coef_design)
+            assert_close(gc, hc, 1e-9, atol=1e-9, what=what + " coef")
+            assert_close(gcov, hcov, 1e-9, atol=1e-12, what=what + " covar")
+            assert_close(gdf, hdf, 1e-12, what=what + " df")
+            contrasts = np.eye(c)[:, : min(c, 2)]
+            hcon, _, hpv = host.test(contrasts)
+            gcon, gpv, gq = e.test_bh(contrasts)
+            assert_close(gcon, hcon, 1e-9, atol=1e-9, what=what + " contrasts")
+            assert_close(gpv, hpv, 1e-8, what=what + " p")
+            assert np.array_equal(gq, oracle.fdr(gpv)), what + " q"
+            assert_close(e.weights(theta), host.weights(theta), 1e-12, what=what + " weights")
+        finally:
+            e.close()
+
+
+def test_degenerate_inputs():
+    """All-missing data, all-zero weights, a single gene: nothing contributes, nothing crashes."""
+    fam = fitnoise.Model_t()._family(6)
+    design = np.array([[1.0, 0.0]] * 3 + [[1.0, 1.0]] * 3)
+    e = _native.Engine(0)
+    try:
+        y = np.full((10, 6), np.nan)
+        info = e.upload(y, None, fam, None, design)
+        assert info.n_eligible == 0
+        v, g, used, bad = e.nll_grad([5.0, 1.0])
+        assert used == 0 and bad == 0 and v == 0.0 and np.all(g == 0.0)
+        score, d2, p = e.per_gene([5.0, 1.0])
+        assert np.all(np.isnan(score))
+        coef, covar, df = e.coef([5.0, 1.0], design)
+        assert np.all(np.isnan(coef))
+        con, pv, q = e.test_bh(np.array([[0.0], [1.0]]))
+        assert np.all(np.isnan(pv)) and np.all(q == 1.0)
+        y = np.random.default_rng(0).normal(size=(10, 6))
+        info = e.upload(y, np.zeros((10, 6)), fam, None, design)
+        assert info.n_eligible == 0
+        with pytest.raises(_native.NativeError):
+            e.nll_grad([5.0, -1.0])
+        with pytest.raises(_native.NativeError):
+            e.nll_grad([5.0])
+        with pytest.raises(_native.NativeError):
+            e.upload(y, None, fam, None, np.ones((6, 2)))          # rank-deficient design
+    finally:
+        e.close()
+    with pytest.raises(AssertionError):
+        fitnoise.Model_t().fit(np.zeros((3, 6)), np.ones((5, 1)))   # design rows != samples
