@@ -663,15 +663,17 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     return 0;
 }
 
-// raw accumulators -> [value, grad[P], n_used, n_bad]
-static void assemble(const fn_handle* h, const double* acc, double* out) {
+// raw accumulators -> [value, grad[P], n_used, n_bad].  `ta` = theta_a by sample: the PATSEQ kernels
+// return term a multiplied by theta_a(j).
+static void assemble(const fn_handle* h, const double* acc, const double* ta, double* out) {
     const Family& f = h->fam;
     const int m = h->m;
+    const bool scale_a = f.kind == KIND_PATSEQ;
     int at = 0;
     out[at++] = acc[ACC_VALUE];
     if (f.dist == DIST_T) out[at++] = acc[ACC_DV];
-    if (f.na == 1) out[at++] = acc[ACC_GA];
-    else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + j];
+    if (f.na == 1) out[at++] = scale_a ? acc[ACC_GA] / ta[0] : acc[ACC_GA];
+    else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = scale_a ? acc[ACC_FIXED + j] / ta[j] : acc[ACC_FIXED + j];
     if (f.nb == 1) out[at++] = acc[ACC_GB];
     else if (f.nb == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + m + j];
     out[at++] = acc[ACC_USED];
@@ -688,7 +690,7 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
     rc = wait_result(h, h->host_seq, eval_nacc(h));
     if (rc) return rc;
     std::vector<double> out(P + 3);
-    assemble(h, h->out_host, out.data());
+    assemble(h, h->out_host, ts.ta.data(), out.data());
     if (value) *value = out[0];
     if (grad) for (int i = 0; i < P; ++i) grad[i] = out[1 + i];
     if (n_used) *n_used = (int64_t)out[P + 1];
@@ -697,13 +699,14 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
 }
 
 // device-side assemble for the asynchronous (multi-GPU) form
-__global__ void assemble_kernel(const double* acc, double* out, Family f, int m, double cst_sum) {
+__global__ void assemble_kernel(const double* acc, double* out, Family f, int m, const double* ta) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const bool scale_a = f.kind == KIND_PATSEQ;
     int at = 0;
     out[at++] = acc[ACC_VALUE];
     if (f.dist == DIST_T) out[at++] = acc[ACC_DV];
-    if (f.na == 1) out[at++] = acc[ACC_GA];
-    else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + j];
+    if (f.na == 1) out[at++] = scale_a ? acc[ACC_GA] / ta[0] : acc[ACC_GA];
+    else if (f.na == m) for (int j = 0; j < m; ++j) out[at++] = scale_a ? acc[ACC_FIXED + j] / ta[j] : acc[ACC_FIXED + j];
     if (f.nb == 1) out[at++] = acc[ACC_GB];
     else if (f.nb == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + m + j];
     out[at++] = acc[ACC_USED];
@@ -717,7 +720,7 @@ extern "C" int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, dou
     if (rc) return rc;
     rc = launch_eval(h, ts, false, false);
     if (rc) return rc;
-    assemble_kernel<<<1, 32, 0, h->stream>>>(h->out_dev, out_dev, h->fam, h->m, h->cst_sum);
+    assemble_kernel<<<1, 32, 0, h->stream>>>(h->out_dev, out_dev, h->fam, h->m, h->tab_dev);
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     return 0;

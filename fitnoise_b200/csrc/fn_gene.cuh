@@ -620,17 +620,26 @@ FN_HD void eval_scale1(const EvalConst& ec, const GeneView& gv, const double* X,
     scale1_finish(ec, mid, cst, out);
 }
 
-// KIND_SCALE_PS / KIND_PATSEQ: general diagonal variance; two more sweeps over the gene's row
-// (residuals, then the per-sample gradient terms).  When a theta block is per-sample
-// (inplace_a / inplace_b) the per-sample gradient contribution is written over the sample's own
-// slot in the y (term a) / aux (term b) tile for the caller to column-sum; otherwise it is
-// accumulated into out.ga / out.gb.
+// KIND_SCALE_PS / KIND_PATSEQ: general diagonal variance.  Two sweeps over the gene's row in shared
+// memory:
+//   1. normal equations, sum_ret ln sigma2_j, k.  PATSEQ pays its one division per sample here and
+//      leaves w_j = 1/sigma2_j (0 for a dropped sample) in the sample's slot of the aux tile, so the
+//      second sweep needs neither a division nor rc_j:  U_j w_j = (1 - theta_b(j) T_j w_j) / theta_a(j).
+//   2. per-sample gradient terms  e~_j = 1/2 (1 - w_j h_j) - kappa w_j r_j^2  (kappa needs d2, which
+//      comes from the first sweep as y'Wy - b'beta, re-derived from residuals if that cancelled).
+// PATSEQ returns term a multiplied by theta_a(j) (saves a division per sample); whoever assembles
+// the gradient divides block a by theta_a.
+// When a theta block is per-sample (inplace_a / inplace_b) the per-sample gradient contribution is
+// written over the sample's own slot in the y (term a) / aux (term b) tile for the caller to
+// column-sum; otherwise it is accumulated into out.ga / out.gb.
 template <int C, int KIND>
 FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int c_real,
                         bool eligible, double cst, bool inplace_a, bool inplace_b, EvalOut& out) {
     Normal<C> nm;
     nm.init();
     LogProd lp; lp.init();
+    double pend = 1.0;                 // PATSEQ: product of up to 4 variances between renormalisations
+    int npend = 0;
     double slt = 0.0;                  // SCALE_PS: sum_ret ln theta_j
     gv.for_each(eligible, [&](int j) {
         const double y = gv.y[j];
@@ -638,13 +647,20 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
         double x[C];
         load_x<C>(X, j, x);
         nm.add(sv.w, sv.valid ? y : 0.0, x);
+        if (KIND == KIND_PATSEQ) gv.aux[j] = sv.w;
         if (sv.valid) {
             ++nm.k;
-            if (KIND == KIND_PATSEQ) lp.mul(sv.s2); else slt += ec.tb[j];
+            if (KIND == KIND_PATSEQ) {
+                pend *= sv.s2;
+                if (++npend == 4) { lp.mul(pend); pend = 1.0; npend = 0; }
+            } else {
+                slt += ec.tb[j];
+            }
         }
     });
+    if (KIND == KIND_PATSEQ) { lp.mul(pend); lp.lane_reduce(gv.lpg); }
+    else slt = lane_sum(slt, gv.lpg);
     nm.reduce(gv.lpg);
-    if (KIND == KIND_PATSEQ) lp.lane_reduce(gv.lpg); else slt = lane_sum(slt, gv.lpg);
     nm.pad(c_real);
     double det;
     const bool ok = chol<C>(nm.a, det, 0.0);
@@ -652,24 +668,38 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
 #pragma unroll
     for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
     chol_solve<C>(nm.a, beta);
-
-    // sweep 2: d2 from residuals
-    double d2 = 0.0;
-    gv.for_each(eligible, [&](int j) {
-        const double y = gv.y[j];
-        const SampleVar sv = sample_var(ec, gv, j, y);
-        double x[C];
-        load_x<C>(X, j, x);
-        double r = sv.valid ? y : 0.0;
+    double d2 = nm.yy;
 #pragma unroll
-        for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
-        d2 += sv.w * r * r;
-    });
-    d2 = lane_sum(d2, gv.lpg);
+    for (int i = 0; i < C; ++i) d2 -= nm.b[i] * beta[i];
+
+    // the weight of sample j as left by the first sweep
+    auto weight = [&](int j, double y, bool& valid) -> double {
+        if (KIND == KIND_PATSEQ) { const double w = gv.aux[j]; valid = w != 0.0; return w; }
+        const SampleVar sv = sample_var(ec, gv, j, y);
+        valid = sv.valid;
+        return sv.w;
+    };
+    if (warp_any(eligible && d2 < 1e-4 * nm.yy)) {          // cancellation: d2 from residuals
+        double s = 0.0;
+        gv.for_each(eligible && d2 < 1e-4 * nm.yy, [&](int j) {
+            const double y = gv.y[j];
+            bool valid;
+            const double w = weight(j, y, valid);
+            double x[C];
+            load_x<C>(X, j, x);
+            double r = valid ? y : 0.0;
+#pragma unroll
+            for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
+            s += w * r * r;
+        });
+        s = lane_sum(s, gv.lpg);
+        if (d2 < 1e-4 * nm.yy) d2 = s;
+    }
+    if (d2 < 0.0) d2 = 0.0;
 
     eval_zero(out);
     const int p = nm.k - c_real;
-    const bool good = eligible && ok && p > 0;
+    const bool good = eligible && ok && p > 0 && d2 == d2;
     double kappa = 0.5;
     if (good) {
         const double lsig = (KIND == KIND_PATSEQ) ? lp.log_value() : slt;
@@ -677,28 +707,33 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
         double dv;
         out.value = finish_density(ec, p, logdet, d2, dv, kappa);
         out.dv = dv; out.d2 = d2; out.p = p; out.used = 1;
+        if (!(out.value == out.value)) { out.dv = 0.0; }
     } else if (eligible) {
         out.value = NAN; out.used = 1;
     }
+    const bool grad_ok = good && out.value == out.value;
 
-    // sweep 3: gradient.  e~_j = sigma2_j * d(-ll)/d sigma2_j = 1/2 (1 - w_j h_j) - kappa w_j r_j^2
+    // second sweep: gradient
     double ga = 0.0, gb = 0.0;
-    gv.for_each(true, [&](int j) {
+    gv.for_each(grad_ok || inplace_a || (KIND == KIND_PATSEQ && inplace_b), [&](int j) {
         const double y = gv.y[j];
         double ca = 0.0, cb = 0.0;
-        if (good) {
-            const SampleVar sv = sample_var(ec, gv, j, y);
-            if (sv.valid) {
+        if (grad_ok) {
+            bool valid;
+            const double w = weight(j, y, valid);
+            if (valid) {
                 double x[C];
                 load_x<C>(X, j, x);
                 double r = y;
 #pragma unroll
                 for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
                 const double h = leverage<C>(nm.a, x);
-                const double et = 0.5 * (1.0 - sv.w * h) - kappa * sv.w * r * r;
+                const double et = 0.5 * (1.0 - w * h) - kappa * w * r * r;
                 if (KIND == KIND_PATSEQ) {
-                    const double e = et * sv.w;
-                    ca = sv.U * e; cb = sv.T * e;
+                    const double T = ec.tail_own ? y * y : gv.gs;
+                    const double tw = T * w;
+                    cb = tw * et;                                         // T_j e_j
+                    ca = (1.0 - ec.tb[j] * tw) * et;                      // theta_a(j) U_j e_j: the caller divides
                 } else {
                     ca = et * ec.ta[j];          // d sigma2_j / d theta_j = sigma2_j / theta_j
                 }

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
         });
         finalize();
     } else {
-    tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, inplace, [&](unsigned char* st, long long tile) {
+    // PATSEQ keeps 1/sigma2 in the aux tile between its two sweeps: the stage is always written
+    tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, inplace || KIND == KIND_PATSEQ, [&](unsigned char* st, long long tile) {
         const long long gene = tile * p.g.genes + gl;
         double* ys = (double*)st;
         double* auxs = (double*)(st + L.aux_off);

@@ -57,6 +57,9 @@ def assert_close(a, b, rtol, atol=0.0, what=""):
     assert np.array_equal(nan_a, nan_b), "%s: NaN pattern differs at %s" % (
         what, np.argwhere(nan_a != nan_b)[:5].tolist())
     ok = ~nan_a
+    inf = np.isinf(a) | np.isinf(b)
+    assert np.array_equal(a[inf], b[inf]), "%s: infinities differ" % what
+    ok &= ~inf
     if not ok.any():
         return
     err = np.abs(a[ok] - b[ok])

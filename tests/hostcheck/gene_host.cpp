@@ -110,6 +110,8 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
         if (inpl_a) for (int j = 0; j < m; ++j) grad[off_a + j] += row[j];
         if (inpl_b) for (int j = 0; j < m; ++j) grad[off_b + j] += arow[j];
     }
+    if (fam->kind == KIND_PATSEQ)            // eval_general returns term a times theta_a(j)
+        for (int j = 0; j < fam->na; ++j) grad[off_a + j] /= theta[off_a + j];
     *value_total = total;
     return 0;
 }
