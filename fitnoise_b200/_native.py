@@ -25,7 +25,7 @@ EXPORTS = [
     "fn_upload", "fn_upload_dev", "fn_nll_grad", "fn_nll_grad_dev", "fn_per_gene", "fn_noise_stats",
     "fn_coef", "fn_test", "fn_bh", "fn_bh_dev", "fn_weights", "fn_set_tuning", "fn_launch_count",
     "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
-    "fn_test_bh", "fn_coef_fetch",
+    "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked",
 ]
 
 
@@ -90,7 +90,9 @@ def load_library():
     lib.fn_coef.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p,
                             c_double_p, c_double_p, c_double_p]
     lib.fn_test.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
-    lib.fn_test_bh.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.fn_test_bh.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
+                               ctypes.c_void_p]
+    lib.fn_bh_ranked.argtypes = [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p, ctypes.c_void_p]
     lib.fn_coef_fetch.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
     lib.fn_bh.argtypes = [ctypes.c_void_p, ctypes.c_int64, c_double_p, c_double_p]
     lib.fn_bh_dev.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
@@ -234,7 +236,10 @@ class Engine(object):
         contrasts = _f64(contrasts)
         kc = contrasts.shape[1]
         contrasted, p, q = np.empty((self.n, kc)), np.empty(self.n), np.empty(self.n)
-        self._check(self._lib.fn_test_bh(self._h, kc, _dp(contrasts), _dp(contrasted), _dp(p), _dp(q)))
+        order = np.empty(self.n, dtype=np.uint32)
+        self._check(self._lib.fn_test_bh(self._h, kc, _dp(contrasts), _dp(contrasted), _dp(p), _dp(q),
+                                         order.ctypes.data))
+        self.last_order = order
         return contrasted, p, q
 
     def test(self, contrasts, want_covar=False):
@@ -251,6 +256,14 @@ class Engine(object):
         q = np.empty(len(p))
         self._check(self._lib.fn_bh(self._h, len(p), _dp(p), _dp(q)))
         return q
+
+    def bh_ranked(self, p):
+        """(q, order): BH q-values and the genes by ascending p (stable, NaN last)."""
+        p = _f64(p).reshape(-1)
+        q, order = np.empty(len(p)), np.empty(len(p), dtype=np.uint32)
+        if len(p):
+            self._check(self._lib.fn_bh_ranked(self._h, len(p), _dp(p), _dp(q), order.ctypes.data))
+        return q, order
 
     def bh_dev(self, n, p_ptr, q_ptr):
         self._check(self._lib.fn_bh_dev(self._h, n, p_ptr, q_ptr))

@@ -812,11 +812,11 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     return 0;
 }
 
-static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work);
+static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev = nullptr);
 static size_t bh_work_bytes(int64_t n);
 
 static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov,
-                     double* pval, double* qval) {
+                     double* pval, double* qval, uint32_t* order) {
     if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_test needs a preceding fn_coef");
     const int c = h->coef_c;
     if (kc < 1 || kc > FN_MAXC || !contrasts) return fail(FN_ERR_UNSUPPORTED, "contrasts has %d columns; 1..%d supported", kc, FN_MAXC);
@@ -848,21 +848,24 @@ static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* 
     if (ccov) CUDA_TRY(cudaMemcpyAsync(ccov, d_cc, nb_cc, cudaMemcpyDeviceToHost, h->stream));
     if (pval) CUDA_TRY(cudaMemcpyAsync(pval, d_p, nb_p, cudaMemcpyDeviceToHost, h->stream));
     if (qval) {
-        rc = bh_run(h, h->n, d_p, d_q, base);          // p never leaves the device between test and BH
+        uint32_t* d_order = nullptr;
+        rc = bh_run(h, h->n, d_p, d_q, base, &d_order);   // p never leaves the device between test and BH
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(qval, d_q, nb_p, cudaMemcpyDeviceToHost, h->stream));
+        if (order) CUDA_TRY(cudaMemcpyAsync(order, d_order, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 extern "C" int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov, double* pval) {
-    return test_core(h, kc, contrasts, contrasted, ccov, pval, nullptr);
+    return test_core(h, kc, contrasts, contrasted, ccov, pval, nullptr, nullptr);
 }
 
-extern "C" int fn_test_bh(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* pval, double* qval) {
+extern "C" int fn_test_bh(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* pval,
+                          double* qval, uint32_t* order) {
     if (!qval) return fail(FN_ERR_ARG, "fn_test_bh: qval is NULL");
-    return test_core(h, kc, contrasts, contrasted, nullptr, pval, qval);
+    return test_core(h, kc, contrasts, contrasted, nullptr, pval, qval, order);
 }
 
 extern "C" int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* dfpost) {
@@ -900,7 +903,7 @@ extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* 
 // ------------------------------------------------------------------------------------------
 // Benjamini-Hochberg
 // ------------------------------------------------------------------------------------------
-static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work) {
+static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev) {
     const int nblocks = (int)((n + BH_CHUNK - 1) / BH_CHUNK);
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     uint64_t* keys0 = (uint64_t*)work; work += up(n * 8);
@@ -931,6 +934,7 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
     bh_finish_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, carry, q_dev);
     h->launches += 3;
     CUDA_TRY(cudaGetLastError());
+    if (order_dev) *order_dev = idx0;          // genes by ascending p (stable, NaN last)
     return 0;
 }
 
@@ -951,7 +955,15 @@ extern "C" int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q
     return bh_run(h, n, p_dev, q_dev, (char*)h->scratch_dev);
 }
 
-extern "C" int fn_bh(fn_handle* h, int64_t n, const double* p, double* q) {
+static int bh_host(fn_handle* h, int64_t n, const double* p, double* q, uint32_t* order);
+
+extern "C" int fn_bh(fn_handle* h, int64_t n, const double* p, double* q) { return bh_host(h, n, p, q, nullptr); }
+
+extern "C" int fn_bh_ranked(fn_handle* h, int64_t n, const double* p, double* q, uint32_t* order) {
+    return bh_host(h, n, p, q, order);
+}
+
+static int bh_host(fn_handle* h, int64_t n, const double* p, double* q, uint32_t* order) {
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
     if (n < 0 || n >= (1LL << 32)) return fail(FN_ERR_UNSUPPORTED, "fn_bh: n out of range");
     if (n == 0) return 0;
@@ -964,9 +976,11 @@ extern "C" int fn_bh(fn_handle* h, int64_t n, const double* p, double* q) {
     double* p_dev = (double*)base; base += up(n * 8);
     double* q_dev = (double*)base; base += up(n * 8);
     CUDA_TRY(cudaMemcpyAsync(p_dev, p, n * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = bh_run(h, n, p_dev, q_dev, base);
+    uint32_t* d_order = nullptr;
+    rc = bh_run(h, n, p_dev, q_dev, base, &d_order);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(q, q_dev, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (order) CUDA_TRY(cudaMemcpyAsync(order, d_order, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -1,6 +1,6 @@
 // K4: Benjamini-Hochberg q-values on the device (replaces p_adjust.py:3-21, two numpy argsorts).
 //
-//   key_i  = bit pattern of p_i (NaN -> 1.0); non-negative doubles order like their bit patterns
+//   key_i  = bit pattern of p_i (NaN -> +inf, read back as 1.0); non-negative doubles order like their bit patterns
 //   sort   = stable LSD radix sort of (key, index), 8 passes of 8 bits: per-CTA digit histograms,
 //            one scan, stable scatter (warp match + per-warp digit offsets)
 //   v_r    = (p_(r) * n) / (r + 1)  with the reference's operation order (p_adjust.py:14-16),
@@ -21,10 +21,16 @@ namespace fn {
 __global__ void bh_keys_kernel(long long n, const double* p, uint64_t* keys, uint32_t* idx) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double v = p[i];
-    if (v != v) v = 1.0;                    // p_adjust.py:7
-    keys[i] = (uint64_t)__double_as_longlong(v);
+    // NaN counts as p = 1.0 (p_adjust.py:7).  Its key is +inf so that the sorted order doubles as
+    // the top-table order (ascending p, stable, missing p last, like R's order()); bh_key_p() maps
+    // the key back to 1.0.  Entries with p = 1 get q = 1 wherever they rank among themselves.
+    const double v = p[i];
+    keys[i] = (v != v) ? 0x7ff0000000000000ull : (uint64_t)__double_as_longlong(v);
     idx[i] = (uint32_t)i;
+}
+
+__device__ __forceinline__ double bh_key_p(uint64_t key) {
+    return key == 0x7ff0000000000000ull ? 1.0 : __longlong_as_double((long long)key);
 }
 
 // hist[d * nblocks + b] = number of keys of CTA b's chunk whose digit is d
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(BH_THREADS) bh_chunkmin_kernel(long long n, co
     for (int k = 0; k < BH_ITEMS; ++k) {
         const long long r = base + k;
         if (r < n) {
-            const double p = __longlong_as_double((long long)keys[r]);
+            const double p = bh_key_p(keys[r]);
             const double v = __ddiv_rn(__dmul_rn(p, (double)n), (double)(r + 1));
             mn = fmin(mn, v);
         }
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(BH_THREADS) bh_finish_kernel(long long n, cons
         const long long r = base + k;
         double x = INFINITY;
         if (r < n) {
-            const double p = __longlong_as_double((long long)keys[r]);
+            const double p = bh_key_p(keys[r]);
             x = __ddiv_rn(__dmul_rn(p, (double)n), (double)(r + 1));
         }
         mn = fmin(mn, x);

@@ -76,6 +76,14 @@ class _Lazy(object):
         return self._value
 
 
+def _row_means(y):
+    """Row means over the finite entries (NaN for an all-missing row)."""
+    finite = np.isfinite(y)
+    count = finite.sum(axis=1)
+    total = np.where(finite, y, 0.0).sum(axis=1)
+    return np.where(count > 0, total / np.maximum(count, 1), np.nan)
+
+
 def _optimize(value_grad, initial, bounds, verbose):
     """The reference's driver loop (fitnoise.py:143-158): L-BFGS-B with analytic gradient and
     ftol = gtol = 1e-12, restarted from the optimum until it moves by less than 1e-6."""
@@ -282,11 +290,13 @@ class Model(Withable):
 
     # ---- test (fitnoise.py:368-396) --------------------------------------------------------
     def test(self, coef=None, contrasts=None):
+        names = None
         if coef is not None:
             assert contrasts is None
             contrasts = np.zeros((self.design.shape[1], len(coef)))
             for i in range(len(coef)):
                 contrasts[coef[i], i] = 1.0
+            names = ["coef%d" % (int(i) + 1) for i in coef]       # old_fitnoise.R:430, 522-531
         assert contrasts is not None, "No coefficients or contrasts to test given."
         contrasts = as_matrix(contrasts)
         assert contrasts.shape[0] == self.design.shape[1]
@@ -294,7 +304,9 @@ class Model(Withable):
         session = self._session
         if session.coef_token is not self._coef_token:        # another fit_coef ran on this session since
             session.coef(self._theta, self.design, self._coef_token)
-        contrasted, p_values, q_values = session.test(contrasts)
+        contrasted, p_values, q_values, order = session.test(contrasts)
+        if names is None:
+            names = ["contrast%d" % (i + 1) for i in range(contrasts.shape[1])]   # old_fitnoise.R:39-47
 
         posterior, mean = self._coef_posterior, self.coef
         is_t = self._family(self.data.y.shape[1]).dist != _native.DIST_NORMAL
@@ -307,7 +319,40 @@ class Model(Withable):
             return base.transformed(contrasts.T)
 
         return self._with(contrasts=contrasted, contrast_dists=_LazyDists(len(mean), make),
-                          p_values=p_values, q_values=q_values)
+                          p_values=p_values, q_values=q_values,
+                          _order=np.asarray(order, dtype=np.int64), _contrast_names=names)
+
+    # ---- top table (legacy R test.fit, backyard/old_fitnoise.R:783-826) ---------------------
+    def top_table(self, sort=True, genes=None):
+        """Table of the tested contrasts in the layout of the legacy R ``test.fit`` (intended there
+        to match limma's topTableF): one column per contrast, ``AveExpr``, ``P.Value``,
+        ``adj.P.Val``, ``noise.P.Value`` and, when control genes were given, ``control``; rows
+        ordered by p (ascending, ties in input order, missing p last -- R's ``order()``).  The order
+        comes from the device radix sort that also produced the q-values.
+
+        Returns a pandas DataFrame when pandas is importable, else a dict of columns plus "row".
+        ``genes``: optional dict of per-gene annotation columns appended to the table."""
+        assert hasattr(self, "p_values"), "top_table() needs a tested fit: call .test(...) first"
+        n = len(self.p_values)
+        rows = self._order if sort else np.arange(n)
+        columns = {}
+        for i, name in enumerate(self._contrast_names):
+            columns[name] = self.contrasts[rows, i]
+        with np.errstate(invalid="ignore"):
+            columns["AveExpr"] = _row_means(self.data.y)[rows]          # rowMeans(fit$data, na.rm=TRUE)
+        columns["P.Value"] = self.p_values[rows]
+        columns["adj.P.Val"] = self.q_values[rows]
+        columns["noise.P.Value"] = self.noise_p_values[rows]
+        if np.any(self.controls):
+            columns["control"] = np.asarray(self.controls)[rows]
+        for key, value in (genes or {}).items():
+            columns[key] = np.asarray(value)[rows]
+        try:
+            import pandas
+        except ImportError:
+            columns["row"] = rows
+            return columns
+        return pandas.DataFrame(columns, index=rows)
 
     # ---- get_weights (fitnoise.py:399-404) -------------------------------------------------
     def get_weights(self):

@@ -136,12 +136,15 @@ class Session(object):
         return parallel.allgather_rows(covar, self.n), parallel.allgather_rows(dfpost, self.n)
 
     def test(self, contrasts):
-        """contrasted, p_values, q_values (BH over ALL genes)."""
+        """contrasted, p_values, q_values (BH over ALL genes), order (genes by ascending p, stable,
+        NaN last: the top-table order)."""
         if self.world == 1:
-            return self.local.test_bh(contrasts)      # p never leaves the device before the adjustment
+            contrasted, p, q = self.local.test_bh(contrasts)   # p never leaves the device before the adjustment
+            return contrasted, p, q, self.local.last_order
         contrasted, _, p = self.local.test(contrasts)
         contrasted, p = parallel.allgather_rows(contrasted, self.n), parallel.allgather_rows(p, self.n)
-        return contrasted, p, self.bh(p)
+        q, order = self.local.bh_ranked(p)
+        return contrasted, p, q, order
 
     def bh(self, p):
         # every rank holds the full p vector after the gather and adjusts it on its own GPU

@@ -108,7 +108,8 @@ int fn_test(fn_handle* h, int32_t kc, const double* contrasts, double* contraste
 
 /* fn_test followed by Benjamini-Hochberg over this handle's genes without p leaving the device
  * (Model.test computes q_values right after p_values, fitnoise.py:395). */
-int fn_test_bh(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* pval, double* qval);
+int fn_test_bh(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* pval, double* qval,
+               uint32_t* order /* n genes by ascending p (stable, NaN last): the top-table order; or NULL */);
 
 /* Copy the device-resident results of the last fn_coef to the host (any pointer may be NULL): lets a
  * caller take `coef` at once and the c x c covariances only if somebody asks for coef_dists. */
@@ -116,6 +117,9 @@ int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* dfpost);
 
 /* p_adjust.fdr (p_adjust.py:3-21): Benjamini-Hochberg q-values; NaN p counts as 1.0. */
 int fn_bh(fn_handle* h, int64_t n, const double* p, double* q);
+/* ... and the top-table order: genes by ascending p, ties in input order, NaN last (what the legacy
+ * R test.fit sorts its table by, backyard/old_fitnoise.R:822-823). */
+int fn_bh_ranked(fn_handle* h, int64_t n, const double* p, double* q, uint32_t* order);
 /* device-resident form: p_dev, q_dev are device pointers of n doubles */
 int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev);
 

@@ -162,7 +162,11 @@ class HostEvaluator(object):
 
     def test_bh(self, contrasts):
         con, _, p = self.test(contrasts)
-        return con, p, self.bh(p)
+        q, self.last_order = self.bh_ranked(p)
+        return con, p, q
+
+    def bh_ranked(self, p):
+        return self.bh(p), np.argsort(np.asarray(p, dtype=np.float64), kind="stable")
 
     def test(self, contrasts, want_covar=False):
         coef, covar, dfp, is_t = self._coef

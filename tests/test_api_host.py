@@ -125,3 +125,26 @@ def test_nan_aware_initial_variance():
     fitted, _ = fit_golden(g, engine_factory=hostcheck.HostEvaluator)
     assert np.isfinite(fitted.optimization_result.x).all()
     assert np.isfinite(fitted.noise_p_values).sum() >= 11
+
+
+def test_top_table():
+    g = load_golden("t_per_sample_controls")
+    fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
+    table = tested.top_table()
+    order = np.argsort(g["ref_p_values"], kind="stable")
+    assert list(table.columns) == ["coef2", "AveExpr", "P.Value", "adj.P.Val", "noise.P.Value", "control"]
+    assert np.array_equal(np.asarray(table.index), order)
+    assert_close(table["P.Value"].values, g["ref_p_values"][order], 1e-8)
+    assert_close(table["adj.P.Val"].values, g["ref_q_values"][order], 1e-8)
+    assert_close(table["coef2"].values, g["ref_contrasts"][order, 0], 1e-9)
+    assert np.array_equal(table["control"].values, g["controls"][order])
+    assert np.all(np.diff(table["P.Value"].values) >= 0)
+    unsorted = tested.top_table(sort=False)
+    assert np.array_equal(np.asarray(unsorted.index), np.arange(len(order)))
+    # status rows: NaN p-values go last, in input order
+    g = load_golden("independent_status")
+    fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
+    table = tested.top_table()
+    nan_rows = np.where(np.isnan(g["ref_p_values"]))[0]
+    assert np.array_equal(np.asarray(table.index)[-len(nan_rows):], nan_rows)
+    assert "control" not in table.columns

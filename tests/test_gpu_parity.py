@@ -336,3 +336,25 @@ def test_degenerate_inputs():
         e.close()
     with pytest.raises(AssertionError):
         fitnoise.Model_t().fit(np.zeros((3, 6)), np.ones((5, 1)))   # design rows != samples
+
+
+def test_top_table_order_bit_exact(engine):
+    """The top-table order is the stable ascending order of p with missing p last (R's order(),
+    backyard/old_fitnoise.R:822-823), bit-exact with numpy's stable argsort."""
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 300, 4097, 250000):
+        p = rng.random(n) ** 4
+        if n > 4:
+            p[rng.integers(0, n, n // 10 + 1)] = np.nan
+            p[rng.integers(0, n, n // 5 + 1)] = p[1]        # many ties
+            p[2] = 1.0
+            p[3] = 0.0
+        q, order = engine.bh_ranked(p)
+        assert np.array_equal(order.astype(np.int64), np.argsort(p, kind="stable")), n
+        assert np.array_equal(q, oracle.fdr(p)), n
+    g = load_golden("t_per_sample_controls")
+    fitted, tested = fit_golden(g, force_param=g["theta"])
+    table = tested.top_table()
+    assert np.array_equal(np.asarray(table.index), np.argsort(tested.p_values, kind="stable"))
+    assert list(table.columns) == ["coef2", "AveExpr", "P.Value", "adj.P.Val", "noise.P.Value", "control"]
+    assert_close(table["adj.P.Val"].values, g["ref_q_values"][np.asarray(table.index)], 1e-8)
