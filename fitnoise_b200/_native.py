@@ -33,7 +33,10 @@ class Family(ctypes.Structure):
     """fn_family (include/fitnoise_b200.h)."""
     _fields_ = [("kind", ctypes.c_int32), ("na", ctypes.c_int32), ("nb", ctypes.c_int32),
                 ("tail_own", ctypes.c_int32), ("v3", ctypes.c_int32), ("dist", ctypes.c_int32),
-                ("fixed_df", ctypes.c_double)]
+                ("nf", ctypes.c_int32), ("fixed_df", ctypes.c_double)]
+
+    def __init__(self, kind=0, na=0, nb=0, tail_own=0, v3=0, dist=0, fixed_df=0.0, nf=0):
+        super(Family, self).__init__(kind, na, nb, tail_own, v3, dist, nf, fixed_df)
 
     def theta_length(self):
         return (1 if self.dist == DIST_T else 0) + self.na + self.nb

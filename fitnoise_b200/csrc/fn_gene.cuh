@@ -36,6 +36,7 @@ struct Family {
     int tail_own;      // PATSEQ v1: T_j = y_j^2
     int v3;            // PATSEQ v3: sigma2_j = (theta_a rc_j + theta_b) * gs
     int dist;          // DIST_NORMAL, DIST_T (df = theta[0]), DIST_T_FIXED (df = fixed_df)
+    int nf;            // unknown batch-effect factors (Model_factors_mixin, fitnoise.py:439-518); SCALE1 only
     double fixed_df;   // Model_independent: 1e-10  (fitnoise.py:577)
 };
 
@@ -748,6 +749,129 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// Factor models (Model_factors_mixin, fitnoise.py:439-518): covariance diag(sigma2) + F F'
+// ------------------------------------------------------------------------------------------
+// With Sigma = D + F F' (F: m x nf, shared by all genes, changes with theta) the REML quantities are
+// those of the DIAGONAL model fitted with the augmented design Z = [X F] and a unit ridge on the
+// factor block of the normal matrix (Henderson's mixed-model equations):
+//   H = Z'WZ + diag(0_c, I_nf),  [beta; u] = H^-1 Z'Wy
+//   d2 = y'Wy - (Z'Wy)'[beta; u] = sum_j w_j r~_j^2 + u'u            (r~ = y - X beta - F u)
+//   ln det S = sum_ret ln sigma2_j + ln det H - ln det(X_ret'X_ret)
+//   d(-ll)/d sigma2_j = 1/2 (w_j - w_j^2 z_j'H^-1 z_j) - kappa (w_j r~_j)^2
+//   d(-ll)/d F[j,i]   = w_j z_j'(H^-1)_{:,c+i} - 2 kappa (w_j r~_j) u_i
+// so the (k-c)x(k-c) dense covariance the reference inverts (plus_covar, distributions.py:74-76)
+// never appears.  Z is m x C row-major with the design in columns [0,c), the factors in
+// [c, c+nf) and zeros beyond.  Only the SCALE1 variance (Model_normal/_t/_independent) combines
+// with factors in the reference (fitnoise.py:558-565, 592-594).
+template <int C>
+FN_HD void ridge_and_pad(double* a, int c_real, int nf) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        if (i >= c_real + nf) a[FN_TRI(i, i)] = 1.0;
+        else if (i >= c_real) a[FN_TRI(i, i)] += 1.0;
+    }
+}
+
+// `gscratch`: this gene's m x nf row block of the CTA's gradient scratch (written for every sample
+// this lane owns: the dF contribution of the gene, zeros when the gene does not contribute).
+template <int C>
+FN_HD void eval_factors(const EvalConst& ec, const GeneView& gv, const double* Z, int c_real, int nf,
+                        bool eligible, double cst, double* gscratch, EvalOut& out) {
+    Normal<C> nm;
+    nm.init();
+    gv.for_each(eligible, [&](int j) {
+        const double y = gv.y[j];
+        const SampleVar sv = sample_var(ec, gv, j, y);
+        double z[C];
+        load_x<C>(Z, j, z);
+        nm.add(sv.w * ec.itheta0, sv.valid ? y : 0.0, z);
+        nm.k += sv.valid ? 1 : 0;
+    });
+    nm.reduce(gv.lpg);
+    ridge_and_pad<C>(nm.a, c_real, nf);
+    double det;
+    const bool ok = chol<C>(nm.a, det, 0.0);
+    double sol[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) sol[i] = nm.b[i];
+    chol_solve<C>(nm.a, sol);
+    double d2 = nm.yy;
+#pragma unroll
+    for (int i = 0; i < C; ++i) d2 -= nm.b[i] * sol[i];
+    if (warp_any(eligible && d2 < 1e-4 * nm.yy)) {          // cancellation: d2 = sum w r~^2 + u'u
+        double s = 0.0;
+        gv.for_each(eligible && d2 < 1e-4 * nm.yy, [&](int j) {
+            const double y = gv.y[j];
+            const SampleVar sv = sample_var(ec, gv, j, y);
+            double z[C];
+            load_x<C>(Z, j, z);
+            double r = sv.valid ? y : 0.0;
+#pragma unroll
+            for (int t = 0; t < C; ++t) r -= z[t] * sol[t];
+            s += sv.w * ec.itheta0 * r * r;
+        });
+        s = lane_sum(s, gv.lpg);
+#pragma unroll
+        for (int i = 0; i < C; ++i) if (i >= c_real && i < c_real + nf) s += sol[i] * sol[i];
+        if (d2 < 1e-4 * nm.yy) d2 = s;
+    }
+    if (d2 < 0.0) d2 = 0.0;
+
+    eval_zero(out);
+    const int p = nm.k - c_real;
+    const bool good = eligible && ok && p > 0 && d2 == d2;
+    double kappa = 0.5;
+    if (good) {
+        const double logdet = nm.k * ec.ltheta0 + log(det) + cst;
+        double dv;
+        out.value = finish_density(ec, p, logdet, d2, dv, kappa);
+        out.dv = dv; out.d2 = d2; out.p = p; out.used = 1;
+    } else if (eligible) {
+        out.value = NAN; out.used = 1;
+    }
+    const bool grad_ok = good && out.value == out.value;
+
+    // columns c..c+nf-1 of H^-1 (at most 4 factors)
+    double hcol[4][C];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) hcol[f][i] = (f < nf && i == c_real + f) ? 1.0 : 0.0;
+        if (f < nf) chol_solve<C>(nm.a, hcol[f]);
+    }
+    double gsum = 0.0;
+    gv.for_each(true, [&](int j) {
+        double gf[4] = {0.0, 0.0, 0.0, 0.0};
+        if (grad_ok) {
+            const double y = gv.y[j];
+            const SampleVar sv = sample_var(ec, gv, j, y);
+            if (sv.valid) {
+                const double w = sv.w * ec.itheta0;
+                double z[C];
+                load_x<C>(Z, j, z);
+                double r = y;
+#pragma unroll
+                for (int t = 0; t < C; ++t) r -= z[t] * sol[t];
+                const double h = leverage<C>(nm.a, z);
+                gsum += 0.5 * (1.0 - w * h) - kappa * w * r * r;
+                const double wr2k = 2.0 * kappa * w * r;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    if (f < nf) {
+                        double zh = 0.0, uf = 0.0;
+#pragma unroll
+                        for (int t = 0; t < C; ++t) { zh += z[t] * hcol[f][t]; if (t == c_real + f) uf = sol[t]; }
+                        gf[f] = w * zh - wr2k * uf;
+                    }
+                }
+            }
+        }
+        for (int f = 0; f < nf; ++f) gscratch[j * nf + f] = gf[f];
+    });
+    out.ga = lane_sum(gsum, gv.lpg) * ec.itheta0;      // d sigma2_j/d theta = sigma2_j/theta
+}
+
+// ------------------------------------------------------------------------------------------
 // K3: GLS coefficients and their posterior (fit_coef, fitnoise.py:294-347)
 // ------------------------------------------------------------------------------------------
 struct CoefOut {
@@ -759,22 +883,31 @@ struct CoefOut {
 // beta (whitened basis) and A^-1 (packed lower, whitened basis).  The caller maps them back through
 // R^-1 of the design's thin QR.  The variance kinds are evaluated at the FITTED theta
 // (fitnoise.py:311-313).
+// With factors (nf > 0) X is the augmented [design | factors] table and beta / ainv are the
+// solution and the inverse of the ridge-augmented system; their first c_real entries / leading
+// c_real x c_real block are the coefficients and (X'Sigma^-1 X)^-1.
 template <int C>
-FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
+FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, int c_real, int nf,
                      double* beta, double* ainv, CoefOut& out) {
     Normal<C> nm, gm;
     nm.init(); gm.init();
+    const double wscale = nf > 0 ? ec.itheta0 : 1.0;       // the ridge does not scale with theta
     gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
         const SampleVar sv = sample_var(ec, gv, j, y);
         double x[C];
         load_x<C>(X, j, x);
-        nm.add(sv.w, sv.valid ? y : 0.0, x);
-        if (sv.valid) { gm.add(1.0, 0.0, x); ++nm.k; }
+        nm.add(sv.w * wscale, sv.valid ? y : 0.0, x);
+        if (sv.valid) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) if (i >= c_real) x[i] = 0.0;     // rank of the design only
+            gm.add(1.0, 0.0, x);
+            ++nm.k;
+        }
     });
     nm.reduce(gv.lpg);
     gm.reduce(gv.lpg);
-    nm.pad(c_real); gm.pad(c_real);
+    ridge_and_pad<C>(nm.a, c_real, nf); gm.pad(c_real);
     double det;
     const bool full_rank = chol<C>(gm.a, det, FN_RANK_TOL);
     const bool okA = chol<C>(nm.a, det, 0.0);
@@ -791,10 +924,12 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
         double r = sv.valid ? y : 0.0;
 #pragma unroll
         for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
-        d2 += sv.w * r * r;
+        d2 += sv.w * wscale * r * r;
     });
     d2 = lane_sum(d2, gv.lpg);
-    if (ec.kind == KIND_SCALE1) {             // sums were taken at theta = 1
+#pragma unroll
+    for (int i = 0; i < C; ++i) if (i >= c_real && i < c_real + nf) d2 += beta[i] * beta[i];   // + u'u
+    if (ec.kind == KIND_SCALE1 && nf == 0) {  // sums were taken at theta = 1
         d2 /= ec.theta0;
 #pragma unroll
         for (int i = 0; i < Tri<C>::N; ++i) ainv[i] *= ec.theta0;

@@ -91,7 +91,20 @@ inline bool unpack_theta(const Family& f, int m, const double* theta, double& v,
     return true;
 }
 
+// [design | factors | 0] table of width `width` for the factor models (fn_gene.cuh, eval_factors)
+inline std::vector<double> augment_design(const Design& d, int width, int nf, const double* F) {
+    std::vector<double> z((size_t)d.m * width, 0.0);
+    for (int j = 0; j < d.m; ++j) {
+        for (int i = 0; i < d.c; ++i) z[(size_t)j * width + i] = d.q[(size_t)j * d.width + i];
+        for (int f = 0; f < nf; ++f) z[(size_t)j * width + d.c + f] = F[(size_t)j * nf + f];
+    }
+    return z;
+}
+
+#define FN_MAX_FACTORS 4
+
 inline bool family_valid(const Family& f, int m, bool has_aux) {
+    if (f.nf < 0 || f.nf > FN_MAX_FACTORS || (f.nf > 0 && f.kind != KIND_SCALE1)) return false;
     if (f.kind == KIND_SCALE1) return (f.na == 0 || f.na == 1) && f.nb == 0;
     if (f.kind == KIND_SCALE_PS) return f.na == m && f.nb == 0;
     if (f.kind == KIND_PATSEQ) return has_aux && (f.na == 1 || f.na == m) && (f.nb == 1 || f.nb == m);

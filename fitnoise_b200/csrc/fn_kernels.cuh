@@ -427,6 +427,7 @@ struct CoefParams {
     const double* x;         // m x width, whitened coefficient design
     const double* rinv;      // c x c upper triangular
     int c;
+    int nf;                  // factor columns following the design in x
     int kind, tail_own, v3, is_t;
     double v, theta0;
     const double* ta; const double* tb;
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
         gv.gs = p.src.gs ? ((const double*)(st + L.gs_off))[gl] : 0.0;
         double beta[C], ainv[Tri<C>::N];
         CoefOut co;
-        coef_gene<C>(ec, gv, x, c, beta, ainv, co);
+        coef_gene<C>(ec, gv, x, c, p.nf, beta, ainv, co);
         if (lane != 0 || gene >= p.g.n) return;
         double* cf = p.coef + gene * c;
         double* cv = p.covar + gene * c * c;

@@ -138,6 +138,18 @@ class Model(Withable):
 
     _aux_key = None                     # which Dataset.context entry is the second n x m array
 
+    # theta as the optimiser sees it <-> what the kernels take: the variance parameters (and df)
+    # plus, for the factor models, the m x nf matrix of factor vectors.  Composed by the mix-ins.
+    def _split_theta(self, theta):
+        return theta, None
+
+    def _join_grad(self, grad_core, grad_factors):
+        return grad_core
+
+    def _cost_grad(self, theta):
+        """_model_cost of the packed theta and its gradient (0 for every model without factors)."""
+        return 0.0, np.zeros(len(theta))
+
     def _initial_bounds(self, m, row_variance_mean):
         return [], []
 
@@ -170,6 +182,15 @@ class Model(Withable):
         initial, bounds = self._initial_bounds(m, session.row_variance_mean)
         return self._with(_session=session, _initial=list(initial), _bounds=list(bounds))
 
+    def _objective(self, theta):
+        """REML objective (model cost + sum of score_row over all genes, fitnoise.py:63-68) and its
+        gradient at the packed theta, evaluated on the GPU: (value, grad, n_used, n_bad)."""
+        theta = as_vector(theta)
+        core, factors = self._split_theta(theta)
+        value, grad_core, grad_factors, used, bad = self._session.nll_grad(core, factors)
+        cost, cost_grad = self._cost_grad(theta)
+        return value + cost, self._join_grad(grad_core, grad_factors) + cost_grad, used, bad
+
     # ---- fit_noise (fitnoise.py:207-291) ---------------------------------------------------
     def fit_noise(self, data, design=None, control_design=None, controls=None, use_theano=True,
                   verbose=False, force_param=None):
@@ -199,7 +220,7 @@ class Model(Withable):
             if verbose:
                 print(theta, end=" ")
                 sys.stdout.flush()
-            value, grad, used, bad = session.nll_grad(theta)
+            value, grad, used, bad = result._objective(theta)
             if bad:
                 value = np.inf
             if verbose:
@@ -219,7 +240,10 @@ class Model(Withable):
         if verbose:
             print("Model cost:", result._model_cost(param))
 
-        noise_p_values, averages = session.noise_stats(fit.x)         # :257-267
+        theta, factors = result._split_theta(as_vector(fit.x))
+        if factors is not None:
+            session.set_factors(factors)
+        noise_p_values, averages = session.noise_stats(theta)         # :257-267
 
         good_p = noise_p_values[np.isfinite(noise_p_values)]          # :270-274
         if not len(good_p):
@@ -231,7 +255,6 @@ class Model(Withable):
         n_residuals = (n - n_controls) * (m - design.shape[1]) + n_controls * (m - control_design.shape[1])
         df = n_residuals - len(initial)
 
-        theta = as_vector(fit.x)
         fitted = result._with(
             optimization_result=fit,
             param=param,
@@ -388,6 +411,111 @@ class Model_t_mixin(Model):
     def _initial_bounds(self, m, row_variance_mean):
         initial, bounds = super(Model_t_mixin, self)._initial_bounds(m, row_variance_mean)
         return [5.0] + list(initial), [(1e-3, 100.0)] + list(bounds)
+
+    def _split_theta(self, theta):
+        core, factors = super(Model_t_mixin, self)._split_theta(theta[1:])
+        return np.concatenate([theta[:1], core]), factors
+
+    def _join_grad(self, grad_core, grad_factors):
+        return np.concatenate([grad_core[:1], super(Model_t_mixin, self)._join_grad(grad_core[1:], grad_factors)])
+
+    def _cost_grad(self, theta):
+        cost, grad = super(Model_t_mixin, self)._cost_grad(theta[1:])
+        return cost, np.concatenate([[0.0], grad])
+
+
+class Model_factors_mixin(Model):
+    """ This mix-in adds unknown batch effect(s) to the model (fitnoise.py:439-518): the covariance
+        of every gene gains sum_i f_i f_i' with f_i = Q2 . pack_i in the orthogonal complement of
+        the (control) design.  The kernels fit it as the diagonal model with the design augmented by
+        the factor vectors and a unit ridge on them (csrc/fn_gene.cuh, eval_factors); the penalty
+        sum_{i<j} (f_i . f_j)^2 and the chain rule through Q2 are host-side (m x nf numbers). """
+
+    def __init__(self, n_factors, *etc):
+        self.n_factors = n_factors
+        super(Model_factors_mixin, self).__init__(*etc)
+
+    def _unpack(self, pack):
+        m2 = self._factor_Q2.shape[1]
+        factors = []
+        for i in range(self.n_factors):
+            factors.append(self._factor_Q2 @ pack[:m2])
+            pack = pack[m2:]
+        return super(Model_factors_mixin, self)._unpack(pack)._with(factors=factors)
+
+    def _describe_noise(self, param):
+        result = ""
+        for i in range(self.n_factors):
+            result += "factor: [%s]\n" % ", ".join("%f" % item for item in param.factors[i])
+        return result + super(Model_factors_mixin, self)._describe_noise(param)
+
+    def _model_cost(self, param):
+        """ It should always be possible to reduce this cost to zero. """
+        cost = super(Model_factors_mixin, self)._model_cost(param)
+        for i in range(self.n_factors):
+            for j in range(i):
+                cost = cost + float(np.dot(param.factors[i], param.factors[j])) ** 2
+        return cost
+
+    def _get_dist(self, param, aux):
+        covar = np.zeros((len(aux), len(aux)))
+        for i in range(self.n_factors):
+            covar = covar + np.outer(param.factors[i], param.factors[i])
+        return super(Model_factors_mixin, self)._get_dist(param, aux).plus_covar(covar)
+
+    def _family(self, m):
+        family = super(Model_factors_mixin, self)._family(m)
+        assert family.kind == _native.KIND_SCALE1, "factors combine with Model_normal/_t/_independent only"
+        family.nf = int(self.n_factors)
+        return family
+
+    def _configured(self):
+        # fitnoise.py:490-518
+        design = self.control_design if np.any(self.controls) else self.noise_design
+        Q, R = np.linalg.qr(design, mode="complete")
+        return super(Model_factors_mixin, self._with(_factor_Q2=Q[:, design.shape[1]:]))._configured()
+
+    def _initial_bounds(self, m, row_variance_mean):
+        initial, bounds = super(Model_factors_mixin, self)._initial_bounds(m, row_variance_mean)
+        Q2 = self._factor_Q2
+        m2 = Q2.shape[1]
+        y = self.data.y
+        good = np.all(np.isfinite(y), axis=1)
+        goody = y[good] @ Q2                                          # (Q2' y')' of :507
+        if goody.size <= 20000000:
+            u, sv, v = np.linalg.svd(goody, full_matrices=0)
+        else:       # same right singular vectors (up to sign) from the m2 x m2 Gram matrix
+            evals, evecs = np.linalg.eigh(goody.T @ goody)
+            sv, v = np.sqrt(np.maximum(evals, 0.0)), evecs.T
+        rows = np.argsort(-np.abs(sv))[:self.n_factors]
+        start = list((v[rows] * sv[rows][:, None]).flatten() / np.sqrt(goody.shape[0]))
+        return start + list(initial), [(None, None)] * (m2 * self.n_factors) + list(bounds)
+
+    def _split_theta(self, theta):
+        m2 = self._factor_Q2.shape[1]
+        npack = m2 * self.n_factors
+        core, nothing = super(Model_factors_mixin, self)._split_theta(theta[npack:])
+        packs = np.asarray(theta[:npack]).reshape(self.n_factors, m2)
+        return core, np.ascontiguousarray(self._factor_Q2 @ packs.T)            # m x nf
+
+    def _join_grad(self, grad_core, grad_factors):
+        packs = (self._factor_Q2.T @ grad_factors).T.reshape(-1)               # chain rule through Q2
+        return np.concatenate([packs, super(Model_factors_mixin, self)._join_grad(grad_core, None)])
+
+    def _cost_grad(self, theta):
+        m2 = self._factor_Q2.shape[1]
+        npack = m2 * self.n_factors
+        cost, grad_rest = super(Model_factors_mixin, self)._cost_grad(theta[npack:])
+        F = self._factor_Q2 @ np.asarray(theta[:npack]).reshape(self.n_factors, m2).T
+        gram = F.T @ F
+        grad_f = np.zeros_like(F)
+        for i in range(self.n_factors):
+            for j in range(self.n_factors):
+                if i != j:
+                    grad_f[:, i] += 2.0 * gram[i, j] * F[:, j]
+                    if j < i:
+                        cost = cost + gram[i, j] ** 2
+        return cost, np.concatenate([(self._factor_Q2.T @ grad_f).T.reshape(-1), grad_rest])
 
 
 class _Weighted(Model):
@@ -588,22 +716,13 @@ Model_t_standard = Model_t
 Model_t_independent = Model_independent
 
 
-class _Unsupported(Model):
-    _why = ""
-
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError(self._why)
-
-
-class Model_normal_factors(_Unsupported):
-    _why = ("the *_factors noise models (full covariance with unknown batch-effect factors, "
-            "fitnoise.py:439-518) are not built yet: they need a rank-n update of the per-gene "
-            "system that the diagonal-variance kernels do not provide (SURVEY 8f, rank 1)")
-
-
-class Model_t_factors(Model_normal_factors):
+class Model_normal_factors(Model_factors_mixin, Model_normal):
     pass
 
 
-class Model_independent_factors(Model_normal_factors):
+class Model_t_factors(Model_t_mixin, Model_factors_mixin, Model_normal):
+    pass
+
+
+class Model_independent_factors(Model_factors_mixin, Model_independent):
     pass

@@ -62,7 +62,7 @@ class Session(object):
         sums of all GPUs over NVLink (csrc/fn_kernels.cuh grid_reduce); FN_REDUCE=nccl keeps the
         kernel + ncclAllReduce path instead."""
         import torch.distributed as dist
-        handle = self.local.comm_mailbox(self.world, 8 + 2 * self.m)
+        handle = self.local.comm_mailbox(self.world, 8 + max(2, self.family.nf) * self.m)
         handles = [None] * self.world
         dist.all_gather_object(handles, handle)
         self.local.comm_connect(self.rank, self.world, b"".join(handles))
@@ -95,23 +95,38 @@ class Session(object):
         self._finalizer()
 
     # ---- likelihood -----------------------------------------------------------------------
-    def nll_grad(self, theta):
-        """Global (all ranks) value and gradient of the REML objective at theta."""
+    def nll_grad(self, theta, factors=None):
+        """Global (all ranks) value and gradient of the REML objective at theta:
+        (value, grad, grad_factors | None, n_used, n_bad).  ``factors``: m x nf matrix of the factor
+        models; its gradient comes back in the same shape."""
         theta = np.asarray(theta, dtype=np.float64)
+        if factors is not None:
+            value, grad, gf, used, bad = self.local.nll_grad_factors(theta, factors)
+            if self.world > 1 and not self._fused:
+                out = parallel.allreduce_sum(np.concatenate([[value], grad, gf.reshape(-1), [used, bad]]))
+                P, F = len(grad), gf.size
+                value, grad, gf = float(out[0]), out[1:1 + P], out[1 + P:1 + P + F].reshape(gf.shape)
+                used, bad = int(out[-2]), int(out[-1])
+            return value, grad, gf, used, bad
         if self._fused:
-            return self.local.nll_grad(theta)        # the kernel epilogue already added all ranks
+            value, grad, used, bad = self.local.nll_grad(theta)   # the kernel epilogue already added all ranks
+            return value, grad, None, used, bad
         if self._cuda_reduce is not None:
             buf = self._cuda_reduce
             with self._torch.cuda.stream(self._stream):
                 self.local.nll_grad_dev(theta, buf.data_ptr())
                 parallel.allreduce_sum_tensor(buf)
                 out = buf.cpu().numpy()
-            return float(out[0]), out[1:1 + self.P].copy(), int(out[self.P + 1]), int(out[self.P + 2])
+            return float(out[0]), out[1:1 + self.P].copy(), None, int(out[self.P + 1]), int(out[self.P + 2])
         value, grad, used, bad = self.local.nll_grad(theta)
         if self.world == 1:
-            return value, grad, used, bad
+            return value, grad, None, used, bad
         out = parallel.allreduce_sum(np.concatenate([[value], grad, [used, bad]]))
-        return float(out[0]), out[1:1 + self.P], int(out[self.P + 1]), int(out[self.P + 2])
+        return float(out[0]), out[1:1 + self.P], None, int(out[self.P + 1]), int(out[self.P + 2])
+
+    def set_factors(self, factors):
+        """Factor vectors (m x nf) used by the per-gene statistics, coefficients and weights."""
+        self.local.set_factors(factors)
 
     def per_gene(self, theta):
         score, d2, p = self.local.per_gene(theta)

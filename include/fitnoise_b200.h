@@ -41,6 +41,7 @@ typedef struct fn_family {
     int32_t tail_own;   /* PATSEQ v1: tail = the gene's own y_j; else the count-weighted average tail */
     int32_t v3;         /* PATSEQ v3: sigma2_j = (theta_a/count_j + theta_b) * avgtail^2 */
     int32_t dist;       /* FN_DIST_* : Mvnormal, Mvt with df = theta[0], Mvt with fixed df */
+    int32_t nf;         /* unknown batch-effect factors (Model_*_factors, fitnoise.py:439-518), 0..4; SCALE1 only */
     double fixed_df;    /* Model_independent: 1e-10 (fitnoise.py:577) */
 } fn_family;
 

@@ -237,12 +237,22 @@ MODELS = {
     "Model_normal_patseq": ("patseq_v2", False), "Model_t_patseq": ("patseq_v2", True),
     "Model_normal_patseq_per_sample": ("patseq_v2_per_sample", False),
     "Model_t_patseq_per_sample": ("patseq_v2_per_sample", True),
+    # Model_factors_mixin on top (fitnoise.py:558-565, 592-594); need n_factors at configure time
+    "Model_normal_factors": ("normal", False), "Model_t_factors": ("normal", True),
+    "Model_independent_factors": ("independent", False),
 }
 
 
 class Configured(object):
-    """A model bound to a data set: what Model.fit_noise holds after _configured()."""
-    def __init__(self, model, y, context=None, nan_aware=False):
+    """A model bound to a data set: what Model.fit_noise holds after _configured().
+
+    ``n_factors`` > 0 adds Model_factors_mixin (fitnoise.py:439-518): unknown batch-effect
+    factors f_i = Q2 . pack_i in the orthogonal complement of the design, covariance
+    diag(sigma2) + sum_i f_i f_i', penalty sum_{i<j} (f_i . f_j)^2.  theta is then ordered
+    [df if t] + [pack_1 .. pack_nf] + [the normal model's parameters] (MRO of
+    Model_t_factors: t-mixin outermost, :563-565)."""
+    def __init__(self, model, y, context=None, nan_aware=False, n_factors=0, design=None,
+                 control_design=None, controls=None):
         spec_name, self.is_t = MODELS[model]
         self.model = model
         self.spec = SPECS[spec_name]
@@ -250,6 +260,26 @@ class Configured(object):
         assert self.y.ndim == 2
         context = context or {}
         aux, initial, bounds = self.spec.configure(self.y, context, nan_aware)
+        self.n_factors = int(n_factors)
+        self.factor_Q2 = None
+        if self.n_factors:
+            # Model_factors_mixin._configured, fitnoise.py:490-518
+            m = self.y.shape[1]
+            if controls is not None and np.any(controls):
+                fdesign = np.asarray(control_design, dtype="float64")
+            else:
+                fdesign = np.asarray(design, dtype="float64")
+            Q, R = np.linalg.qr(fdesign, mode="complete")
+            Q2 = Q[:, fdesign.shape[1]:]
+            m2 = Q2.shape[1]
+            good = np.all(np.isfinite(self.y), axis=1)
+            goody = (Q2.T @ self.y[good].T).T
+            u, sv, v = np.linalg.svd(goody, full_matrices=0)
+            rows = np.argsort(-np.abs(sv))[:self.n_factors]
+            finit = list((v[rows] * sv[rows][:, None]).flatten() / np.sqrt(goody.shape[0]))
+            initial = finit + list(initial)
+            bounds = [(None, None)] * (m2 * self.n_factors) + list(bounds)
+            self.factor_Q2 = Q2
         if self.is_t:                                   # Model_t_mixin._configured :431-436
             initial = [5.0] + list(initial)
             bounds = [(1e-3, 100.0)] + list(bounds)
@@ -258,13 +288,48 @@ class Configured(object):
         self.bounds = list(bounds)
 
     def split(self, theta):
-        """Model_t_mixin._unpack :410-416: df is theta[0] for t models."""
+        """Model_t_mixin._unpack :410-416: df is theta[0] for t models; then the factor packs
+        (Model_factors_mixin._unpack :447-458); the rest belongs to the normal model."""
         theta = np.asarray(theta, dtype="float64")
         if self.is_t:
-            return float(theta[0]), theta[1:]
-        if self.spec.name == "independent":
-            return INDEPENDENT_DF, theta
-        return None, theta                               # Mvnormal
+            df, theta = float(theta[0]), theta[1:]
+        elif self.spec.name == "independent":
+            df = INDEPENDENT_DF
+        else:
+            df = None                                    # Mvnormal
+        if self.n_factors:
+            theta = theta[self.factor_Q2.shape[1] * self.n_factors:]
+        return df, theta
+
+    def factors(self, theta):
+        """List of the factor vectors f_i (length m)."""
+        if not self.n_factors:
+            return []
+        theta = np.asarray(theta, dtype="float64")
+        at = 1 if self.is_t else 0
+        m2 = self.factor_Q2.shape[1]
+        return [self.factor_Q2 @ theta[at + i * m2: at + (i + 1) * m2] for i in range(self.n_factors)]
+
+    def model_cost(self, theta):
+        """Model_factors_mixin._model_cost :470-478."""
+        f = self.factors(theta)
+        return sum(float(f[i] @ f[j]) ** 2 for i in range(len(f)) for j in range(i))
+
+    def model_cost_grad(self, theta):
+        theta = np.asarray(theta, dtype="float64")
+        grad = np.zeros(len(theta))
+        f = self.factors(theta)
+        if len(f) < 2:
+            return grad
+        at = 1 if self.is_t else 0
+        m2 = self.factor_Q2.shape[1]
+        for i in range(len(f)):
+            gf = np.zeros(len(f[i]))
+            for j in range(len(f)):
+                if j != i:
+                    gf += 2.0 * float(f[i] @ f[j]) * f[j]
+            grad[at + i * m2: at + (i + 1) * m2] = self.factor_Q2.T @ gf
+        return grad
 
     def sigma2(self, theta, row):
         df, rest = self.split(theta)
@@ -273,6 +338,13 @@ class Configured(object):
     def dsigma2(self, theta, row):
         df, rest = self.split(theta)
         return self.spec.dsigma2(rest, self.aux[row])
+
+    def covariance(self, theta, row):
+        """_get_dist(...).covar: diag(sigma2) (+ sum_i f_i f_i', Model_factors_mixin._get_dist :481-487)."""
+        covar = np.diag(self.sigma2(theta, row))
+        for f in self.factors(theta):
+            covar = covar + np.outer(f, f)
+        return covar
 
     def df_of(self, theta):
         return self.split(theta)[0]
@@ -345,8 +417,7 @@ def prepare_rows(cfg, designs, theta_for_good=None, skip_rank_deficient=False):
 
 def score_row(cfg, theta, row, retain, tQ2, z2):
     """fitnoise.py:44-50: -log density of z2 under marginal(retain).transformed(tQ2)."""
-    s2 = cfg.sigma2(theta, row)
-    covar = np.diag(s2)[np.ix_(retain, retain)]                  # marginal :84-86/:186-188
+    covar = cfg.covariance(theta, row)[np.ix_(retain, retain)]   # marginal :84-86/:186-188
     S = tQ2 @ covar @ tQ2.T                                      # transformed :66-71/:167-173
     return -log_density(S, z2, cfg.df_of(theta))
 
@@ -356,8 +427,7 @@ def score_row_grad(cfg, theta, row, retain, tQ2, z2):
     (what theano.gradient.grad would return, fitnoise.py:93).  Not the REML identities."""
     theta = np.asarray(theta, dtype="float64")
     df = cfg.df_of(theta)
-    s2 = cfg.sigma2(theta, row)
-    covar = np.diag(s2[retain])
+    covar = cfg.covariance(theta, row)[np.ix_(retain, retain)]
     S = tQ2 @ covar @ tQ2.T
     p = S.shape[0]
     Sinv = np.linalg.inv(S)
@@ -366,9 +436,14 @@ def score_row_grad(cfg, theta, row, retain, tQ2, z2):
     M = tQ2.T @ Sinv @ tQ2                  # k x k
     tu = tQ2.T @ u
     kappa = 0.5 if (df is None) else 0.5 * (df + p) / (df + d2)
-    g_s2 = 0.5 * np.diag(M) - kappa * tu * tu          # d(-ll)/d sigma2_j, j in retain
+    g_cov = 0.5 * M - kappa * np.outer(tu, tu)         # d(-ll)/d covar[retain, retain]
+    g_s2 = np.diag(g_cov)                              # d(-ll)/d sigma2_j, j in retain
     ds2 = cfg.dsigma2(theta, row)[:, retain]
     g_rest = ds2 @ g_s2
+    if cfg.n_factors:                                  # d covar = df f' + f df'  ->  2 g_cov f ; f = Q2 pack
+        Q2r = cfg.factor_Q2[retain]
+        g_pack = [Q2r.T @ (2.0 * g_cov @ f[retain]) for f in cfg.factors(theta)]
+        g_rest = np.concatenate(g_pack + [g_rest])
     value = -log_density(S, z2, df)
     if cfg.is_t:
         v = df
@@ -380,13 +455,13 @@ def score_row_grad(cfg, theta, row, retain, tQ2, z2):
 
 
 def total_score(cfg, prepared, theta):
-    """fitnoise.py:63-68 (model cost is 0 for every in-scope model, :204-205)."""
-    return sum(score_row(cfg, theta, row, *item) for row, item in prepared.items())
+    """fitnoise.py:63-68: model cost (:204-205, :470-478) + sum of score_row."""
+    return cfg.model_cost(theta) + sum(score_row(cfg, theta, row, *item) for row, item in prepared.items())
 
 
 def total_score_grad(cfg, prepared, theta):
-    value = 0.0
-    grad = np.zeros(len(np.atleast_1d(theta)))
+    value = cfg.model_cost(theta)
+    grad = cfg.model_cost_grad(theta)
     for row, item in prepared.items():
         v, g = score_row_grad(cfg, theta, row, *item)
         value += v
@@ -445,8 +520,7 @@ def fit_noise(cfg, design, control_design=None, controls=None, force_param=None,
     noise_p = np.repeat(np.nan, n)
     averages = np.repeat(np.nan, n)
     for row, (retain, tQ2, z2) in prepared.items():                           # :259-267
-        s2 = cfg.sigma2(x, row)
-        S = tQ2 @ np.diag(s2[retain]) @ tQ2.T
+        S = tQ2 @ cfg.covariance(x, row)[np.ix_(retain, retain)] @ tQ2.T
         noise_p[row] = tail_p_value(S, z2, df_t)
         averages[row] = np.mean(y[row, retain])
     good_p = noise_p[np.isfinite(noise_p)]                                    # :270-274
@@ -484,7 +558,7 @@ def fit_coef(cfg, theta, design):
         Q, R = np.linalg.qr(design[retain], mode="complete")
         Rinv = np.linalg.inv(R[:c])
         z = Q.T @ y[row, retain]                                              # :324
-        T = Q.T @ np.diag(s2[retain]) @ Q                                     # marginal+transformed
+        T = Q.T @ cfg.covariance(theta, row)[np.ix_(retain, retain)] @ Q     # marginal+transformed
         T11, T12, T21, T22 = T[:c, :c], T[:c, c:], T[c:, :c], T[c:, c:]
         T22inv = np.linalg.inv(T22)
         G = T12 @ T22inv
@@ -542,15 +616,17 @@ def fdr(p):
 
 def get_weights(cfg, theta):
     """Model.get_weights, fitnoise.py:399-404: 1/diag(covar) per gene."""
-    return np.array([1.0 / cfg.sigma2(theta, row) for row in range(cfg.y.shape[0])])
+    return np.array([1.0 / np.diag(cfg.covariance(theta, row)) for row in range(cfg.y.shape[0])])
 
 
 def fit_and_test(model, y, design, context=None, coef_idx=None, contrasts=None,
                  control_design=None, controls=None, noise_design=None, force_param=None,
-                 nan_aware=False, tight=True, skip_rank_deficient=False):
+                 nan_aware=False, tight=True, skip_rank_deficient=False, n_factors=0):
     """Model.fit + .test end to end (fitnoise.py:350-365, 368-396) as one dict."""
-    cfg = Configured(model, y, context, nan_aware=nan_aware)
     nd = design if noise_design is None else noise_design
+    cfg = Configured(model, y, context, nan_aware=nan_aware, n_factors=n_factors, design=nd,
+                     control_design=control_design if control_design is not None else np.ones((np.shape(y)[1], 1)),
+                     controls=controls)
     out = fit_noise(cfg, nd, control_design, controls, force_param, tight=tight,
                     skip_rank_deficient=skip_rank_deficient)
     coef, covar, dfs = fit_coef(cfg, out["x"], design)

@@ -53,9 +53,12 @@ def t_noise(rng, n, m, df):
 
 def run_case(ref, name, model, y, design, theta, context=None, test_coef=None,
              test_contrasts=None, controls=None, control_design=None, noise_design=None,
-             optimise=False):
+             optimise=False, n_factors=0):
+    """`theta` may be a function of the reference's configured initial vector (factor models: the
+    pack coordinates depend on the reference's own Q2)."""
     context = context or {}
-    cls = getattr(ref, model)
+    base_cls = getattr(ref, model)
+    cls = (lambda: base_cls(n_factors)) if n_factors else base_cls
     data = ref.Dataset(y, context)
     n, m = y.shape
     kwargs = dict(design=design, use_theano=False)
@@ -66,8 +69,15 @@ def run_case(ref, name, model, y, design, theta, context=None, test_coef=None,
     if control_design is not None:
         kwargs["control_design"] = control_design
 
+    if callable(theta):
+        nd0 = design if noise_design is None else noise_design
+        cd0 = np.ones((m, 1)) if control_design is None else control_design
+        fl0 = [False] * n if controls is None else list(controls)
+        conf0 = cls()._with(data=data, noise_design=nd0, control_design=cd0, controls=np.asarray(fl0, bool),
+                            _aux=np.zeros((n, 0)))._configured()
+        theta = theta(np.asarray(conf0._initial, float))
     fitted = cls().fit(data, force_param=theta, **kwargs)
-    out = dict(model=model, y=y, design=design, theta=np.asarray(theta, float))
+    out = dict(model=model, y=y, design=design, theta=np.asarray(theta, float), n_factors=np.int64(n_factors))
     for key, value in context.items():
         out[key] = np.asarray(value, float)
     if controls is not None:
@@ -98,7 +108,12 @@ def run_case(ref, name, model, y, design, theta, context=None, test_coef=None,
                         .transformed(tQ2).log_density(z2))
     out["ref_score_rows"] = scores
     out["ref_initial"] = np.asarray(configured._initial, float)
-    out["ref_bounds"] = np.asarray(configured._bounds, float).reshape(-1, 2)
+    out["ref_bounds"] = np.asarray([[np.nan if v is None else v for v in b] for b in configured._bounds],
+                                   float).reshape(-1, 2)
+    if n_factors:
+        out["ref_factor_Q2"] = configured._factor_Q2
+        out["ref_factors"] = np.asarray(fitted.param.factors, float)
+        out["ref_model_cost"] = np.float64(configured._model_cost(configured._unpack(th)))
 
     out["ref_noise_p_values"] = fitted.noise_p_values
     out["ref_averages"] = fitted.averages
@@ -280,6 +295,39 @@ def main():
     y = rng.normal(size=(n, m))
     y[2, 1] = np.nan
     run_case(ref, "t_nan_quirk", "Model_t", y, two_group(m), [5.0, 1.0], test_coef=[1])
+
+    # 10. Unknown batch-effect factors (Model_factors_mixin, fitnoise.py:439-518).
+    def factor_data(n, m, nf, sd=0.7):
+        load = rng.normal(size=(n, nf)) * 1.5
+        batch = rng.normal(size=(nf, m))
+        return rng.normal(size=(n, m)) * sd + load @ batch
+
+    perturb = lambda init: init * (1.0 + 0.1 * np.cos(np.arange(len(init)) + 1.0))
+    n, m = 80, 6
+    y = factor_data(n, m, 1)
+    y[:8, 3:] += 3.0
+    run_case(ref, "t_factors1", "Model_t_factors", y, two_group(m), perturb, test_coef=[1],
+             n_factors=1, optimise=True)
+    n, m = 60, 8
+    w = np.exp(rng.normal(0, 0.4, size=(n, m)))
+    y = factor_data(n, m, 2) / np.sqrt(w)
+    w[4, 1] = 0.0
+    run_case(ref, "normal_factors2_weights", "Model_normal_factors", y, two_group(m), perturb,
+             context={"weights": w}, test_coef=[1], n_factors=2)
+    n, m = 60, 6
+    y = factor_data(n, m, 1)
+    y[3, 0] = np.nan; y[7, 4:] = np.nan; y[9, :] = np.nan; y[11, 3:] = np.nan
+    run_case(ref, "independent_factors1_nan", "Model_independent_factors", y, two_group(m), perturb,
+             test_coef=[1], n_factors=1)
+    n, m = 70, 8
+    treat = (np.arange(m) >= m // 2) * 1.0
+    design = np.stack([np.ones(m), treat, (np.arange(m) % 2) * 1.0], axis=1)
+    control_design = np.stack([np.ones(m), (np.arange(m) % 2) * 1.0], axis=1)
+    y = factor_data(n, m, 1)
+    y[:7] += 2.0 * treat
+    controls = np.arange(n) % 3 == 0
+    run_case(ref, "t_factors1_controls", "Model_t_factors", y, design, perturb, test_coef=[1],
+             controls=controls, control_design=control_design, n_factors=1)
 
     # 9. fdr vectors (p_adjust.py:3-21).
     p1 = rng.random(500); p1[::17] = np.nan; p1[5] = p1[6] = p1[7]; p1[20] = 0.0; p1[21] = 1.0

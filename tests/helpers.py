@@ -49,7 +49,8 @@ def check_against_golden(g, fitted, tested, rtol=1e-9, p_rtol=1e-8):
 
 
 def fit_golden(g, engine_factory=None, **extra):
-    model = getattr(fitnoise, str(g["model"]))()
+    nf = int(g.get("n_factors", 0))
+    model = getattr(fitnoise, str(g["model"]))(nf) if nf else getattr(fitnoise, str(g["model"]))()
     if engine_factory is not None:
         model = model._with(_engine_factory=engine_factory)
     data = fitnoise.Dataset(g["y"], golden_context(g))

@@ -93,6 +93,7 @@ class HostEvaluator(object):
         self.dn = np.ascontiguousarray(design_noise, dtype=np.float64)
         self.dc = np.ascontiguousarray(np.ones((self.m, 1)) if design_ctrl is None else design_ctrl,
                                        dtype=np.float64)
+        self.F = np.zeros((self.m, max(family.nf, 1)))
         theta0 = np.ones(max(family.theta_length(), 1))
         r = self._eval(theta0)
         info = _Info()
@@ -110,16 +111,27 @@ class HostEvaluator(object):
         pdf, elig = np.empty(n, np.int32), np.empty(n, np.uint8)
         val, rv, bad = ctypes.c_double(), ctypes.c_double(), ctypes.c_long()
         grad = np.zeros(max(P, 1))
+        F = np.ascontiguousarray(self.F, dtype=np.float64)
+        grad_f = np.zeros_like(F)
         rc = self.lib.hc_eval(
             ctypes.byref(self.family), ctypes.c_long(n), self.m, _dp(self.y), _dp(self.aux),
             self.controls.ctypes.data_as(U8) if self.controls is not None else None,
             self.dn.shape[1], _dp(self.dn), self.dc.shape[1], _dp(self.dc), _dp(theta),
             _dp(score), _dp(d2), pdf.ctypes.data_as(I32), _dp(avg), elig.ctypes.data_as(U8),
-            ctypes.byref(val), _dp(grad), ctypes.byref(rv), ctypes.byref(bad))
+            ctypes.byref(val), _dp(grad), ctypes.byref(rv), ctypes.byref(bad), _dp(F), _dp(grad_f))
         if rc != 0:
             raise RuntimeError("hc_eval failed with %d" % rc)
         return dict(score=score, d2=d2, p=pdf, averages=avg, eligible=elig, value=val.value,
-                    grad=grad[:P], rowvar=rv.value, bad=bad.value)
+                    grad=grad[:P], rowvar=rv.value, bad=bad.value, grad_f=grad_f)
+
+    def set_factors(self, F):
+        self.F = np.ascontiguousarray(F, dtype=np.float64).reshape(self.m, -1)
+
+    def nll_grad_factors(self, theta, F):
+        self.set_factors(F)
+        r = self._eval(theta)
+        used = int(np.isfinite(r["score"]).sum())
+        return r["value"], r["grad"], r["grad_f"], used, 0
 
     def nll_grad(self, theta):
         r = self._eval(theta)
@@ -149,7 +161,8 @@ class HostEvaluator(object):
         c = design.shape[1]
         coef, covar, dfp = np.empty((self.n, c)), np.empty((self.n, c, c)), np.empty(self.n)
         rc = self.lib.hc_coef(ctypes.byref(self.family), ctypes.c_long(self.n), self.m, _dp(self.y),
-                              _dp(self.aux), c, _dp(design), _dp(theta), _dp(coef), _dp(covar), _dp(dfp))
+                              _dp(self.aux), c, _dp(design), _dp(theta), _dp(coef), _dp(covar), _dp(dfp),
+                              _dp(np.ascontiguousarray(self.F, dtype=np.float64)))
         if rc != 0:
             raise RuntimeError("hc_coef failed with %d" % rc)
         self._coef = (coef, covar, dfp, int(self.family.dist != 0))
@@ -205,4 +218,6 @@ class HostEvaluator(object):
                 T = y0 * y0 if fam.tail_own else np.broadcast_to(gs, self.y.shape)
                 return 1.0 / (a * U + b * T)
             w = np.ones_like(self.y) if self.aux is None else self.aux
+            if fam.nf:
+                return 1.0 / ((a if fam.na else 1.0) / w + (self.F ** 2).sum(axis=1)[None, :])
             return w / (a if fam.na else 1.0)

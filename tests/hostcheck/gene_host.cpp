@@ -52,14 +52,18 @@ extern "C" {
 
 // One likelihood + gradient evaluation over all genes.  grad has theta_length entries.
 // Widths of the two designs are rounded up to the same template width (max of the two).
+// factors: F is m x fam->nf (may be NULL when nf == 0); grad_f receives d/dF (m x nf).
 int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux_raw,
             const uint8_t* controls, int c_noise, const double* xn, int c_ctrl, const double* xc,
             const double* theta, double* score, double* d2, int* pdf, double* averages,
-            uint8_t* eligible, double* value_total, double* grad, double* rowvar_mean, long* bad_counts) {
+            uint8_t* eligible, double* value_total, double* grad, double* rowvar_mean, long* bad_counts,
+            const double* F, double* grad_f) {
     Design dn, dc;
     if (!dn.build(m, c_noise, xn)) return -1;
     if (!dc.build(m, c_ctrl, xc)) return -2;
-    const int width = dn.width > dc.width ? dn.width : dc.width;
+    const int nf = fam->nf;
+    const int width = round_width((dn.c > dc.c ? dn.c : dc.c) + nf);
+    if (width < 0) return -5;
     // re-pad both to the common width
     auto repad = [&](Design& d) {
         std::vector<double> q((size_t)m * width, 0.0);
@@ -81,6 +85,12 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
     FN_DISPATCH_WIDTH(width, prepare_all<C>(*fam, n, m, y, aux_raw, controls, dn, dc, pr));
     *rowvar_mean = pr.rowvar_mean; *bad_counts = pr.bad_counts;
 
+    std::vector<double> zn, zc, gscratch((size_t)m * (nf ? nf : 1), 0.0);
+    if (nf) {
+        zn = augment_design(dn, width, nf, F);
+        zc = augment_design(dc, width, nf, F);
+        for (int i = 0; i < m * nf; ++i) grad_f[i] = 0.0;
+    }
     const int P = theta_length(*fam);
     for (int i = 0; i < P; ++i) grad[i] = 0.0;
     const int off_a = fam->dist == DIST_T ? 1 : 0, off_b = off_a + fam->na;
@@ -94,7 +104,8 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
         EvalOut eo;
         const bool inpl_a = fam->na == m && fam->kind != KIND_SCALE1, inpl_b = fam->nb == m;
         FN_DISPATCH_WIDTH(width,
-            if (fam->kind == KIND_SCALE1) eval_scale1<C>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], eo);
+            if (nf) eval_factors<C>(ec, gv, ((controls && controls[g]) ? zc : zn).data(), d.c, nf, pr.eligible[g], pr.cst[g], gscratch.data(), eo);
+            else if (fam->kind == KIND_SCALE1) eval_scale1<C>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], eo);
             else if (fam->kind == KIND_SCALE_PS) eval_general<C, KIND_SCALE_PS>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], inpl_a, inpl_b, eo);
             else eval_general<C, KIND_PATSEQ>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], inpl_a, inpl_b, eo));
         score[g] = eo.used ? eo.value : NAN;
@@ -107,6 +118,7 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
             if (fam->na == 1) grad[off_a] += eo.ga;
             if (fam->nb == 1) grad[off_b] += eo.gb;
         }
+        if (nf) for (int i = 0; i < m * nf; ++i) grad_f[i] += gscratch[i];
         if (inpl_a) for (int j = 0; j < m; ++j) grad[off_a + j] += row[j];
         if (inpl_b) for (int j = 0; j < m; ++j) grad[off_b + j] += arow[j];
     }
@@ -117,9 +129,19 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
 }
 
 int hc_coef(const Family* fam, long n, int m, const double* y, const double* aux_raw,
-            int c, const double* x, const double* theta, double* coef, double* covar, double* dfpost) {
+            int c, const double* x, const double* theta, double* coef, double* covar, double* dfpost,
+            const double* F) {
     Design d;
     if (!d.build(m, c, x)) return -1;
+    const int nf = fam->nf;
+    std::vector<double> z;
+    if (nf) {
+        const int width = round_width(c + nf);
+        if (width < 0) return -5;
+        z = augment_design(d, width, nf, F);
+        d.width = width;
+        d.q = z;
+    }
     double v, theta0; int is_t;
     std::vector<double> ta, tb;
     if (!unpack_theta(*fam, m, theta, v, is_t, theta0, ta, tb)) return -4;
@@ -136,7 +158,7 @@ int hc_coef(const Family* fam, long n, int m, const double* y, const double* aux
         gv.setup(m, 0, 1, 0);
         double beta[8], ainv[36];
         CoefOut co;
-        FN_DISPATCH_WIDTH(d.width, coef_gene<C>(ec, gv, d.q.data(), d.c, beta, ainv, co));
+        FN_DISPATCH_WIDTH(d.width, coef_gene<C>(ec, gv, d.q.data(), d.c, nf, beta, ainv, co));
         double* cf = coef + g * c; double* cv = covar + g * c * c;
         if (!co.ok) {
             for (int i = 0; i < c; ++i) cf[i] = NAN;

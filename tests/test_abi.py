@@ -32,5 +32,5 @@ def test_version_and_device_count():
 
 
 def test_family_struct_layout():
-    assert ctypes.sizeof(_native.Family) == 32
+    assert ctypes.sizeof(_native.Family) == 40
     assert ctypes.sizeof(_native.PrepInfo) == 40

@@ -12,7 +12,7 @@ from conftest import assert_close, golden_context, golden_fit_kwargs, load_golde
 from helpers import fit_golden
 from oracle import fitnoise_oracle as oracle
 
-OPT_CASES = ["t_twogroup", "t_patseq_v2", "t_controls_opt"]
+OPT_CASES = ["t_twogroup", "t_patseq_v2", "t_controls_opt", "t_factors1"]
 
 
 @pytest.mark.parametrize("name", OPT_CASES)
@@ -23,7 +23,7 @@ def test_fitted_hyperparameters_match_oracle(name):
     fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator)
     ref = oracle.fit_and_test(str(g["model"]), g["y"], g["design"], golden_context(g),
                               coef_idx=[int(i) for i in g["test_coef"]], nan_aware=True,
-                              skip_rank_deficient=True,
+                              skip_rank_deficient=True, n_factors=int(g.get("n_factors", 0)),
                               **golden_fit_kwargs(g))
     x, rx = fitted.optimization_result.x, ref["x"]
     free = ~(np.isclose(rx, 100.0) | np.isclose(rx, 1e-3))          # df may sit on its bound
@@ -96,8 +96,8 @@ def test_errors():
     with pytest.raises(AssertionError):                           # zero count with finite tail
         fitnoise.Model_t_patseq()._with(_engine_factory=hostcheck.HostEvaluator).fit(
             fitnoise.Dataset(y, {"counts": counts}), design)
-    with pytest.raises(NotImplementedError):
-        fitnoise.Model_t_factors(1)
+    with pytest.raises(AssertionError):                           # factors need a SCALE1 variance model
+        type("Bad", (fitnoise.Model_factors_mixin, fitnoise.Model_normal_per_sample), {})(1)._family(6)
     with pytest.raises(NotImplementedError):
         fitnoise.transform(y)
 

@@ -35,7 +35,7 @@ def _run_case(name, forced):
         kw["force_param"] = g["theta"]
     fitted = model.fit(fitnoise.Dataset(g["y"], golden_context(g)), design=g["design"], **kw)
     tested = fitted.test(**golden_test_kwargs(g))
-    value, grad, used, bad = fitted._session.nll_grad(g["theta"])
+    value, grad, used, bad = fitted._objective(g["theta"])
     return dict(x=np.asarray(fitted.optimization_result.x), value=value, grad=grad, used=used,
                 noise_p=fitted.noise_p_values, averages=fitted.averages, coef=fitted.coef,
                 covar=fitted._coef_covar, p=tested.p_values, q=tested.q_values, weights=fitted.get_weights(),

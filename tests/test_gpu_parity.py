@@ -31,7 +31,7 @@ def test_golden_forced_param(name):
     g = load_golden(name)
     fitted, tested = fit_golden(g, force_param=g["theta"])
     check_against_golden(g, fitted, tested)
-    score, d2, p = fitted._session.per_gene(g["theta"])
+    score, d2, p = fitted._session.per_gene(fitted._theta)
     ref = g["ref_score_rows"].copy()
     ref[rank_deficient_rows(g)] = np.nan
     assert_close(score, ref, 1e-9, what="per-gene score_row")
@@ -46,7 +46,7 @@ def test_golden_value_and_gradient(name):
     if len(theta) == 0:
         pytest.skip("no hyper-parameters")
     fitted, _ = fit_golden(g, force_param=theta)
-    value, grad, used, bad = fitted._session.nll_grad(theta)
+    value, grad, used, bad = fitted._objective(theta)
     cfg = oracle.Configured(str(g["model"]), g["y"], golden_context(g))
     kw = golden_fit_kwargs(g)
     out = oracle.fit_noise(cfg, g.get("noise_design", g["design"]), kw.get("control_design"),
@@ -162,7 +162,7 @@ def test_synthetic_configs_against_oracle(config, n):
     assert_close(tested.p_values, ref["p_values"], 1e-8, what="p")
     assert np.array_equal(tested.q_values, oracle.fdr(tested.p_values)), "BH not bit-exact"
     if len(theta):
-        value, grad, used, bad = fitted._session.nll_grad(theta)
+        value, grad, used, bad = fitted._objective(theta)
         ov, og = oracle.total_score_grad(ref["cfg"], ref["prepared"], theta)
         assert_close(value, ov, 1e-11, what="objective")
         assert_close(grad, og, 1e-8, atol=1e-9 * abs(ov), what="gradient")

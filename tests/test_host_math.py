@@ -63,7 +63,7 @@ def test_kernel_math_matches_reference_golden(name):
     g = load_golden(name)
     fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
     check_against_golden(g, fitted, tested)
-    score, d2, p = fitted._session.per_gene(g["theta"])
+    score, d2, p = fitted._session.per_gene(fitted._theta)
     ref = g["ref_score_rows"].copy()
     from helpers import rank_deficient_rows
     ref[rank_deficient_rows(g)] = np.nan
@@ -96,13 +96,39 @@ def test_blocked_sample_order(model):
     fitted = getattr(fitnoise, model)()._with(_engine_factory=hostcheck.HostEvaluator).fit(
         fitnoise.Dataset(y, context), design, force_param=theta)
     ref = oracle.fit_and_test(model, y, design, context, coef_idx=[1], force_param=theta, nan_aware=True)
-    score, d2, p = fitted._session.per_gene(theta)
+    score, d2, p = fitted._session.per_gene(fitted._theta)
     want = np.full(n, np.nan)
     for row, item in ref["prepared"].items():
         want[row] = oracle.score_row(ref["cfg"], np.asarray(theta), row, *item)
     assert_close(score, want, 1e-9, what="score")
-    value, grad, used, bad = fitted._session.nll_grad(theta)
+    value, grad, used, bad = fitted._objective(theta)
     ov, og = oracle.total_score_grad(ref["cfg"], ref["prepared"], np.asarray(theta))
     assert_close(value, ov, 1e-11)
     assert_close(grad, og, 1e-8, atol=1e-9 * abs(ov))
     assert_close(fitted.coef, ref["coef"], 1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_objective_and_gradient_match_oracle(name):
+    """Packed-theta objective (incl. the factor penalty and the chain rule through Q2) against the
+    oracle's matrix-calculus gradient on the reference's own covariance."""
+    from conftest import assert_close, golden_context, golden_fit_kwargs
+    from helpers import rank_deficient_rows
+    from oracle import fitnoise_oracle as oracle
+    g = load_golden(name)
+    theta = g["theta"]
+    if len(theta) == 0:
+        pytest.skip("no hyper-parameters")
+    fitted, _ = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=theta)
+    value, grad, used, bad = fitted._objective(theta)
+    kw = golden_fit_kwargs(g)
+    nd = g.get("noise_design", g["design"])
+    cfg = oracle.Configured(str(g["model"]), g["y"], golden_context(g), n_factors=int(g.get("n_factors", 0)),
+                            design=nd, control_design=kw.get("control_design", np.ones((g["y"].shape[1], 1))),
+                            controls=kw.get("controls"))
+    out = oracle.fit_noise(cfg, nd, kw.get("control_design"), kw.get("controls"), force_param=theta,
+                           skip_rank_deficient=True)
+    ov, og = oracle.total_score_grad(cfg, out["prepared"], theta)
+    assert used == len(out["prepared"]) and bad == 0
+    assert_close(value, ov, 1e-11, what="objective")
+    assert_close(grad, og, 1e-8, atol=1e-9 * abs(ov), what="gradient")

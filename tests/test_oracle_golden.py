@@ -22,7 +22,8 @@ def run_oracle(g, **extra):
     else:
         kw["contrasts"] = g["test_contrasts"]
     kw.update(extra)
-    return oracle.fit_and_test(str(g["model"]), g["y"], g["design"], golden_context(g), **kw)
+    return oracle.fit_and_test(str(g["model"]), g["y"], g["design"], golden_context(g),
+                               n_factors=int(g.get("n_factors", 0)), **kw)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -31,7 +32,11 @@ def test_forced_param_outputs(name):
     out = run_oracle(g, force_param=g["theta"])
     cfg = out["cfg"]
     assert_close(cfg.initial, g["ref_initial"], 1e-14, what="initial")
-    assert_close(np.asarray(cfg.bounds, float).reshape(-1, 2), g["ref_bounds"], 1e-14, what="bounds")
+    bounds = np.asarray([[np.nan if v is None else v for v in b] for b in cfg.bounds], float).reshape(-1, 2)
+    assert_close(bounds, g["ref_bounds"], 1e-14, what="bounds")
+    if "ref_factors" in g:
+        assert_close(np.asarray(cfg.factors(g["theta"])), g["ref_factors"], 1e-13, what="factors")
+        assert_close(cfg.model_cost(g["theta"]), g["ref_model_cost"], 1e-12, atol=1e-300, what="model cost")
 
     n = g["y"].shape[0]
     scores = np.repeat(np.nan, n)
