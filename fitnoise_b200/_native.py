@@ -25,7 +25,7 @@ EXPORTS = [
     "fn_upload", "fn_upload_dev", "fn_nll_grad", "fn_nll_grad_dev", "fn_per_gene", "fn_noise_stats",
     "fn_coef", "fn_test", "fn_bh", "fn_bh_dev", "fn_weights", "fn_set_tuning", "fn_launch_count",
     "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
-    "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked",
+    "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked", "fn_nll_grad_factors", "fn_set_factors",
 ]
 
 
@@ -87,6 +87,10 @@ def load_library():
     lib.fn_upload_dev.argtypes = upload_args
     lib.fn_nll_grad.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p,
                                 ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    lib.fn_nll_grad_factors.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p,
+                                        c_double_p, c_double_p, ctypes.POINTER(ctypes.c_int64),
+                                        ctypes.POINTER(ctypes.c_int64)]
+    lib.fn_set_factors.argtypes = [ctypes.c_void_p, c_double_p]
     lib.fn_nll_grad_dev.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_void_p]
     lib.fn_per_gene.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_int32_p]
     lib.fn_noise_stats.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p]
@@ -194,6 +198,22 @@ class Engine(object):
         self._check(self._lib.fn_nll_grad(self._h, _dp(theta), P, ctypes.byref(value), _dp(grad),
                                           ctypes.byref(used), ctypes.byref(bad)))
         return value.value, grad[:P], used.value, bad.value
+
+    def nll_grad_factors(self, theta, factors):
+        """Factor models: (value, grad of [df, variance], d/dF (m x nf), n_used, n_bad)."""
+        theta = _f64(theta).reshape(-1)
+        factors = _f64(factors).reshape(self.m, -1)
+        P = len(theta)
+        value = ctypes.c_double()
+        grad, grad_f = np.zeros(max(P, 1)), np.zeros_like(factors)
+        used, bad = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.fn_nll_grad_factors(self._h, _dp(theta), P, _dp(factors), ctypes.byref(value),
+                                                  _dp(grad), _dp(grad_f), ctypes.byref(used), ctypes.byref(bad)))
+        return value.value, grad[:P], grad_f, used.value, bad.value
+
+    def set_factors(self, factors):
+        factors = _f64(factors).reshape(self.m, -1)
+        self._check(self._lib.fn_set_factors(self._h, _dp(factors)))
 
     def nll_grad_dev(self, theta, out_ptr):
         theta = _f64(theta).reshape(-1)

@@ -79,6 +79,10 @@ struct fn_handle {
     DevBuf b_y, b_aux, b_gs, b_cst, b_avg, b_status, b_xn, b_xc, b_tab, b_pg_score, b_pg_d2, b_pg_p, b_noise_p,
         b_coef, b_covar, b_dfpost, b_xcoef, b_rinv;
     size_t tab_host_cap = 0;
+    // factor models: current factor vectors (m x nf) and the augmented design tables built from them
+    std::vector<double> factors;
+    DevBuf b_zn, b_zc, b_fsq;
+    double *zn = nullptr, *zc = nullptr, *fsq = nullptr;
     // pinned staging for uploads from pageable host memory
     static const int kStageWorkers = 8;
     void* stage_buf[2 * kStageWorkers] = {nullptr};
@@ -142,6 +146,8 @@ static void release_data(fn_handle* h) {
     h->pg_score = h->pg_d2 = h->noise_p = nullptr;
     h->pg_p = nullptr;
     h->coef = h->covar = h->dfpost = h->x_coef = h->rinv_dev = nullptr;
+    h->zn = h->zc = h->fsq = nullptr;
+    h->factors.clear();
     h->loaded = false;
     h->coef_c = 0;
 }
@@ -150,7 +156,7 @@ static void free_buffers(fn_handle* h) {
     release_data(h);
     DevBuf* all[] = {&h->b_y, &h->b_aux, &h->b_gs, &h->b_cst, &h->b_avg, &h->b_status, &h->b_xn, &h->b_xc, &h->b_tab,
                      &h->b_pg_score, &h->b_pg_d2, &h->b_pg_p, &h->b_noise_p, &h->b_coef, &h->b_covar, &h->b_dfpost,
-                     &h->b_xcoef, &h->b_rinv};
+                     &h->b_xcoef, &h->b_rinv, &h->b_zn, &h->b_zc, &h->b_fsq};
     for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     if (h->tab_host) { cudaFreeHost(h->tab_host); h->tab_host = nullptr; h->tab_host_cap = 0; }
     for (int i = 0; i < 2 * fn_handle::kStageWorkers; ++i) {
@@ -249,7 +255,8 @@ extern "C" double fn_last_kernel_ms(fn_handle* h) {
 // ------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------
-static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_bytes, Geom& g, int min_threads = 0) {
+static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_bytes, Geom& g, int min_threads = 0,
+                       size_t per_gene_extra = 0) {
     const int m = h->m;
     int ctas = h->tune_ctas > 0 ? h->tune_ctas : 2;
     int threads = h->tune_threads > 0 ? h->tune_threads : 256;
@@ -261,13 +268,13 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     int lpg = h->tune_lpg > 0 ? h->tune_lpg : 1;
     if (h->tune_lpg == 0) {
         while (lpg < 32 && threads / (lpg * 2) >= 16 &&
-               tile_stage_bytes(threads / lpg, m, aux, gs, cst) > stage_target) lpg *= 2;
+               tile_stage_bytes(threads / lpg, m, aux, gs, cst) + (size_t)(threads / lpg) * per_gene_extra > stage_target) lpg *= 2;
     }
     if (lpg > 32 || threads % lpg || (threads / lpg) % 16)
         return fail(FN_ERR_ARG, "invalid geometry: threads %d lpg %d (genes per tile must be a multiple of 16)", threads, lpg);
     const int genes = threads / lpg;
     const size_t stage = tile_stage_bytes(genes, m, aux, gs, cst);
-    const size_t fixed = table_bytes + 256;
+    const size_t fixed = table_bytes + 256 + (size_t)genes * per_gene_extra;
     if (fixed + stage > h->smem_optin - 1024)
         return fail(FN_ERR_UNSUPPORTED, "m = %d is too large for one tile stage in shared memory (%zu bytes)", m, fixed + stage);
     int stages = h->tune_stages > 0 ? h->tune_stages : 3;
@@ -451,7 +458,9 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     if (!design_ctrl) { design_ctrl = ones.data(); c_ctrl = 1; }      // fitnoise.py:216
     if (c_ctrl < 1 || c_ctrl > FN_MAXC) return fail(FN_ERR_UNSUPPORTED, "control design has %d columns; 1..%d supported", c_ctrl, FN_MAXC);
     if (!dc.build(m, c_ctrl, design_ctrl)) return fail(FN_ERR_ARG, "control design (%d x %d) is rank deficient", m, c_ctrl);
-    const int width = dn.width > dc.width ? dn.width : dc.width;
+    const int width = round_width((dn.c > dc.c ? dn.c : dc.c) + fam.nf);
+    if (width < 0) return fail(FN_ERR_UNSUPPORTED, "design columns + factors = %d; at most %d supported", (dn.c > dc.c ? dn.c : dc.c) + fam.nf, FN_MAXC);
+    if (fam.nf > 0 && m * fam.nf > 256) return fail(FN_ERR_UNSUPPORTED, "factor models support m * n_factors <= 256 (m = %d, n_factors = %d)", m, fam.nf);
     auto repad = [&](Design& d) {
         std::vector<double> q((size_t)m * width, 0.0);
         for (int j = 0; j < m; ++j)
@@ -663,6 +672,100 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// factor models
+// ------------------------------------------------------------------------------------------
+static int set_factors(fn_handle* h, const double* F) {
+    const int m = h->m, nf = h->fam.nf, width = h->width;
+    if (nf <= 0) return fail(FN_ERR_STATE, "the uploaded family has no factors");
+    if (!F) return fail(FN_ERR_ARG, "factors is NULL");
+    for (int i = 0; i < m * nf; ++i) if (!(fabs(F[i]) < INFINITY)) return fail(FN_ERR_ARG, "factors must be finite");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));        // the previous kernel may still read the tables
+    h->factors.assign(F, F + (size_t)m * nf);
+    const std::vector<double> zn = augment_design(h->dn, width, nf, F), zc = augment_design(h->dc, width, nf, F);
+    std::vector<double> fsq(m, 0.0);
+    for (int j = 0; j < m; ++j) for (int f = 0; f < nf; ++f) fsq[j] += F[j * nf + f] * F[j * nf + f];
+    const size_t zb = (size_t)m * width * sizeof(double);
+    CUDA_TRY(ensure_buf(h->b_zn, zb));
+    CUDA_TRY(ensure_buf(h->b_zc, zb));
+    CUDA_TRY(ensure_buf(h->b_fsq, m * sizeof(double)));
+    h->zn = (double*)h->b_zn.p; h->zc = (double*)h->b_zc.p; h->fsq = (double*)h->b_fsq.p;
+    CUDA_TRY(cudaMemcpy(h->zn, zn.data(), zb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->zc, zc.data(), zb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->fsq, fsq.data(), m * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int fn_set_factors(fn_handle* h, const double* factors) {
+    if (!h || !h->loaded) return fail(FN_ERR_STATE, "no data uploaded");
+    return set_factors(h, factors);
+}
+
+static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene, bool exchange) {
+    const int m = h->m, nf = h->fam.nf, ncol = m * nf;
+    if (!h->zn) return fail(FN_ERR_STATE, "factors have not been set (fn_set_factors / fn_nll_grad_factors)");
+    Geom g;
+    const size_t table_bytes = (2 * (size_t)m * h->width + 2 * (m + 1) + ACC_FIXED + ncol + 256) * sizeof(double);
+    int rc = choose_geom(h, h->has_aux, false, per_gene, table_bytes, g, ncol, (size_t)ncol * sizeof(double));
+    if (rc) return rc;
+    if (ncol > g.threads) return fail(FN_ERR_UNSUPPORTED, "factor models need m * n_factors <= threads per CTA (%d)", g.threads);
+    const int nacc = ACC_FIXED + ncol;
+    rc = ensure_reduce(h, g.grid, nacc);
+    if (rc) return rc;
+    if (per_gene && !h->pg_score) {
+        CUDA_TRY(ensure_buf(h->b_pg_score, h->n * sizeof(double)));
+        CUDA_TRY(ensure_buf(h->b_pg_d2, h->n * sizeof(double)));
+        CUDA_TRY(ensure_buf(h->b_pg_p, h->n * sizeof(int)));
+        h->pg_score = (double*)h->b_pg_score.p; h->pg_d2 = (double*)h->b_pg_d2.p; h->pg_p = (int*)h->b_pg_p.p;
+    }
+    EvalFactorsParams ep;
+    ep.g = geom_params(h, g);
+    ep.src.y = h->y; ep.src.aux = h->aux; ep.src.gs = nullptr; ep.src.cst = per_gene ? h->cst : nullptr;
+    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes;
+    ep.zn = h->zn; ep.zc = h->zc; ep.c_noise = h->dn.c; ep.c_ctrl = h->dc.c; ep.nf = nf;
+    ep.is_t = ts.is_t; ep.v = ts.v; ep.theta0 = ts.theta0;
+    ep.pg_score = per_gene ? h->pg_score : nullptr;
+    ep.pg_d2 = per_gene ? h->pg_d2 : nullptr;
+    ep.pg_p = per_gene ? h->pg_p : nullptr;
+    fill_reduce(h, ep.gr, nacc, per_gene ? -1 : ACC_VALUE, per_gene ? 0.0 : 0.5 * h->cst_sum, exchange);
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    FN_DISPATCH_WIDTH(h->width, {
+        rc = set_smem(h, eval_factors_kernel<C>, g.smem);
+        if (rc) return rc;
+        eval_factors_kernel<C><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
+    });
+    if (h->timing) { CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->timing_pending = true; }
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fn_nll_grad_factors(fn_handle* h, const double* theta, int32_t P, const double* factors,
+                                   double* value, double* grad, double* grad_factors, int64_t* n_used, int64_t* n_bad) {
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    rc = set_factors(h, factors);
+    if (rc) return rc;
+    rc = launch_eval_factors(h, ts, false, true);
+    if (rc) return rc;
+    const int m = h->m, nf = h->fam.nf, nacc = ACC_FIXED + m * nf;
+    rc = wait_result(h, h->host_seq, nacc);
+    if (rc) return rc;
+    const double* acc = h->out_host;
+    if (value) *value = acc[ACC_VALUE];
+    if (grad) {
+        int at = 0;
+        if (h->fam.dist == DIST_T) grad[at++] = acc[ACC_DV];
+        if (h->fam.na == 1) grad[at++] = acc[ACC_GA];
+    }
+    if (grad_factors) for (int i = 0; i < m * nf; ++i) grad_factors[i] = acc[ACC_FIXED + i];
+    if (n_used) *n_used = (int64_t)acc[ACC_USED];
+    if (n_bad) *n_bad = (int64_t)acc[ACC_BAD];
+    return 0;
+}
+
 // raw accumulators -> [value, grad[P], n_used, n_bad].  `ta` = theta_a by sample: the PATSEQ kernels
 // return term a multiplied by theta_a(j).
 static void assemble(const fn_handle* h, const double* acc, const double* ta, double* out) {
@@ -685,6 +788,7 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
+    if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
     rc = launch_eval(h, ts, false, true);
     if (rc) return rc;
     rc = wait_result(h, h->host_seq, eval_nacc(h));
@@ -718,6 +822,7 @@ extern "C" int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, dou
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
+    if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
     rc = launch_eval(h, ts, false, false);
     if (rc) return rc;
     assemble_kernel<<<1, 32, 0, h->stream>>>(h->out_dev, out_dev, h->fam, h->m, h->tab_dev);
@@ -730,7 +835,7 @@ extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double*
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
-    rc = launch_eval(h, ts, true, false);
+    rc = h->fam.nf > 0 ? launch_eval_factors(h, ts, true, false) : launch_eval(h, ts, true, false);
     if (rc) return rc;
     if (score) CUDA_TRY(cudaMemcpyAsync(score, h->pg_score, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (d2) CUDA_TRY(cudaMemcpyAsync(d2, h->pg_d2, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -743,7 +848,7 @@ extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, doub
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
-    rc = launch_eval(h, ts, true, false);
+    rc = h->fam.nf > 0 ? launch_eval_factors(h, ts, true, false) : launch_eval(h, ts, true, false);
     if (rc) return rc;
     if (!h->noise_p) {
         CUDA_TRY(ensure_buf(h->b_noise_p, h->n * sizeof(double)));
@@ -774,6 +879,14 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     CUDA_TRY(ensure_buf(h->b_coef, (size_t)h->n * c * sizeof(double)));
     CUDA_TRY(ensure_buf(h->b_covar, (size_t)h->n * c * c * sizeof(double)));
     CUDA_TRY(ensure_buf(h->b_dfpost, (size_t)h->n * sizeof(double)));
+    const int nf = h->fam.nf;
+    if (nf > 0) {
+        if (h->factors.empty()) return fail(FN_ERR_STATE, "factors have not been set (fn_set_factors)");
+        const int width = round_width(c + nf);
+        if (width < 0) return fail(FN_ERR_UNSUPPORTED, "design columns + factors = %d; at most %d supported", c + nf, FN_MAXC);
+        d.q = augment_design(d, width, nf, h->factors.data());
+        d.width = width;
+    }
     CUDA_TRY(ensure_buf(h->b_xcoef, (size_t)m * d.width * sizeof(double)));
     CUDA_TRY(ensure_buf(h->b_rinv, (size_t)c * c * sizeof(double)));
     h->coef = (double*)h->b_coef.p; h->covar = (double*)h->b_covar.p; h->dfpost = (double*)h->b_dfpost.p;
@@ -792,7 +905,7 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     cp.g.width = d.width;
     cp.src.y = h->y; cp.src.aux = h->aux; cp.src.gs = h->gs; cp.src.cst = nullptr; cp.src.status = h->status;
     cp.src.m = m; cp.src.genes = g.genes;
-    cp.x = h->x_coef; cp.rinv = h->rinv_dev; cp.c = c;
+    cp.x = h->x_coef; cp.rinv = h->rinv_dev; cp.c = c; cp.nf = nf;
     cp.kind = h->fam.kind; cp.tail_own = h->fam.tail_own; cp.v3 = h->fam.v3; cp.is_t = ts.is_t;
     cp.v = ts.v; cp.theta0 = ts.theta0;
     cp.ta = h->fam.kind != KIND_SCALE1 ? h->tab_dev : nullptr;
@@ -891,6 +1004,8 @@ extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* 
     wp.n = h->n; wp.m = h->m; wp.y = h->y; wp.aux = h->aux; wp.gs = h->gs;
     wp.kind = h->fam.kind; wp.tail_own = h->fam.tail_own; wp.v3 = h->fam.v3; wp.theta0 = ts.theta0;
     wp.ta = h->tab_dev; wp.tb = h->tab_dev + h->m;
+    wp.fsq = h->fam.nf > 0 ? h->fsq : nullptr;
+    if (h->fam.nf > 0 && !h->fsq) return fail(FN_ERR_STATE, "factors have not been set (fn_set_factors)");
     wp.out = (double*)h->scratch_dev;
     weights_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(wp);
     ++h->launches;

@@ -408,6 +408,95 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
     grid_reduce(p.gr, vals);
 }
 
+// ------------------------------------------------------------------------------------------
+// K2f -log likelihood + gradient of the factor models (covariance diag(sigma2) + F F')
+// ------------------------------------------------------------------------------------------
+struct EvalFactorsParams {
+    GeomParams g;
+    TileSrc src;             // y, aux (precision weights), cst (per-gene mode only), status
+    const double* zn; const double* zc;     // [design | factors | 0], m x C, for ordinary / control genes
+    int c_noise, c_ctrl, nf;
+    int is_t;
+    double v, theta0;
+    double* pg_score; double* pg_d2; int* pg_p;
+    GridReduce gr;           // nacc = ACC_FIXED + m * nf  (d/dF follows the fixed accumulators)
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) eval_factors_kernel(const EvalFactorsParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bars[FN_MAX_STAGES];
+    __shared__ double red_scratch[32 * ACC_FIXED];
+    const int m = p.g.m, nf = p.nf, ncol = m * nf;
+    const TileLayout L = tile_layout(p.src);
+    tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);
+    double* zn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
+    double* zc = zn + m * C;
+    double* t0 = zc + m * C;
+    double* t1 = t0 + (m + 1);
+    double* vals = t1 + (m + 1);
+    double* colscr = vals + (ACC_FIXED + ncol);
+    double* gscr = colscr + blockDim.x;              // genes x m x nf: d/dF terms of the current tile
+    for (int i = threadIdx.x; i < m * C; i += blockDim.x) { zn[i] = p.zn[i]; zc[i] = p.zc[i]; }
+    for (int i = threadIdx.x; i <= m; i += blockDim.x) density_tables(p.is_t, p.v, i, t0[i], t1[i]);
+    __syncthreads();
+
+    EvalConst ec;
+    ec.kind = KIND_SCALE1; ec.tail_own = 0; ec.v3 = 0; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
+    ec.ta = nullptr; ec.tb = nullptr; ec.t0 = t0; ec.t1 = t1; ec.finish_setup();
+
+    const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
+    GeneView gv;
+    gv.setup(m, lane, p.g.lpg, gl);
+    gv.gs = 0.0;
+    double acc[ACC_FIXED];
+#pragma unroll
+    for (int i = 0; i < ACC_FIXED; ++i) acc[i] = 0.0;
+    const int nsub = blockDim.x / ncol;
+    const int col = threadIdx.x % ncol, sub = threadIdx.x / ncol;
+    double col_f = 0.0;
+
+    tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, false, [&](unsigned char* st, long long tile) {
+        const long long gene = tile * p.g.genes + gl;
+        gv.y = (double*)st + (size_t)gl * m;
+        gv.aux = p.src.aux ? (double*)(st + L.aux_off) + (size_t)gl * m : nullptr;
+        const uint8_t status = st[L.status_off + gl];
+        const bool control = (status & 2) != 0;
+        const double cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
+        EvalOut eo;
+        eval_factors<C>(ec, gv, control ? zc : zn, control ? p.c_ctrl : p.c_noise, nf, (status & 1) != 0, cst,
+                        gscr + (size_t)gl * ncol, eo);
+        if (lane == 0 && gene < p.g.n) {
+            if (eo.used) {
+                if (eo.value == eo.value) {
+                    acc[ACC_VALUE] += eo.value; acc[ACC_DV] += eo.dv; acc[ACC_GA] += eo.ga; acc[ACC_USED] += 1.0;
+                } else {
+                    acc[ACC_BAD] += 1.0;
+                }
+            }
+            if (p.pg_score) {
+                p.pg_score[gene] = eo.used ? eo.value : NAN;
+                p.pg_d2[gene] = eo.d2;
+                p.pg_p[gene] = eo.p;
+            }
+        }
+        __syncthreads();
+        if (sub < nsub)
+            for (int g = sub; g < p.g.genes; g += nsub) col_f += gscr[(size_t)g * ncol + col];
+    });
+
+    block_sum<ACC_FIXED>(acc, vals, red_scratch);
+    colscr[threadIdx.x] = col_f;
+    __syncthreads();
+    if (threadIdx.x < ncol) {
+        double s = 0.0;
+        for (int q = 0; q < nsub; ++q) s += colscr[q * ncol + threadIdx.x];
+        vals[ACC_FIXED + threadIdx.x] = s;
+    }
+    __syncthreads();
+    grid_reduce(p.gr, vals);
+}
+
 // noise p-values from (d2, p): Mvt.p_value F sf (distributions.py:150-155) / Mvnormal chi2 sf (:52-57)
 __global__ void noise_p_kernel(long long n, const double* d2, const int* pdf, int is_t, double v, double* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -554,6 +643,7 @@ struct WeightParams {
     int kind, tail_own, v3;
     double theta0;
     const double* ta; const double* tb;
+    const double* fsq;       // factor models: sum_i F[j,i]^2 per sample (the diagonal of F F'), or nullptr
     double* out;
 };
 
@@ -573,7 +663,8 @@ __global__ void weights_kernel(const WeightParams p) {
             w = 1.0 / (p.ta[j] * U + p.tb[j] * T);
         } else {
             const double wp = p.aux ? p.aux[i] : 1.0;
-            w = (p.kind == KIND_SCALE_PS) ? wp * p.ta[j] : wp / p.theta0;
+            if (p.fsq) w = 1.0 / (p.theta0 / wp + p.fsq[j]);
+            else w = (p.kind == KIND_SCALE_PS) ? wp * p.ta[j] : wp / p.theta0;
         }
         p.out[i] = w;
     }

@@ -90,6 +90,16 @@ int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double* value, dou
  * device memory at out_dev on the handle's stream, for the caller to allreduce.  No host sync. */
 int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, double* out_dev);
 
+/* Factor models (family.nf > 0; Model_normal_factors / Model_t_factors / Model_independent_factors,
+ * fitnoise.py:439-518, 558-565, 592-594): covariance diag(sigma2) + F F' with F (m x nf, row-major)
+ * shared by all genes.  theta holds only [df], [variance]; the caller maps its packed parameters
+ * to F (F = Q2 . pack, fitnoise.py:447-458) and the returned d/dF back (and adds the penalty
+ * _model_cost, :470-478).  fn_nll_grad_factors also makes `factors` current for fn_per_gene,
+ * fn_noise_stats, fn_coef and fn_weights; fn_set_factors does only that. */
+int fn_nll_grad_factors(fn_handle* h, const double* theta, int32_t P, const double* factors,
+                        double* value, double* grad, double* grad_factors, int64_t* n_used, int64_t* n_bad);
+int fn_set_factors(fn_handle* h, const double* factors);
+
 /* Per-gene score_row, Mahalanobis distance d2 and residual df p at theta (NaN / 0 for genes the
  * REML prep skips).  Parity/diagnostic entry; any output pointer may be NULL. */
 int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double* score, double* d2, int32_t* p);

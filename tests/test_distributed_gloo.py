@@ -14,7 +14,7 @@ import torch.multiprocessing as mp  # noqa: E402
 
 from conftest import ROOT, assert_close, golden_context, golden_fit_kwargs, golden_test_kwargs, load_golden
 
-CASES = ["t_twogroup", "t_patseq_v2", "t_per_sample_controls"]
+CASES = ["t_twogroup", "t_patseq_v2", "t_per_sample_controls", "t_factors1_controls"]
 
 
 def _free_port():
@@ -29,7 +29,9 @@ def _run_case(name, forced):
     import fitnoise_b200 as fitnoise
     import hostcheck
     g = load_golden(name)
-    model = getattr(fitnoise, str(g["model"]))()._with(_engine_factory=hostcheck.HostEvaluator)
+    nf = int(g.get("n_factors", 0))
+    cls = getattr(fitnoise, str(g["model"]))
+    model = (cls(nf) if nf else cls())._with(_engine_factory=hostcheck.HostEvaluator)
     kw = golden_fit_kwargs(g)
     if forced:
         kw["force_param"] = g["theta"]

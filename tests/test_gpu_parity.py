@@ -47,10 +47,13 @@ def test_golden_value_and_gradient(name):
         pytest.skip("no hyper-parameters")
     fitted, _ = fit_golden(g, force_param=theta)
     value, grad, used, bad = fitted._objective(theta)
-    cfg = oracle.Configured(str(g["model"]), g["y"], golden_context(g))
     kw = golden_fit_kwargs(g)
-    out = oracle.fit_noise(cfg, g.get("noise_design", g["design"]), kw.get("control_design"),
-                           kw.get("controls"), force_param=theta, skip_rank_deficient=True)
+    nd = g.get("noise_design", g["design"])
+    cfg = oracle.Configured(str(g["model"]), g["y"], golden_context(g), n_factors=int(g.get("n_factors", 0)),
+                            design=nd, control_design=kw.get("control_design", np.ones((g["y"].shape[1], 1))),
+                            controls=kw.get("controls"))
+    out = oracle.fit_noise(cfg, nd, kw.get("control_design"), kw.get("controls"), force_param=theta,
+                           skip_rank_deficient=True)
     ov, og = oracle.total_score_grad(cfg, out["prepared"], theta)
     assert used == len(out["prepared"]) and bad == 0
     assert_close(value, ov, 1e-11, what="objective")
@@ -83,13 +86,14 @@ def test_lane_mappings_agree(lpg, threads):
     assert_close(gr, bg, 1e-9, atol=1e-12 * abs(bv))
 
 
-@pytest.mark.parametrize("name", ["t_twogroup", "t_patseq_v2", "t_controls_opt"])
+@pytest.mark.parametrize("name", ["t_twogroup", "t_patseq_v2", "t_controls_opt", "t_factors1"])
 def test_fitted_hyperparameters(name):
     g = load_golden(name)
     fitted, tested = fit_golden(g)
     ref = oracle.fit_and_test(str(g["model"]), g["y"], g["design"], golden_context(g),
                               coef_idx=[int(i) for i in g["test_coef"]], nan_aware=True,
-                              skip_rank_deficient=True, **golden_fit_kwargs(g))
+                              skip_rank_deficient=True, n_factors=int(g.get("n_factors", 0)),
+                              **golden_fit_kwargs(g))
     x, rx = fitted.optimization_result.x, ref["x"]
     free = ~(np.isclose(rx, 100.0) | np.isclose(rx, 1e-3))
     assert_close(x[free], rx[free], 1e-6, what="theta")
@@ -358,3 +362,46 @@ def test_top_table_order_bit_exact(engine):
     assert np.array_equal(np.asarray(table.index), np.argsort(tested.p_values, kind="stable"))
     assert list(table.columns) == ["coef2", "AveExpr", "P.Value", "adj.P.Val", "noise.P.Value", "control"]
     assert_close(table["adj.P.Val"].values, g["ref_q_values"][np.asarray(table.index)], 1e-8)
+
+
+@pytest.mark.parametrize("lpg,threads", [(0, 0), (1, 128), (2, 256), (4, 256), (8, 256)])
+def test_factor_models_lane_mappings(lpg, threads):
+    """The factor-model kernel (augmented ridge system, d/dF column sums) under every lane mapping and
+    at m = 32 (blocked order), n = 700, against the host build of the same arithmetic."""
+    import hostcheck
+    rng = np.random.default_rng(21)
+    n, m, nf = 700, 32, 2
+    design = np.stack([np.ones(m), (np.arange(m) >= 16) * 1.0, rng.normal(size=m)], axis=1)
+    F = rng.normal(size=(m, nf)) * 0.8
+    y = rng.normal(size=(n, m)) + (rng.normal(size=(n, nf)) @ F.T) + 5.0
+    y[rng.random((n, m)) < 0.03] = np.nan
+    w = np.exp(rng.normal(0, 0.3, size=(n, m)))
+    controls = rng.random(n) < 0.3
+    control_design = design[:, [0, 2]]
+    fam = fitnoise.Model_t_factors(nf)._family(m)
+    theta = np.array([7.0, 1.2])
+    host = hostcheck.HostEvaluator()
+    host.upload(y, w, fam, controls, design, control_design)
+    hv, hg, hgf, hu, _ = host.nll_grad_factors(theta, F)
+    hs, hd, hp = host.per_gene(theta)
+    hc, hcov, hdf = host.coef(theta, design)
+    e = _native.Engine(0)
+    try:
+        e.set_tuning(lpg=lpg, threads=threads)
+        e.upload(y, w, fam, controls, design, control_design)
+        gv, gg, ggf, gu, gb = e.nll_grad_factors(theta, F)
+        assert gu == hu and gb == 0
+        assert_close(gv, hv, 1e-11, what="value")
+        assert_close(gg, hg, 1e-8, atol=1e-10 * abs(hv), what="grad core")
+        assert_close(ggf, hgf, 1e-8, atol=1e-10 * abs(hv), what="grad factors")
+        gs, gd, gp = e.per_gene(theta)
+        assert_close(gs, hs, 1e-10, what="score")
+        assert np.array_equal(gp, hp)
+        gc, gcov, gdf = e.coef(theta, design)
+        assert_close(gc, hc, 1e-9, atol=1e-9, what="coef")
+        assert_close(gcov, hcov, 1e-9, atol=1e-12, what="covar")
+        assert_close(e.weights(theta), host.weights(theta), 1e-12, what="weights")
+        with pytest.raises(_native.NativeError):
+            e.nll_grad(theta)                      # factor families go through nll_grad_factors
+    finally:
+        e.close()
