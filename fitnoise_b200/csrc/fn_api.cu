@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -93,8 +94,9 @@ struct fn_handle {
     size_t partials_cap = 0;
     unsigned int* ticket = nullptr;
     double* out_dev = nullptr;
-    double* out_host = nullptr;        // pinned, mapped
-    double* out_host_devptr = nullptr;
+    Slot* out_host = nullptr;          // pinned, mapped: {value, seq} per accumulator
+    Slot* out_host_devptr = nullptr;
+    std::vector<double> out_vals;      // the values of the last completed launch
     size_t out_cap = 0;
     double* tab_dev = nullptr;         // 2m
     double* tab_host = nullptr;        // pinned 2m
@@ -118,8 +120,8 @@ struct fn_handle {
     // fused multi-GPU exchange (fn_comm_*): mailboxes mapped with CUDA IPC
     int comm_world = 0, comm_rank = 0, comm_slot = 0;
     unsigned long long comm_seq = 0;
-    double* comm_own = nullptr;
-    double* comm_peer[FN_MAX_RANKS] = {nullptr};
+    Slot* comm_own = nullptr;
+    Slot* comm_peer[FN_MAX_RANKS] = {nullptr};
 };
 
 template <class T>
@@ -327,8 +329,8 @@ static int ensure_reduce(fn_handle* h, int grid, int nacc) {
         if (h->out_host) { cudaFreeHost(h->out_host); h->out_host = nullptr; }
         const size_t cap = (size_t)nacc + 64;
         CUDA_TRY(cudaMalloc(&h->out_dev, cap * sizeof(double)));
-        CUDA_TRY(cudaHostAlloc(&h->out_host, cap * sizeof(double), cudaHostAllocMapped));
-        memset(h->out_host, 0, cap * sizeof(double));
+        CUDA_TRY(cudaHostAlloc(&h->out_host, cap * sizeof(Slot), cudaHostAllocMapped));
+        memset(h->out_host, 0, cap * sizeof(Slot));
         CUDA_TRY(cudaHostGetDevicePointer(&h->out_host_devptr, h->out_host, 0));
         h->out_cap = cap;
     }
@@ -344,27 +346,39 @@ static int ensure_scratch(fn_handle* h, size_t bytes) {
     return 0;
 }
 
-// Wait for the kernel that carries `seq` to publish its totals in the pinned result buffer.  The
-// last CTA stores the flag after the values (system-scope fence in between), so spinning on host
-// memory sees the result a PCIe write after the kernel finishes -- several microseconds sooner than
-// cudaStreamSynchronize returns.  Falls back to the stream's status to notice a failed launch.
+// Wait for the kernel that carries `seq` to publish its totals in the pinned result slots and copy
+// them to h->out_vals.  Every slot is one 16-byte {value, seq} store of the last CTA, so a slot that
+// shows `seq` also shows its value; spinning on host memory sees the result one PCIe write after
+// the last CTA finishes -- several microseconds sooner than cudaStreamSynchronize returns.  Falls
+// back to the stream's status to notice a failed launch.
 static int wait_result(fn_handle* h, unsigned long long seq, int nacc) {
-    volatile unsigned long long* flag = (volatile unsigned long long*)&h->out_host[nacc];
+    h->out_vals.resize(nacc);
     unsigned long long spins = 0;
-    while (*flag != seq) {
-        if ((++spins & 0x3fff) == 0) {
-            cudaError_t e = cudaStreamQuery(h->stream);
-            if (e == cudaSuccess) {
-                if (*flag == seq) break;
-                return fail(FN_ERR_CUDA, "kernel finished without publishing its result");
+    for (int i = 0; i < nacc; ++i) {
+        volatile Slot* slot = &h->out_host[i];
+        while (slot->seq != seq) {
+            if ((++spins & 0x3fff) == 0) {
+                cudaError_t e = cudaStreamQuery(h->stream);
+                if (e == cudaSuccess) {
+                    if (slot->seq == seq) break;
+                    return fail(FN_ERR_CUDA, "kernel finished without publishing its result");
+                }
+                if (e != cudaErrorNotReady) return fail(FN_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
             }
-            if (e != cudaErrorNotReady) return fail(FN_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
-        }
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+            __builtin_ia32_pause();
 #endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        h->out_vals[i] = slot->value;
     }
     return 0;
+}
+
+// after a plain stream synchronisation the slots of the last launch are complete
+static void collect_result(fn_handle* h, int nacc) {
+    h->out_vals.resize(nacc);
+    for (int i = 0; i < nacc; ++i) h->out_vals[i] = h->out_host[i].value;
 }
 
 static void fill_reduce(fn_handle* h, GridReduce& gr, int nacc, int add_index, double add_value, bool exchange) {
@@ -372,10 +386,10 @@ static void fill_reduce(fn_handle* h, GridReduce& gr, int nacc, int add_index, d
     gr.out_host = h->out_host_devptr; gr.nacc = nacc;
     gr.add_index = add_index; gr.add_value = add_value;
     gr.host_seq = ++h->host_seq;
-    gr.comm.world = 0; gr.comm.rank = 0; gr.comm.slot_doubles = 0; gr.comm.seq = 0; gr.comm.timeout_ns = 0;
+    gr.comm.world = 0; gr.comm.rank = 0; gr.comm.slot_count = 0; gr.comm.seq = 0; gr.comm.timeout_ns = 0;
     for (int r = 0; r < FN_MAX_RANKS; ++r) gr.comm.mailbox[r] = nullptr;
     if (exchange && h->comm_world > 1) {
-        gr.comm.world = h->comm_world; gr.comm.rank = h->comm_rank; gr.comm.slot_doubles = h->comm_slot;
+        gr.comm.world = h->comm_world; gr.comm.rank = h->comm_rank; gr.comm.slot_count = h->comm_slot;
         gr.comm.seq = ++h->comm_seq;
         gr.comm.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
         for (int r = 0; r < h->comm_world; ++r) gr.comm.mailbox[r] = h->comm_peer[r];
@@ -557,13 +571,14 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->cst_sum = h->out_host[PREP_CSTSUM];
+    collect_result(h, PREP_NACC);
+    h->cst_sum = h->out_vals[PREP_CSTSUM];
     if (info) {
-        const double cnt = h->out_host[PREP_VARCNT];
-        info->row_variance_mean = cnt > 0 ? h->out_host[PREP_VARSUM] / cnt : NAN;
+        const double cnt = h->out_vals[PREP_VARCNT];
+        info->row_variance_mean = cnt > 0 ? h->out_vals[PREP_VARSUM] / cnt : NAN;
         info->cst_sum = h->cst_sum;
-        info->n_eligible = (int64_t)h->out_host[PREP_ELIG];
-        info->n_bad_counts = (int64_t)h->out_host[PREP_BAD];
+        info->n_eligible = (int64_t)h->out_vals[PREP_ELIG];
+        info->n_bad_counts = (int64_t)h->out_vals[PREP_BAD];
         info->n_variance_rows = (int64_t)cnt;
     }
     h->loaded = true;
@@ -753,7 +768,7 @@ extern "C" int fn_nll_grad_factors(fn_handle* h, const double* theta, int32_t P,
     const int m = h->m, nf = h->fam.nf, nacc = ACC_FIXED + m * nf;
     rc = wait_result(h, h->host_seq, nacc);
     if (rc) return rc;
-    const double* acc = h->out_host;
+    const double* acc = h->out_vals.data();
     if (value) *value = acc[ACC_VALUE];
     if (grad) {
         int at = 0;
@@ -794,7 +809,7 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
     rc = wait_result(h, h->host_seq, eval_nacc(h));
     if (rc) return rc;
     std::vector<double> out(P + 3);
-    assemble(h, h->out_host, ts.ta.data(), out.data());
+    assemble(h, h->out_vals.data(), ts.ta.data(), out.data());
     if (value) *value = out[0];
     if (grad) for (int i = 0; i < P; ++i) grad[i] = out[1 + i];
     if (n_used) *n_used = (int64_t)out[P + 1];
@@ -1108,8 +1123,8 @@ extern "C" int fn_comm_mailbox(fn_handle* h, int32_t world, int32_t max_values, 
     if (world < 2 || world > FN_MAX_RANKS) return fail(FN_ERR_ARG, "fn_comm_mailbox: world must be 2..%d", FN_MAX_RANKS);
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->comm_own) { cudaFree(h->comm_own); h->comm_own = nullptr; }
-    h->comm_slot = ((max_values + 1 + 15) / 16) * 16;
-    const size_t bytes = (size_t)2 * world * h->comm_slot * sizeof(double);
+    h->comm_slot = ((max_values + 15) / 16) * 16;
+    const size_t bytes = (size_t)2 * world * h->comm_slot * sizeof(Slot);
     CUDA_TRY(cudaMalloc(&h->comm_own, bytes));
     CUDA_TRY(cudaMemset(h->comm_own, 0, bytes));
     CUDA_TRY(cudaDeviceSynchronize());
@@ -1131,7 +1146,7 @@ extern "C" int fn_comm_connect(fn_handle* h, int32_t rank, int32_t world, const 
         memcpy(&handle, (const char*)ipc_handles + (size_t)r * sizeof handle, sizeof handle);
         void* ptr = nullptr;
         CUDA_TRY(cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess));
-        h->comm_peer[r] = (double*)ptr;
+        h->comm_peer[r] = (Slot*)ptr;
     }
     h->comm_rank = rank; h->comm_world = world; h->comm_seq = 0;
     return 0;

@@ -16,30 +16,51 @@ enum { ACC_VALUE = 0, ACC_DV = 1, ACC_GA = 2, ACC_GB = 3, ACC_USED = 4, ACC_BAD 
 
 #define FN_MAX_RANKS 16
 
+// Hand-over slots.  A result value travels together with the sequence number of the evaluation that
+// produced it, as ONE aligned 16-byte store {value, seq}: whoever reads a slot (the host spinning on
+// pinned memory, a peer GPU polling its mailbox) and finds the expected seq has the value too, so no
+// system-scope fence has to separate "data" from "flag" (each such fence over PCIe / NVLink costs
+// microseconds, and the whole evaluation of a small data set takes ~15).
+struct __align__(16) Slot {
+    double value;
+    unsigned long long seq;
+};
+
+__device__ __forceinline__ void slot_store(Slot* s, double value, unsigned long long seq) {
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(s), "l"(__double_as_longlong(value)), "l"(seq) : "memory");
+}
+__device__ __forceinline__ Slot slot_load(const Slot* s) {
+    long long v; unsigned long long q;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(q) : "l"(s) : "memory");
+    Slot r; r.value = __longlong_as_double(v); r.seq = q;
+    return r;
+}
+
 // Cross-GPU exchange fused into the kernel epilogue (multi-GPU, one process per GPU).
-// Every rank owns a mailbox in its device memory: [parity 2][sender world][slot] doubles, slot[0] is
-// the sender's sequence flag and slot[1..] its values.  All ranks' mailboxes are mapped into every
-// process with CUDA IPC, so the last CTA of rank r stores its sums straight into every peer's
-// mailbox over NVLink (st.global on the peer mapping), publishes them with a system-scope fence and
-// a flag, waits for the other ranks' flags in its OWN mailbox, and adds the slots in rank order
-// (so every rank computes bit-identical totals).  No NCCL call, no extra launch, no host round trip.
+// Every rank owns a mailbox in its device memory: [parity 2][sender world][slot_count] Slots.  All
+// ranks' mailboxes are mapped into every process with CUDA IPC, so the last CTA of rank r stores
+// its sums straight into every peer's mailbox over NVLink (16-byte stores on the peer mapping),
+// polls its OWN mailbox until every sender's slots carry this evaluation's seq, and adds them in
+// rank order (so every rank computes bit-identical totals).  No NCCL call, no extra launch, no
+// host round trip.  Two parities: a fast rank may already write evaluation k+1 while a slow one
+// still reads k.
 struct PeerComm {
     int world, rank;                       // world <= 1: no exchange
-    int slot_doubles;                      // capacity of a slot (flag + values)
+    int slot_count;                        // slots per (parity, sender)
     unsigned long long seq;                // evaluation number, identical on every rank, >= 1
     unsigned long long timeout_ns;         // give up waiting for a peer after this long
-    double* mailbox[FN_MAX_RANKS];         // mailbox[r]: rank r's mailbox as mapped in this process
+    Slot* mailbox[FN_MAX_RANKS];           // mailbox[r]: rank r's mailbox as mapped in this process
 };
 
 struct GridReduce {
     double* partials;        // gridDim.x * nacc
     unsigned int* ticket;
     double* out_dev;         // nacc doubles
-    double* out_host;        // mapped pinned: nacc values then the completion flag, or nullptr
+    Slot* out_host;          // mapped pinned: nacc slots, or nullptr
     int nacc;
     int add_index;           // out[add_index] += add_value (theta-independent part of the objective)
     double add_value;
-    unsigned long long host_seq;   // written to out_host[nacc] (as an integer) when the values are there
+    unsigned long long host_seq;   // seq of this launch in the out_host slots
     PeerComm comm;
 };
 
@@ -68,6 +89,20 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
     if (!is_last) return;
     __threadfence();
     const unsigned int G = gridDim.x;
+    const PeerComm& pc = gr.comm;
+    const bool exchange = pc.world > 1;
+    const int parity = (int)(pc.seq & 1ull);
+    // total of component i over the grid, by thread i (nacc <= T) or by a strided loop
+    auto publish = [&](int i, double s) {
+        if (i == gr.add_index) s += gr.add_value;
+        if (exchange) {
+            const size_t mine = ((size_t)parity * pc.world + pc.rank) * pc.slot_count + i;
+            for (int r = 0; r < pc.world; ++r) slot_store(&pc.mailbox[r][mine], s, pc.seq);
+        } else {
+            gr.out_dev[i] = s;
+            if (gr.out_host) slot_store(&gr.out_host[i], s, gr.host_seq);
+        }
+    };
     if (nacc <= T) {
         // thread (slice, i) adds blocks slice, slice+S, ... of component i; then the slices are added
         const int S = T / nacc, i = threadIdx.x % nacc, slice = threadIdx.x / nacc;
@@ -80,72 +115,37 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
         if (threadIdx.x < nacc) {
             double s = 0.0;
             for (int q = 0; q < S; ++q) s += gsum[q * nacc + threadIdx.x];
-            if (threadIdx.x == gr.add_index) s += gr.add_value;
-            gr.out_dev[threadIdx.x] = s;
+            publish(threadIdx.x, s);
         }
     } else {
         for (int i = threadIdx.x; i < nacc; i += T) {
             double s = 0.0;
             for (unsigned int b = 0; b < G; ++b) s += __ldcg(&gr.partials[(size_t)b * nacc + i]);
-            if (i == gr.add_index) s += gr.add_value;
-            gr.out_dev[i] = s;
+            publish(i, s);
         }
     }
     if (threadIdx.x == 0) *gr.ticket = 0;
-    __syncthreads();
+    if (!exchange) return;
 
-    const PeerComm& pc = gr.comm;
-    bool failed = false;
-    if (pc.world > 1) {
-        const int parity = (int)(pc.seq & 1ull);
-        const size_t slot_of_me = ((size_t)parity * pc.world + pc.rank) * pc.slot_doubles;
-        for (int i = threadIdx.x; i < nacc; i += T) {
-            const double v = gr.out_dev[i];
-            for (int r = 0; r < pc.world; ++r) pc.mailbox[r][slot_of_me + 1 + i] = v;
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < pc.world) {
-            volatile unsigned long long* flag = (volatile unsigned long long*)&pc.mailbox[threadIdx.x][slot_of_me];
-            *flag = pc.seq;
-        }
-        __threadfence_system();
-        // wait for every sender's flag in my own mailbox
-        __shared__ int peer_failed;
-        if (threadIdx.x == 0) peer_failed = 0;
-        __syncthreads();
-        if (threadIdx.x < pc.world) {
-            const size_t slot = ((size_t)parity * pc.world + threadIdx.x) * pc.slot_doubles;
-            volatile unsigned long long* flag = (volatile unsigned long long*)&pc.mailbox[pc.rank][slot];
-            const unsigned long long t0 = global_ns();
-            while (*flag != pc.seq) {
-                if (global_ns() - t0 > pc.timeout_ns) { peer_failed = 1; break; }
-                __nanosleep(100);
+    // every component: wait for all senders' slots of this evaluation in my own mailbox, add in rank order
+    for (int i = threadIdx.x; i < nacc; i += T) {
+        double s = 0.0;
+        bool failed = false;
+        const unsigned long long t0 = global_ns();
+        for (int r = 0; r < pc.world; ++r) {
+            const Slot* slot = &pc.mailbox[pc.rank][((size_t)parity * pc.world + r) * pc.slot_count + i];
+            Slot got = slot_load(slot);
+            while (got.seq != pc.seq) {
+                if (global_ns() - t0 > pc.timeout_ns) { failed = true; break; }
+                __nanosleep(64);
+                got = slot_load(slot);
             }
+            s += got.value;
         }
-        __threadfence_system();
-        __syncthreads();
-        failed = peer_failed != 0;
-        for (int i = threadIdx.x; i < nacc; i += T) {
-            double s = 0.0;
-            for (int r = 0; r < pc.world; ++r) {
-                const size_t slot = ((size_t)parity * pc.world + r) * pc.slot_doubles;
-                s += __ldcg(&pc.mailbox[pc.rank][slot + 1 + i]);
-            }
-            gr.out_dev[i] = failed ? NAN : s;
-        }
-        __syncthreads();
+        if (failed) s = NAN;
+        gr.out_dev[i] = s;
+        if (gr.out_host) slot_store(&gr.out_host[i], s, gr.host_seq);
     }
-    if (gr.out_host) {
-        for (int i = threadIdx.x; i < nacc; i += T) gr.out_host[i] = gr.out_dev[i];
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            volatile unsigned long long* flag = (volatile unsigned long long*)&gr.out_host[nacc];
-            *flag = gr.host_seq;
-        }
-    }
-    __threadfence_system();
 }
 
 // CTA-wide sum of NV thread-local doubles into shared `out[NV]` (deterministic order).
