@@ -190,14 +190,22 @@ class Engine(object):
 
     # ---- likelihood -----------------------------------------------------------------------
     def nll_grad(self, theta):
-        theta = _f64(theta).reshape(-1)
+        """One REML objective + gradient evaluation over this engine's genes (all ranks' genes when
+        the fused exchange is connected): (value, grad, n_used, n_bad).  Called once per optimiser
+        step, so the ctypes scaffolding is built once and reused."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1)
         P = len(theta)
-        value = ctypes.c_double()
-        grad = np.zeros(max(P, 1))
-        used, bad = ctypes.c_int64(), ctypes.c_int64()
-        self._check(self._lib.fn_nll_grad(self._h, _dp(theta), P, ctypes.byref(value), _dp(grad),
-                                          ctypes.byref(used), ctypes.byref(bad)))
-        return value.value, grad[:P], used.value, bad.value
+        call = self.__dict__.get("_nll_call")
+        if call is None or call[0] != P:
+            value, used, bad = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+            grad = np.zeros(max(P, 1))
+            call = self._nll_call = (P, value, used, bad, grad, ctypes.byref(value), ctypes.byref(used),
+                                     ctypes.byref(bad), grad.ctypes.data_as(c_double_p), self._lib.fn_nll_grad)
+        _, value, used, bad, grad, pvalue, pused, pbad, pgrad, fn = call
+        rc = fn(self._h, theta.ctypes.data_as(c_double_p), P, pvalue, pgrad, pused, pbad)
+        if rc != 0:
+            self._check(rc)
+        return value.value, grad[:P].copy(), used.value, bad.value
 
     def nll_grad_factors(self, theta, factors):
         """Factor models: (value, grad of [df, variance], d/dF (m x nf), n_used, n_bad)."""

@@ -798,16 +798,30 @@ static void assemble(const fn_handle* h, const double* acc, const double* ta, do
     out[at++] = acc[ACC_BAD];
 }
 
+#ifdef FN_TRACE
+#include <chrono>
+static double g_host_trace[4];
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+extern "C" void fn_host_trace(double* out) { for (int i = 0; i < 4; ++i) out[i] = g_host_trace[i]; }
+#define FN_HOST_STAMP(i) g_host_trace[i] = now_us()
+#else
+#define FN_HOST_STAMP(i) do { } while (0)
+#endif
+
 extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double* value, double* grad,
                            int64_t* n_used, int64_t* n_bad) {
+    FN_HOST_STAMP(0);
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts);
     if (rc) return rc;
     if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
+    FN_HOST_STAMP(1);
     rc = launch_eval(h, ts, false, true);
     if (rc) return rc;
+    FN_HOST_STAMP(2);
     rc = wait_result(h, h->host_seq, eval_nacc(h));
     if (rc) return rc;
+    FN_HOST_STAMP(3);
     std::vector<double> out(P + 3);
     assemble(h, h->out_vals.data(), ts.ta.data(), out.data());
     if (value) *value = out[0];
@@ -1163,3 +1177,12 @@ extern "C" int fn_comm_disconnect(fn_handle* h) {
     if (h->comm_own) { cudaFree(h->comm_own); h->comm_own = nullptr; }
     return 0;
 }
+
+#ifdef FN_TRACE
+extern "C" int fn_trace_dump(fn_handle* h, unsigned long long* out64) {
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(out64, fn::g_trace, 64 * sizeof(unsigned long long)));
+    return 0;
+}
+#endif

@@ -120,45 +120,45 @@ struct GeneView {
     int m;
     int lane, lpg;      // this lane's index within the gene, lanes per gene
     int cnt;            // number of samples this lane owns
-    int skew;           // rotation of the lane-local sample order (shared-memory bank spreading)
-    int blocked;        // 1: rotate within blocks of 16 samples (m % 16 == 0, lpg <= 16)
-    int steps, nblk;    // blocked order: 16/lpg rotation steps, m/16 blocks
-    // `gene_local` = index of the gene within the tile.  Rows of a tile are m doubles apart, so
-    // without a rotation the lanes of a warp that work on different genes would hit the same
-    // shared-memory banks whenever m is a multiple of 16 (8-byte bank pairs).
+    int skew;           // per-gene rotation of the sample order (shared-memory bank spreading)
+    int blocked;        // 1: rotate within blocks of `bsize` samples
+    int bsize, steps, nblk;   // block size B (power of two dividing m, <= 16), B/lpg steps, m/B blocks
+    // `gene_local` = index of the gene within the tile.  Rows of a tile are m doubles apart, so when
+    // m is a multiple of 16 the lanes of a warp that work on different genes would all hit the same
+    // shared-memory banks (8-byte bank pairs); for other even m part of them would.
     FN_HD void setup(int m_, int lane_, int lpg_, int gene_local) {
         m = m_; lane = lane_; lpg = lpg_;
         cnt = (m - lane + lpg - 1) / lpg;
         if (cnt < 0) cnt = 0;
-        blocked = ((m & 15) == 0 && lpg <= 16) ? 1 : 0;
-        steps = blocked ? 16 / lpg : 0;
-        nblk = m >> 4;
-        if (blocked) skew = (((m / lpg) & 1) == 0) ? gene_local : 0;
-        else skew = cnt > 0 ? gene_local % cnt : 0;
+        bsize = m & -m;                      // largest power of two dividing m
+        if (bsize > 16) bsize = 16;
+        blocked = (lpg <= bsize) ? 1 : 0;
+        steps = blocked ? bsize / lpg : 0;
+        nblk = blocked ? m / bsize : 0;
+        skew = blocked ? gene_local : 0;
     }
-    // Visit this lane's samples, each exactly once, in a bank-friendly order; `on` = false visits
-    // nothing.  The order only changes the association of the floating-point sums.
-    //  blocked: step (r, t) -> sample 16 t + ((lane + lpg (skew + r)) mod 16), r < 16/lpg, t < m/16.
-    //           Same trip count for every thread (no divergence); at any step the 16 threads of a
-    //           half-warp read 16 distinct bank pairs, and a warp touches only 16 distinct rows of X.
-    //  else:    lane-local indices skew..cnt-1 then 0..skew-1 as two plain strided loops.
+    // Visit this lane's samples, each exactly once; `on` = false visits nothing.  The order only
+    // changes the association of the floating-point sums.  Every thread of a warp makes the same
+    // number of visits (no divergence).
+    //  blocked: step (r, t) -> sample B t + ((lane + lpg (skew + r)) mod B), r < B/lpg, t < m/B.
+    //           With B = 16 the 16 threads of a half-warp read 16 distinct bank pairs at every step
+    //           and a warp touches only 16 distinct rows of X; smaller B spreads as far as m allows.
+    //  else:    lane, lane + lpg, ... (lpg does not divide a power-of-two factor of m).
     template <class F>
     FN_HD void for_each(bool on, F f) const {
         if (!on) return;
         if (blocked) {
+            const int mask = bsize - 1;
             for (int r = 0; r < steps; ++r) {
-                const int jr = (lane + lpg * (skew + r)) & 15;
+                const int jr = (lane + lpg * (skew + r)) & mask;
 #pragma unroll 2
-                for (int t = 0; t < nblk; ++t) f(jr + 16 * t);
+                for (int t = 0; t < nblk; ++t) f(jr + bsize * t);
             }
             return;
         }
-        int j = lane + lpg * skew;
-#pragma unroll 4
-        for (int ii = skew; ii < cnt; ++ii, j += lpg) f(j);
-        j = lane;
-#pragma unroll 4
-        for (int ii = 0; ii < skew; ++ii, j += lpg) f(j);
+        int j = lane;
+#pragma unroll 2
+        for (int i = 0; i < cnt; ++i, j += lpg) f(j);
     }
     // The same visit for the one sweep that is hot at large m: the block loop is fully unrolled
     // for the common m/16, so that a rotation step issues all its shared-memory loads (constant
@@ -174,7 +174,7 @@ struct GeneView {
     template <class F>
     FN_HD void for_each_hot(bool on, F f) const {
         if (!on) return;
-        if (blocked) {
+        if (blocked && bsize == 16) {
             switch (nblk) {
                 case 1: blocked_unrolled<1>(f); return;
                 case 2: blocked_unrolled<2>(f); return;

@@ -11,6 +11,16 @@
 
 namespace fn {
 
+#ifdef FN_TRACE
+// Development-only phase timestamps (globaltimer ns) of CTA 0 and of the last CTA; see tools/micro.
+__device__ unsigned long long g_trace[64];
+#define FN_STAMP(slot) do { if (threadIdx.x == 0 && (blockIdx.x == 0)) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_trace[slot] = t__; } } while (0)
+#define FN_STAMP_ANY(slot) do { if (threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_trace[slot] = t__; } } while (0)
+#else
+#define FN_STAMP(slot) do { } while (0)
+#define FN_STAMP_ANY(slot) do { } while (0)
+#endif
+
 // accumulator layout of one CTA's partial sums
 enum { ACC_VALUE = 0, ACC_DV = 1, ACC_GA = 2, ACC_GB = 3, ACC_USED = 4, ACC_BAD = 5, ACC_FIXED = 6 };
 
@@ -87,6 +97,7 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
     }
     __syncthreads();
     if (!is_last) return;
+    FN_STAMP_ANY(8);
     __threadfence();
     const unsigned int G = gridDim.x;
     const PeerComm& pc = gr.comm;
@@ -125,6 +136,7 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
         }
     }
     if (threadIdx.x == 0) *gr.ticket = 0;
+    FN_STAMP_ANY(9);
     if (!exchange) return;
 
     // every component: wait for all senders' slots of this evaluation in my own mailbox, add in rank order
@@ -164,6 +176,33 @@ __device__ __forceinline__ void block_sum(double* v, double* out, double* scratc
         double s = 0.0;
         for (int w = 0; w < nwarp; ++w) s += scratch[w * NV + threadIdx.x];
         out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// Per-evaluation tables t0[p], t1[p] (p = 0..m) of density_tables(), filled by the whole CTA.  The
+// two special functions of an entry go to different warps and the three p-independent terms are
+// computed once, so the latency is one lgamma or one digamma instead of two of each plus a log
+// (this sits on the critical path of every launch: ~3 us of a ~9 us small-data kernel before).
+__device__ __forceinline__ void fill_density_tables(int is_t, double v, int m, double* t0, double* t1) {
+    __shared__ double common[3];
+    if (!is_t) {
+        for (int p = threadIdx.x; p <= m; p += blockDim.x) density_tables(0, v, p, t0[p], t1[p]);
+        __syncthreads();
+        return;
+    }
+    const int n1 = m + 1, total = 2 * n1 + 3;
+    for (int w = threadIdx.x; w < total; w += blockDim.x) {
+        if (w < n1) t0[w] = lgamma(0.5 * (v + w));
+        else if (w < 2 * n1) t1[w - n1] = digamma(0.5 * (v + (w - n1)));
+        else if (w == 2 * n1) common[0] = lgamma(0.5 * v);
+        else if (w == 2 * n1 + 1) common[1] = digamma(0.5 * v);
+        else common[2] = log(3.14159265358979323846 * v);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p <= m; p += blockDim.x) {
+        t0[p] = -(t0[p] - common[0] - (0.5 * p) * common[2]);
+        t1[p] = -0.5 * t1[p] + 0.5 * common[1] + 0.5 * p / v;
     }
     __syncthreads();
 }
@@ -275,8 +314,10 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
     __shared__ uint64_t bars[FN_MAX_STAGES];
     __shared__ double red_scratch[32 * ACC_FIXED];
     const int m = p.g.m;
+    FN_STAMP(0);
     const TileLayout L = tile_layout(p.src);
     tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);     // first tiles are in flight
+    FN_STAMP(1);
     // tables behind the stage area: xn, xc (m*C each), ta, tb (m each), t0, t1 (m+1 each),
     // vals (ACC_FIXED + 2m), colscr (2*blockDim when a theta block is per-sample)
     double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
@@ -294,8 +335,8 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
         ta[i] = p.ta ? p.ta[i] : 0.0;
         tb[i] = p.tb ? p.tb[i] : 0.0;
     }
-    for (int i = threadIdx.x; i <= m; i += blockDim.x) density_tables(p.is_t, p.v, i, t0[i], t1[i]);
-    __syncthreads();
+    fill_density_tables(p.is_t, p.v, m, t0, t1);
+    FN_STAMP(2);
 
     EvalConst ec;
     ec.kind = KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
@@ -362,7 +403,9 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
             }
             if (++sel == p.g.lpg) { sel = 0; finalize(); }
         });
+        FN_STAMP(3);
         finalize();
+        FN_STAMP(4);
     } else {
     // PATSEQ keeps 1/sigma2 in the aux tile between its two sweeps: the stage is always written
     tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, inplace || KIND == KIND_PATSEQ, [&](unsigned char* st, long long tile) {
@@ -393,6 +436,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
     }
 
     block_sum<ACC_FIXED>(acc, vals, red_scratch);
+    FN_STAMP(5);
     if (inplace) {
         colscr[threadIdx.x] = col_a;
         colscr[blockDim.x + threadIdx.x] = col_b;
@@ -438,8 +482,7 @@ __global__ void __launch_bounds__(256) eval_factors_kernel(const EvalFactorsPara
     double* colscr = vals + (ACC_FIXED + ncol);
     double* gscr = colscr + blockDim.x;              // genes x m x nf: d/dF terms of the current tile
     for (int i = threadIdx.x; i < m * C; i += blockDim.x) { zn[i] = p.zn[i]; zc[i] = p.zc[i]; }
-    for (int i = threadIdx.x; i <= m; i += blockDim.x) density_tables(p.is_t, p.v, i, t0[i], t1[i]);
-    __syncthreads();
+    fill_density_tables(p.is_t, p.v, m, t0, t1);
 
     EvalConst ec;
     ec.kind = KIND_SCALE1; ec.tail_own = 0; ec.v3 = 0; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
