@@ -228,9 +228,31 @@ def run_gpu(args):
         # NVLink into IPC-mapped mailboxes); FN_REDUCE=nccl times kernel + ncclAllReduce instead.
         reduce_mode = os.environ.get("FN_REDUCE", "fused") if world > 1 else "none"
         if reduce_mode == "fused":
+            # every rank must end up in the same mode: agree on whether the IPC mapping worked
+            ok, why, mine = 1, "", None
+            try:
+                mine = engine.comm_mailbox(world, 8 + 2 * m)
+            except Exception as exc:            # e.g. CUDA IPC not permitted on this box
+                ok, why = 0, str(exc)
             handles = [None] * world
-            dist.all_gather_object(handles, engine.comm_mailbox(world, 8 + 2 * m))
-            engine.comm_connect(rank, world, b"".join(handles))
+            dist.all_gather_object(handles, mine)       # every rank takes part, whatever happened
+            if ok and all(h is not None for h in handles):
+                try:
+                    engine.comm_connect(rank, world, b"".join(handles))
+                except Exception as exc:        # peer access not available
+                    ok, why = 0, str(exc)
+            else:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                try:
+                    engine.comm_disconnect()
+                except Exception:
+                    pass
+                reduce_mode = "nccl"
+                if rank == 0:
+                    sys.stderr.write("fused exchange unavailable (%s); using ncclAllReduce\n" % why)
             dist.barrier()
 
         def step():

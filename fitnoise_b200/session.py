@@ -62,12 +62,31 @@ class Session(object):
         sums of all GPUs over NVLink (csrc/fn_kernels.cuh grid_reduce); FN_REDUCE=nccl keeps the
         kernel + ncclAllReduce path instead."""
         import torch.distributed as dist
-        handle = self.local.comm_mailbox(self.world, 8 + max(2, self.family.nf) * self.m)
+        ok, handle = 1, None
+        try:
+            handle = self.local.comm_mailbox(self.world, 8 + max(2, self.family.nf) * self.m)
+        except _native.NativeError:               # CUDA IPC not available on this box
+            ok = 0
         handles = [None] * self.world
-        dist.all_gather_object(handles, handle)
-        self.local.comm_connect(self.rank, self.world, b"".join(handles))
+        dist.all_gather_object(handles, handle)   # every rank takes part, whatever happened
+        if ok and all(h is not None for h in handles):
+            try:
+                self.local.comm_connect(self.rank, self.world, b"".join(handles))
+            except _native.NativeError:           # peer access not available
+                ok = 0
+        else:
+            ok = 0
+        with self._torch.cuda.stream(self._stream):
+            flag = self._torch.tensor([ok], dtype=self._torch.int64, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            agreed = int(flag.item())
+        if not agreed:                            # every rank falls back together: kernel + ncclAllReduce
+            try:
+                self.local.comm_disconnect()
+            except _native.NativeError:
+                pass
         dist.barrier()
-        self._fused = True
+        self._fused = bool(agreed)
 
     @staticmethod
     def _nan0(x):

@@ -190,9 +190,9 @@ def test_bh_bit_exact(engine):
 
 
 def test_full_size_properties():
-    """BASELINE.json's largest shape (1M x 96 would take the oracle days): size-independent
-    properties at 200k x 96 -- the oracle on a slice, invariances on the whole."""
-    n, m = 200000, 96
+    """BASELINE.json's largest shape at FULL size, 1,000,000 x 96 (the oracle would take days):
+    size-independent properties -- the oracle on a slice, invariances on the whole."""
+    n, m = 1000000, 96
     rng = np.random.default_rng(5)
     design = np.array([[1.0, 0.0]] * 48 + [[1.0, 1.0]] * 48)
     y = rng.normal(size=(n, m)) * np.sqrt(10.0 / rng.chisquare(10.0, size=(n, 1)))
@@ -403,5 +403,53 @@ def test_factor_models_lane_mappings(lpg, threads):
         assert_close(e.weights(theta), host.weights(theta), 1e-12, what="weights")
         with pytest.raises(_native.NativeError):
             e.nll_grad(theta)                      # factor families go through nll_grad_factors
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("config", [1, 2, 3, 4, 5])
+def test_full_size_configs_against_host_build(config):
+    """The five BASELINE.json configs at their FULL sizes: objective, gradient, per-gene scores,
+    coefficients and p-values of the CUDA path against the host build of the same arithmetic
+    (tests/hostcheck, pinned to the reference goldens by test_host_math.py), and BH against numpy."""
+    import hostcheck
+    s = synthetic(config)
+    model = getattr(fitnoise, "Model_t" if config == 5 else s["model"])()
+    n, m = s["y"].shape
+    fam = model._family(m)
+    aux = s["context"].get("weights", s["context"].get("counts"))
+    controls, cdesign = s.get("controls"), s.get("control_design")
+    theta = {1: [9.0, 1.0], 2: [], 3: [12.0, 750.0, 0.0025], 4: [8.0, 0.5], 5: [10.0, 1.0]}[config]
+    theta = np.asarray(theta, dtype=float)
+    host = hostcheck.HostEvaluator()
+    host.upload(s["y"], aux, fam, controls, s["design"], cdesign)
+    e = _native.Engine(0)
+    try:
+        info = e.upload(s["y"], aux, fam, controls, s["design"], cdesign)
+        hs, hd, hp = host.per_gene(theta)
+        gs, gd, gp = e.per_gene(theta)
+        assert np.array_equal(gp, hp)
+        assert_close(gs, hs, 1e-10, what="per-gene score")
+        if len(theta):
+            hv, hg, hu, _ = host.nll_grad(theta)
+            gv, gg, gu, gb = e.nll_grad(theta)
+            assert gu == hu == info.n_eligible and gb == 0
+            assert_close(gv, hv, 1e-11, what="objective")
+            assert_close(gg, hg, 1e-7, atol=1e-11 * abs(hv), what="gradient")
+        hc, hcov, hdf = host.coef(theta, s["design"])
+        gc, gcov, gdf = e.coef(theta, s["design"])
+        assert_close(gc, hc, 1e-9, atol=1e-9, what="coef")
+        assert_close(gcov, hcov, 1e-9, atol=1e-13, what="covar")
+        t = s["test"]
+        contrasts = t.get("contrasts")
+        if contrasts is None:
+            contrasts = np.zeros((s["design"].shape[1], len(t["coef"])))
+            for i, j in enumerate(t["coef"]):
+                contrasts[j, i] = 1.0
+        hcon, _, hpv = host.test(contrasts)
+        gcon, gpv, gq = e.test_bh(contrasts)
+        assert_close(gpv, hpv, 1e-8, what="p-values")
+        assert np.array_equal(gq, oracle.fdr(gpv)), "BH not bit-exact"
+        assert np.array_equal(e.last_order.astype(np.int64), np.argsort(gpv, kind="stable")), "top-table order"
     finally:
         e.close()
