@@ -135,23 +135,21 @@ def _cpu_chunk(args):
     return time.perf_counter() - t0, value
 
 
-def cpu_evals_per_sec(cores, genes_per_core):
+def cpu_evals_per_sec(cores, genes_per_core, pool=None):
     """Gene-likelihood evaluations per second of the oracle port on `cores` processes."""
     if cores == 1:
         dt, _ = _cpu_chunk((1, genes_per_core))
         return genes_per_core / dt
-    import multiprocessing as mp
-    with mp.get_context("spawn").Pool(cores) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_chunk, [(100 + i, genes_per_core) for i in range(cores)])
-        wall = time.perf_counter() - t0
+    res = pool.map(_cpu_chunk, [(100 + i, genes_per_core) for i in range(cores)])
     # per-process evaluation time excludes data generation and the one-off QR prep
     slowest = max(r[0] for r in res)
-    del wall
     return cores * genes_per_core / slowest
 
 
 def run_reference(args):
+    """The reference arm: the oracle port of the reference's CPU algorithm (the reference itself is
+    Python-2 source and cannot travel to the GPU box) on all host cores, each
+    step one objective+gradient evaluation over a bounded sample of the workload's genes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -159,13 +157,20 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cores = max(1, min(cores, 64))
     genes_per_core = int(os.environ.get("FN_REF_GENES_PER_CORE", 1500))
-    for _ in range(min(args.warmup, 1)):
-        cpu_evals_per_sec(cores, max(50, genes_per_core // 10))
-    rates, t0 = [], time.perf_counter()
-    for _ in range(args.steps):
-        rates.append(cpu_evals_per_sec(cores, genes_per_core))
-        if time.perf_counter() - t0 > 150:
-            break
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(cores) if cores > 1 else None
+    try:
+        for _ in range(min(args.warmup, 1)):
+            cpu_evals_per_sec(cores, max(50, genes_per_core // 10), pool)
+        rates, t0 = [], time.perf_counter()
+        for _ in range(max(args.steps, 1)):
+            rates.append(cpu_evals_per_sec(cores, genes_per_core, pool))
+            if time.perf_counter() - t0 > 120:
+                break
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
     value = float(np.median(rates))
     sample = "%d genes x %d samples per step (%d processes x %d genes), one objective+gradient evaluation each" % (
         cores * genes_per_core, M, cores, genes_per_core)
