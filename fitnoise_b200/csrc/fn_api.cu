@@ -448,6 +448,62 @@ static int copy_h2d(fn_handle* h, void* dst, const void* src, size_t bytes) {
     return 0;
 }
 
+// Device -> host copy of a large result array: the mirror image of copy_h2d.  Into pinned memory:
+// one cudaMemcpyAsync (completes on the stream).  Into pageable memory (a plain numpy array):
+// worker threads each pull every kStageWorkers-th 8 MB chunk through their own pinned buffers and
+// copy it out, instead of the runtime's single-threaded staging.  Returns with the data in place
+// in the staged case; the caller synchronises the stream afterwards in either case.
+static int copy_d2h(fn_handle* h, void* dst, const void* src, size_t bytes) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, dst);
+    if (e != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
+    const size_t stage = 8u << 20;           // size of the pinned staging buffers (shared with copy_h2d)
+    const size_t chunk = 1u << 20;           // results are tens of MB: small chunks keep all workers busy
+    if (attr.type != cudaMemoryTypeUnregistered || bytes < 4 * chunk) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    }
+    const int W = fn_handle::kStageWorkers;
+    if (h->stage_bytes != stage) {
+        for (int i = 0; i < 2 * W; ++i) {
+            CUDA_TRY(cudaHostAlloc(&h->stage_buf[i], stage, cudaHostAllocDefault));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+        }
+        h->stage_bytes = stage;
+    }
+    // the kernels that produce `src` were launched on h->stream: let the copy stream follow them
+    cudaEvent_t ready = h->stage_ev[0];
+    CUDA_TRY(cudaEventRecord(ready, h->stream));
+    CUDA_TRY(cudaEventSynchronize(ready));
+    const size_t nchunks = (bytes + chunk - 1) / chunk;
+    std::vector<std::thread> workers;
+    std::vector<int> status(W, 0);
+    for (int w = 0; w < W; ++w) {
+        workers.emplace_back([=, &status]() {
+            if (cudaSetDevice(h->device) != cudaSuccess) { status[w] = 1; return; }
+            cudaStream_t s;
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { status[w] = 1; return; }
+            for (size_t c = w; c < nchunks; c += W) {
+                const size_t off = c * chunk, len = (off + chunk <= bytes) ? chunk : bytes - off;
+                void* buf = h->stage_buf[2 * w];
+                if (cudaMemcpyAsync(buf, (const char*)src + off, len, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                    cudaStreamSynchronize(s) != cudaSuccess) { status[w] = 1; break; }
+                memcpy((char*)dst + off, buf, len);
+            }
+            cudaStreamDestroy(s);
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int w = 0; w < W; ++w) if (status[w]) return fail(FN_ERR_CUDA, "staged device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+#define D2H_TRY(dst, src, bytes)                                  \
+    do {                                                          \
+        int rc__ = copy_d2h(h, (dst), (src), (bytes));            \
+        if (rc__) return rc__;                                    \
+    } while (0)
+
 static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, const double* aux,
                          const fn_family* family, const uint8_t* controls, int32_t c_noise,
                          const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
@@ -636,8 +692,6 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     const bool ia = h->fam.na == m && h->fam.kind != KIND_SCALE1, ib = h->fam.nb == m;
     const bool inplace = ia || ib;
     Geom g;
-    int threads_for_cols = 0;
-    (void)threads_for_cols;
     const size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
     int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0);
     if (rc) return rc;
@@ -866,9 +920,9 @@ extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double*
     if (rc) return rc;
     rc = h->fam.nf > 0 ? launch_eval_factors(h, ts, true, false) : launch_eval(h, ts, true, false);
     if (rc) return rc;
-    if (score) CUDA_TRY(cudaMemcpyAsync(score, h->pg_score, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (d2) CUDA_TRY(cudaMemcpyAsync(d2, h->pg_d2, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (p) CUDA_TRY(cudaMemcpyAsync(p, h->pg_p, h->n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (score) D2H_TRY(score, h->pg_score, h->n * sizeof(double));
+    if (d2) D2H_TRY(d2, h->pg_d2, h->n * sizeof(double));
+    if (p) D2H_TRY(p, h->pg_p, h->n * sizeof(int));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -887,8 +941,8 @@ extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, doub
     noise_p_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(h->n, h->pg_d2, h->pg_p, ts.is_t, ts.v, h->noise_p);
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
-    if (noise_p) CUDA_TRY(cudaMemcpyAsync(noise_p, h->noise_p, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (averages) CUDA_TRY(cudaMemcpyAsync(averages, h->avg, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (noise_p) D2H_TRY(noise_p, h->noise_p, h->n * sizeof(double));
+    if (averages) D2H_TRY(averages, h->avg, h->n * sizeof(double));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -947,9 +1001,9 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     });
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
-    if (coef) CUDA_TRY(cudaMemcpyAsync(coef, h->coef, (size_t)h->n * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (covar) CUDA_TRY(cudaMemcpyAsync(covar, h->covar, (size_t)h->n * c * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (dfpost) CUDA_TRY(cudaMemcpyAsync(dfpost, h->dfpost, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (coef) D2H_TRY(coef, h->coef, (size_t)h->n * c * sizeof(double));
+    if (covar) D2H_TRY(covar, h->covar, (size_t)h->n * c * c * sizeof(double));
+    if (dfpost) D2H_TRY(dfpost, h->dfpost, (size_t)h->n * sizeof(double));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -986,15 +1040,15 @@ static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* 
     test_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(tp);
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
-    if (contrasted) CUDA_TRY(cudaMemcpyAsync(contrasted, d_out, nb_out, cudaMemcpyDeviceToHost, h->stream));
-    if (ccov) CUDA_TRY(cudaMemcpyAsync(ccov, d_cc, nb_cc, cudaMemcpyDeviceToHost, h->stream));
-    if (pval) CUDA_TRY(cudaMemcpyAsync(pval, d_p, nb_p, cudaMemcpyDeviceToHost, h->stream));
+    if (contrasted) D2H_TRY(contrasted, d_out, nb_out);
+    if (ccov) D2H_TRY(ccov, d_cc, nb_cc);
+    if (pval) D2H_TRY(pval, d_p, nb_p);
     if (qval) {
         uint32_t* d_order = nullptr;
         rc = bh_run(h, h->n, d_p, d_q, base, &d_order);   // p never leaves the device between test and BH
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(qval, d_q, nb_p, cudaMemcpyDeviceToHost, h->stream));
-        if (order) CUDA_TRY(cudaMemcpyAsync(order, d_order, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        D2H_TRY(qval, d_q, nb_p);
+        if (order) D2H_TRY(order, d_order, (size_t)h->n * sizeof(uint32_t));
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1014,9 +1068,9 @@ extern "C" int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* 
     if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_coef_fetch needs a preceding fn_coef");
     const int c = h->coef_c;
     CUDA_TRY(cudaSetDevice(h->device));
-    if (coef) CUDA_TRY(cudaMemcpyAsync(coef, h->coef, (size_t)h->n * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (covar) CUDA_TRY(cudaMemcpyAsync(covar, h->covar, (size_t)h->n * c * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (dfpost) CUDA_TRY(cudaMemcpyAsync(dfpost, h->dfpost, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (coef) D2H_TRY(coef, h->coef, (size_t)h->n * c * sizeof(double));
+    if (covar) D2H_TRY(covar, h->covar, (size_t)h->n * c * c * sizeof(double));
+    if (dfpost) D2H_TRY(dfpost, h->dfpost, (size_t)h->n * sizeof(double));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1039,7 +1093,7 @@ extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* 
     weights_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(wp);
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(weights, wp.out, bytes, cudaMemcpyDeviceToHost, h->stream));
+    D2H_TRY(weights, wp.out, bytes);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1123,8 +1177,8 @@ static int bh_host(fn_handle* h, int64_t n, const double* p, double* q, uint32_t
     uint32_t* d_order = nullptr;
     rc = bh_run(h, n, p_dev, q_dev, base, &d_order);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(q, q_dev, n * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (order) CUDA_TRY(cudaMemcpyAsync(order, d_order, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    D2H_TRY(q, q_dev, n * 8);
+    if (order) D2H_TRY(order, d_order, n * sizeof(uint32_t));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }

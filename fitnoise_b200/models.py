@@ -17,7 +17,7 @@ import sys
 import numpy as np
 import scipy.optimize
 
-from . import _native, p_adjust
+from . import _native
 from .distributions import Mvnormal, Mvt
 from .env import Withable, as_matrix, as_vector
 from .session import Session
