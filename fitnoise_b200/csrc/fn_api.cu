@@ -509,8 +509,9 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
                          const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
                          fn_prep_info* info, cudaMemcpyKind kind) {
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
-    if (!y || !family || !design_noise) return fail(FN_ERR_ARG, "fn_upload: y, family and design_noise are required");
-    if (n < 1 || m < 1) return fail(FN_ERR_ARG, "fn_upload: empty data (n=%lld, m=%d)", (long long)n, m);
+    // n == 0 is allowed: an empty shard (fewer genes than GPUs) still takes part in every exchange
+    if ((!y && n > 0) || !family || !design_noise) return fail(FN_ERR_ARG, "fn_upload: y, family and design_noise are required");
+    if (n < 0 || m < 1) return fail(FN_ERR_ARG, "fn_upload: bad shape (n=%lld, m=%d)", (long long)n, m);
     if (n >= (1LL << 31)) return fail(FN_ERR_UNSUPPORTED, "fn_upload: more than 2^31 genes per handle; shard across handles");
     Family fam;
     memcpy(&fam, family, sizeof fam);
@@ -544,18 +545,21 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     release_data(h);
     h->n = n; h->m = m; h->fam = fam; h->has_aux = aux != nullptr; h->dn = dn; h->dc = dc; h->width = width;
     h->n_pad = (n + FN_ROW_PAD - 1) / FN_ROW_PAD * FN_ROW_PAD;
+    if (h->n_pad == 0) h->n_pad = FN_ROW_PAD;
     const size_t rows = (size_t)h->n_pad * m * sizeof(double);
     const size_t used = (size_t)n * m * sizeof(double);
     CUDA_TRY(ensure_buf(h->b_y, rows));
     h->y = (double*)h->b_y.p;
     CUDA_TRY(cudaMemsetAsync((char*)h->y + used, 0xFF, rows - used, h->stream));       // NaN padding rows
-    if (kind == cudaMemcpyHostToDevice) { int rcc = copy_h2d(h, h->y, y, used); if (rcc) return rcc; }
+    if (used == 0) { /* empty shard: padding only */ }
+    else if (kind == cudaMemcpyHostToDevice) { int rcc = copy_h2d(h, h->y, y, used); if (rcc) return rcc; }
     else CUDA_TRY(cudaMemcpyAsync(h->y, y, used, kind, h->stream));
     if (aux) {
         CUDA_TRY(ensure_buf(h->b_aux, rows));
         h->aux = (double*)h->b_aux.p;
         CUDA_TRY(cudaMemsetAsync((char*)h->aux + used, 0xFF, rows - used, h->stream));
-        if (kind == cudaMemcpyHostToDevice) { int rcc = copy_h2d(h, h->aux, aux, used); if (rcc) return rcc; }
+        if (used == 0) { /* empty shard */ }
+        else if (kind == cudaMemcpyHostToDevice) { int rcc = copy_h2d(h, h->aux, aux, used); if (rcc) return rcc; }
         else CUDA_TRY(cudaMemcpyAsync(h->aux, aux, used, kind, h->stream));
     }
     CUDA_TRY(ensure_buf(h->b_status, h->n_pad));
@@ -572,7 +576,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     }
     {
         uint8_t* ctl_dev = nullptr;
-        if (controls) {
+        if (controls && n > 0) {
             if (kind == cudaMemcpyHostToDevice) {
                 const int rcs = ensure_scratch(h, (size_t)n);
                 if (rcs) return rcs;
@@ -938,8 +942,10 @@ extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, doub
         h->noise_p = (double*)h->b_noise_p.p;
     }
     const int tb = 128;
-    noise_p_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(h->n, h->pg_d2, h->pg_p, ts.is_t, ts.v, h->noise_p);
-    ++h->launches;
+    if (h->n > 0) {
+        noise_p_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(h->n, h->pg_d2, h->pg_p, ts.is_t, ts.v, h->noise_p);
+        ++h->launches;
+    }
     CUDA_TRY(cudaGetLastError());
     if (noise_p) D2H_TRY(noise_p, h->noise_p, h->n * sizeof(double));
     if (averages) D2H_TRY(averages, h->avg, h->n * sizeof(double));
@@ -1037,13 +1043,15 @@ static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* 
     tp.coef = h->coef; tp.covar = h->covar; tp.dfpost = h->dfpost; tp.contrasts = d_con;
     tp.contrasted = d_out; tp.ccov = d_cc; tp.pval = d_p;
     const int tb = 128;
-    test_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(tp);
-    ++h->launches;
+    if (h->n > 0) {
+        test_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(tp);
+        ++h->launches;
+    }
     CUDA_TRY(cudaGetLastError());
     if (contrasted) D2H_TRY(contrasted, d_out, nb_out);
     if (ccov) D2H_TRY(ccov, d_cc, nb_cc);
     if (pval) D2H_TRY(pval, d_p, nb_p);
-    if (qval) {
+    if (qval && h->n > 0) {
         uint32_t* d_order = nullptr;
         rc = bh_run(h, h->n, d_p, d_q, base, &d_order);   // p never leaves the device between test and BH
         if (rc) return rc;

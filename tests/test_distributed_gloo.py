@@ -86,6 +86,40 @@ def test_two_ranks_match_one(tmp_path):
         assert ranks[0][key]["description"] == ranks[1][key]["description"]
 
 
+def _tiny_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fitnoise_b200 as fitnoise
+        import hostcheck
+        rng = np.random.default_rng(5)
+        y = rng.normal(size=(1, 6))                       # ONE gene on two ranks: rank 1 owns nothing
+        design = np.array([[1.0, 0.0]] * 3 + [[1.0, 1.0]] * 3)
+        model = fitnoise.Model_t()._with(_engine_factory=hostcheck.HostEvaluator)
+        fitted = model.fit(y, design, force_param=[5.0, 1.0])
+        tested = fitted.test(coef=[1])
+        value, grad, used, bad = fitted._objective([5.0, 1.0])
+        np.save(os.path.join(out_dir, "tiny%d.npy" % rank),
+                dict(shard=(fitted._session.lo, fitted._session.hi), coef=fitted.coef, p=tested.p_values,
+                     q=tested.q_values, value=value, used=used), allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fewer_genes_than_ranks(tmp_path):
+    port = _free_port()
+    mp.spawn(_tiny_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(os.path.join(str(tmp_path), "tiny%d.npy" % k), allow_pickle=True).item() for k in range(2)]
+    assert r[0]["shard"] == (0, 1) and r[1]["shard"] == (1, 1)
+    for k in range(2):
+        assert r[k]["coef"].shape == (1, 2) and r[k]["used"] == 1
+        assert np.array_equal(r[k]["p"], r[0]["p"]) and np.array_equal(r[k]["q"], r[0]["q"])
+    assert r[0]["value"] == r[1]["value"]
+
+
 def test_shard_bounds():
     from fitnoise_b200 import parallel
     for n, w in [(10, 1), (10, 3), (7, 8), (1000001, 8), (0, 2)]:

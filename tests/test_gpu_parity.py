@@ -342,6 +342,34 @@ def test_degenerate_inputs():
         fitnoise.Model_t().fit(np.zeros((3, 6)), np.ones((5, 1)))   # design rows != samples
 
 
+def test_empty_shard():
+    """n = 0 (a rank that owns no gene when there are fewer genes than GPUs) goes through every call."""
+    fam = fitnoise.Model_t()._family(6)
+    design = np.array([[1.0, 0.0]] * 3 + [[1.0, 1.0]] * 3)
+    e = _native.Engine(0)
+    try:
+        info = e.upload(np.zeros((0, 6)), None, fam, None, design)
+        assert info.n_eligible == 0
+        v, g, used, bad = e.nll_grad([5.0, 1.0])
+        assert (v, used, bad) == (0.0, 0, 0) and np.all(g == 0.0)
+        assert all(len(a) == 0 for a in e.per_gene([5.0, 1.0]))
+        assert all(len(a) == 0 for a in e.noise_stats([5.0, 1.0]))
+        coef, covar, df = e.coef([5.0, 1.0], design)
+        assert coef.shape == (0, 2) and covar.shape == (0, 2, 2)
+        con, pv, q = e.test_bh(np.array([[0.0], [1.0]]))
+        assert con.shape == (0, 1) and len(pv) == 0 and len(q) == 0
+        assert e.weights([5.0, 1.0]).shape == (0, 6)
+        pat = fitnoise.Model_t_patseq()._family(6)
+        e.upload(np.zeros((0, 6)), np.zeros((0, 6)), pat, None, design)
+        v, g, used, bad = e.nll_grad([5.0, 100.0, 0.01])
+        assert used == 0 and v == 0.0
+    finally:
+        e.close()
+    fitted = fitnoise.Model_t().fit(np.zeros((0, 6)), design, force_param=[5.0, 1.0])
+    tested = fitted.test(coef=[1])
+    assert fitted.coef.shape == (0, 2) and len(tested.q_values) == 0 and fitted.noise_combined_p_value == 0.0
+
+
 def test_top_table_order_bit_exact(engine):
     """The top-table order is the stable ascending order of p with missing p last (R's order(),
     backyard/old_fitnoise.R:822-823), bit-exact with numpy's stable argsort."""
