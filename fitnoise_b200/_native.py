@@ -25,7 +25,7 @@ EXPORTS = [
     "fn_upload", "fn_upload_dev", "fn_nll_grad", "fn_nll_grad_dev", "fn_per_gene", "fn_noise_stats",
     "fn_coef", "fn_test", "fn_bh", "fn_bh_dev", "fn_weights", "fn_set_tuning", "fn_launch_count",
     "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
-    "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked", "fn_nll_grad_factors", "fn_set_factors",
+    "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked", "fn_nll_grad_factors", "fn_set_factors", "fn_time_nll_grad",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
                                         c_double_p, c_double_p, ctypes.POINTER(ctypes.c_int64),
                                         ctypes.POINTER(ctypes.c_int64)]
     lib.fn_set_factors.argtypes = [ctypes.c_void_p, c_double_p]
+    lib.fn_time_nll_grad.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p]
     lib.fn_nll_grad_dev.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_void_p]
     lib.fn_per_gene.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_int32_p]
     lib.fn_noise_stats.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p]
@@ -329,6 +330,13 @@ class Engine(object):
 
     def set_timing(self, on=True):
         self._check(self._lib.fn_set_timing(self._h, 1 if on else 0))
+
+    def time_nll_grad(self, theta, reps=50):
+        """Kernel-only ms per nll+grad launch: `reps` launches queued back to back between events."""
+        theta = _f64(theta).reshape(-1)
+        ms = ctypes.c_double()
+        self._check(self._lib.fn_time_nll_grad(self._h, _dp(theta), len(theta), int(reps), ctypes.byref(ms)))
+        return ms.value
 
     def last_kernel_ms(self):
         return float(self._lib.fn_last_kernel_ms(self._h))

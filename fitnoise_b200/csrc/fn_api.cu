@@ -889,6 +889,30 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
     return 0;
 }
 
+// Kernel-only duration: `reps` evaluations queued back to back on the handle's stream between two
+// CUDA events (no host wait and no idle gap in between, so launch latency is not counted).
+extern "C" int fn_time_nll_grad(fn_handle* h, const double* theta, int32_t P, int32_t reps, double* ms_per_launch) {
+    ThetaState ts;
+    int rc = stage_theta(h, theta, P, ts);
+    if (rc) return rc;
+    if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
+    if (reps < 1 || !ms_per_launch) return fail(FN_ERR_ARG, "fn_time_nll_grad: bad arguments");
+    const bool was_timing = h->timing;
+    h->timing = false;
+    rc = launch_eval(h, ts, false, false);          // warm: attributes set, buffers sized
+    if (rc) { h->timing = was_timing; return rc; }
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps && rc == 0; ++i) rc = launch_eval(h, ts, false, false);
+    h->timing = was_timing;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *ms_per_launch = (double)ms / reps;
+    return 0;
+}
+
 // device-side assemble for the asynchronous (multi-GPU) form
 __global__ void assemble_kernel(const double* acc, double* out, Family f, int m, const double* ta) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

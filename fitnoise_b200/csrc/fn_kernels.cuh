@@ -114,7 +114,18 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
             if (gr.out_host) slot_store(&gr.out_host[i], s, gr.host_seq);
         }
     };
-    if (nacc <= T) {
+    if (nacc * 32 <= T) {
+        // one warp per component: lane l adds blocks l, l+32, ... (independent loads), then a shuffle
+        // tree; no shared memory, no barrier.  The usual case (6 accumulators, 256 threads).
+        const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (i < nacc) {
+            double s = 0.0;
+            for (unsigned int b = lane; b < G; b += 32) s += __ldcg(&gr.partials[(size_t)b * nacc + i]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) publish(i, s);
+        }
+    } else if (nacc <= T) {
         // thread (slice, i) adds blocks slice, slice+S, ... of component i; then the slices are added
         const int S = T / nacc, i = threadIdx.x % nacc, slice = threadIdx.x / nacc;
         if (slice < S) {

@@ -157,6 +157,9 @@ int64_t fn_launch_count(fn_handle* h);
 /* Average device time (ms) of the last fn_nll_grad kernel, measured with CUDA events on the
  * handle's stream when timing is enabled with fn_set_timing(h, 1). */
 int fn_set_timing(fn_handle* h, int32_t on);
+/* Kernel-only duration of the nll+grad kernel: `reps` launches queued back to back between two CUDA
+ * events (no idle gap, so launch latency is not counted); this handle's genes only (no exchange). */
+int fn_time_nll_grad(fn_handle* h, const double* theta, int32_t P, int32_t reps, double* ms_per_launch);
 double fn_last_kernel_ms(fn_handle* h);
 
 #ifdef __cplusplus

@@ -60,9 +60,9 @@ with torch.cuda.stream(stream):
             for _ in range(2):
                 v = e.nll_grad(theta)
             ts = []
-            for _ in range(7):
+            for _ in range(3):
                 v = e.nll_grad(theta)
-                ts.append(e.last_kernel_ms())
+                ts.append(e.time_nll_grad(theta, 50))        # queued: kernel-only
         except Exception as exc:
             print(threads, lpg, stages, ctas, "ERR", exc)
             continue
