@@ -116,6 +116,14 @@ struct fn_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
 
+    // Benjamini-Hochberg as a captured CUDA graph (see bh_run)
+    cudaGraphExec_t bh_exec = nullptr;
+    int64_t bh_n = 0;
+    const void* bh_p = nullptr;
+    void* bh_q = nullptr;
+    void* bh_work = nullptr;
+    uint32_t* bh_order = nullptr;
+
     unsigned long long host_seq = 0;   // completion-flag sequence of the pinned result buffer
     // fused multi-GPU exchange (fn_comm_*): mailboxes mapped with CUDA IPC
     int comm_world = 0, comm_rank = 0, comm_slot = 0;
@@ -218,6 +226,7 @@ extern "C" int fn_destroy(fn_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     fn_comm_disconnect(h);
+    if (h->bh_exec) { cudaGraphExecDestroy(h->bh_exec); h->bh_exec = nullptr; }
     free_buffers(h);
     dfree(h->partials); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
     if (h->out_host) cudaFreeHost(h->out_host);
@@ -339,6 +348,7 @@ static int ensure_reduce(fn_handle* h, int grid, int nacc) {
 
 static int ensure_scratch(fn_handle* h, size_t bytes) {
     if (bytes > h->scratch_cap) {
+        if (h->bh_exec) { cudaGraphExecDestroy(h->bh_exec); h->bh_exec = nullptr; }   // it points into the old scratch
         dfree(h->scratch_dev);
         CUDA_TRY(cudaMalloc(&h->scratch_dev, bytes));
         h->scratch_cap = bytes;
@@ -1133,7 +1143,8 @@ extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* 
 // ------------------------------------------------------------------------------------------
 // Benjamini-Hochberg
 // ------------------------------------------------------------------------------------------
-static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev) {
+// Enqueue the 44 kernels of one Benjamini-Hochberg adjustment on the handle's stream.
+static void bh_enqueue(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev) {
     const int nblocks = (int)((n + BH_CHUNK - 1) / BH_CHUNK);
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     uint64_t* keys0 = (uint64_t*)work; work += up(n * 8);
@@ -1147,7 +1158,6 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
     const long long hist_total = (long long)256 * nblocks;
     const int nseg = (int)((hist_total + BH_SEG - 1) / BH_SEG);
     bh_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, p_dev, keys0, idx0);
-    ++h->launches;
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = 8 * pass;
         bh_hist_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, shift, hist, nblocks);
@@ -1155,16 +1165,52 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
         bh_segscan_kernel<<<1, 1024, 0, h->stream>>>(seg, nseg);
         bh_segapply_kernel<<<nseg, BH_THREADS, 0, h->stream>>>(hist, hist_total, seg);
         bh_scatter_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, keys1, idx1, shift, hist, nblocks);
-        h->launches += 5;
         std::swap(keys0, keys1);
         std::swap(idx0, idx1);
     }
     bh_chunkmin_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, chunk_min);
     bh_carry_kernel<<<(nblocks + 127) / 128, 128, 0, h->stream>>>(nblocks, chunk_min, carry);
     bh_finish_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, carry, q_dev);
-    h->launches += 3;
-    CUDA_TRY(cudaGetLastError());
     if (order_dev) *order_dev = idx0;          // genes by ascending p (stable, NaN last)
+}
+
+// The adjustment is a fixed sequence of 44 small launches -- launch-bound at the usual 10^4..10^6
+// p-values -- so it is captured once into a CUDA graph per (n, buffers) and replayed with a single
+// cudaGraphLaunch afterwards.  Any failure of the capture machinery falls back to plain launches.
+static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev) {
+    const bool use_graph = getenv("FN_NO_GRAPH") == nullptr;
+    if (use_graph && h->bh_exec && h->bh_n == n && h->bh_p == p_dev && h->bh_q == q_dev && h->bh_work == work) {
+        if (cudaGraphLaunch(h->bh_exec, h->stream) == cudaSuccess) {
+            h->launches += 44;
+            if (order_dev) *order_dev = h->bh_order;
+            return 0;
+        }
+        cudaGetLastError();
+    }
+    if (h->bh_exec) { cudaGraphExecDestroy(h->bh_exec); h->bh_exec = nullptr; }
+    if (use_graph && cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        uint32_t* order = nullptr;
+        bh_enqueue(h, n, p_dev, q_dev, work, &order);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (e == cudaSuccess && graph && cudaGraphInstantiate(&h->bh_exec, graph, 0) == cudaSuccess) {
+            cudaGraphDestroy(graph);
+            h->bh_n = n; h->bh_p = p_dev; h->bh_q = q_dev; h->bh_work = work; h->bh_order = order;
+            if (cudaGraphLaunch(h->bh_exec, h->stream) == cudaSuccess) {
+                h->launches += 44;
+                if (order_dev) *order_dev = order;
+                return 0;
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (h->bh_exec) { cudaGraphExecDestroy(h->bh_exec); h->bh_exec = nullptr; }
+        cudaGetLastError();
+    } else {
+        cudaGetLastError();
+    }
+    bh_enqueue(h, n, p_dev, q_dev, work, order_dev);
+    h->launches += 44;
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
