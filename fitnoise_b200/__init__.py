@@ -14,7 +14,7 @@ VERSION = "2.2"
 
 from .env import Withable, as_jsonic  # noqa: F401,E402
 from .p_adjust import fdr  # noqa: F401,E402
-from .fittransform import transform  # noqa: F401,E402
+from .fittransform import Transform, Transform_polynomial, transform  # noqa: F401,E402
 from .distributions import Mvnormal, Mvt  # noqa: F401,E402
 from .models import *  # noqa: F401,F403,E402
 from .models import Dataset, Model, as_dataset  # noqa: F401,E402

@@ -26,6 +26,7 @@ EXPORTS = [
     "fn_coef", "fn_test", "fn_bh", "fn_bh_dev", "fn_weights", "fn_set_tuning", "fn_launch_count",
     "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
     "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked", "fn_nll_grad_factors", "fn_set_factors", "fn_time_nll_grad",
+    "fn_transform_upload", "fn_transform_sums", "fn_transform_apply",
 ]
 
 
@@ -91,6 +92,10 @@ def load_library():
                                         c_double_p, c_double_p, ctypes.POINTER(ctypes.c_int64),
                                         ctypes.POINTER(ctypes.c_int64)]
     lib.fn_set_factors.argtypes = [ctypes.c_void_p, c_double_p]
+    lib.fn_transform_upload.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                        ctypes.c_int32, c_double_p]
+    lib.fn_transform_sums.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p]
+    lib.fn_transform_apply.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p]
     lib.fn_time_nll_grad.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p]
     lib.fn_nll_grad_dev.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_void_p]
     lib.fn_per_gene.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_int32_p]
@@ -305,6 +310,27 @@ class Engine(object):
         out = np.empty((self.n, self.m))
         self._check(self._lib.fn_weights(self._h, _dp(theta), len(theta), _dp(out)))
         return out
+
+    # ---- fitnoise.transform -----------------------------------------------------------------
+    def transform_upload(self, x, design):
+        x, design = _f64(x), _f64(design)
+        self._tr_shape = x.shape
+        self._check(self._lib.fn_transform_upload(self._h, x.shape[0], x.shape[1], x.ctypes.data,
+                                                  design.shape[1], _dp(design)))
+
+    def transform_sums(self, order, a):
+        """Raw sums of one pass over x at polynomial coefficients a (order x m); see fn_transform.cuh."""
+        a = _f64(a).reshape(order, -1)
+        m = a.shape[1]
+        sums = np.empty(2 + m * (1 + 3 * order))
+        self._check(self._lib.fn_transform_sums(self._h, order, _dp(a), _dp(sums)))
+        return sums
+
+    def transform_apply(self, order, a, col_mean):
+        a, col_mean = _f64(a).reshape(order, -1), _f64(col_mean).reshape(-1)
+        y = np.empty(self._tr_shape)
+        self._check(self._lib.fn_transform_apply(self._h, order, _dp(a), _dp(col_mean), _dp(y)))
+        return y
 
     # ---- fused multi-GPU exchange ---------------------------------------------------------
     def comm_mailbox(self, world, max_values):

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -17,6 +18,7 @@
 #include "fn_bh.cuh"
 #include "fn_host.hpp"
 #include "fn_kernels.cuh"
+#include "fn_transform.cuh"
 
 using namespace fn;
 
@@ -124,6 +126,11 @@ struct fn_handle {
     void* bh_work = nullptr;
     uint32_t* bh_order = nullptr;
 
+    // fitnoise.transform (fn_transform_*): the count matrix and the design basis
+    DevBuf b_tx, b_tq, b_ta, b_tmean;
+    int64_t tr_n = 0;
+    int tr_m = 0, tr_c = 0;
+
     unsigned long long host_seq = 0;   // completion-flag sequence of the pinned result buffer
     // fused multi-GPU exchange (fn_comm_*): mailboxes mapped with CUDA IPC
     int comm_world = 0, comm_rank = 0, comm_slot = 0;
@@ -166,7 +173,7 @@ static void free_buffers(fn_handle* h) {
     release_data(h);
     DevBuf* all[] = {&h->b_y, &h->b_aux, &h->b_gs, &h->b_cst, &h->b_avg, &h->b_status, &h->b_xn, &h->b_xc, &h->b_tab,
                      &h->b_pg_score, &h->b_pg_d2, &h->b_pg_p, &h->b_noise_p, &h->b_coef, &h->b_covar, &h->b_dfpost,
-                     &h->b_xcoef, &h->b_rinv, &h->b_zn, &h->b_zc, &h->b_fsq};
+                     &h->b_xcoef, &h->b_rinv, &h->b_zn, &h->b_zc, &h->b_fsq, &h->b_tx, &h->b_tq, &h->b_ta, &h->b_tmean};
     for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     if (h->tab_host) { cudaFreeHost(h->tab_host); h->tab_host = nullptr; h->tab_host_cap = 0; }
     for (int i = 0; i < 2 * fn_handle::kStageWorkers; ++i) {
@@ -1318,3 +1325,104 @@ extern "C" int fn_trace_dump(fn_handle* h, unsigned long long* out64) {
     return 0;
 }
 #endif
+
+// ------------------------------------------------------------------------------------------
+// fitnoise.transform: moderated log transform of counts (fittransform.py)
+// ------------------------------------------------------------------------------------------
+extern "C" int fn_transform_upload(fn_handle* h, int64_t n, int32_t m, const double* x, int32_t c, const double* design) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    if (n < 0 || m < 1 || (!x && n > 0)) return fail(FN_ERR_ARG, "fn_transform_upload: bad arguments");
+    if (m > 256) return fail(FN_ERR_UNSUPPORTED, "transform supports m <= 256 (m = %d)", m);
+    if (c < 1 || c > FN_MAXC || !design) return fail(FN_ERR_UNSUPPORTED, "design has %d columns; 1..%d supported", c, FN_MAXC);
+    Design d;
+    if (!d.build(m, c, design)) return fail(FN_ERR_ARG, "design (%d x %d) is rank deficient", m, c);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::vector<double> q((size_t)m * c);
+    for (int j = 0; j < m; ++j) for (int i = 0; i < c; ++i) q[(size_t)j * c + i] = d.q[(size_t)j * d.width + i];
+    const size_t bytes = (size_t)n * m * sizeof(double);
+    CUDA_TRY(ensure_buf(h->b_tx, bytes));
+    CUDA_TRY(ensure_buf(h->b_tq, q.size() * sizeof(double)));
+    if (bytes) { int rc = copy_h2d(h, h->b_tx.p, x, bytes); if (rc) return rc; }
+    CUDA_TRY(cudaMemcpyAsync(h->b_tq.p, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->tr_n = n; h->tr_m = m; h->tr_c = c;
+    return 0;
+}
+
+#define FN_DISPATCH_TRANSFORM(K_, ORDER_, ...)                                                      \
+    switch ((K_) * 10 + (ORDER_)) {                                                                 \
+        case 11: { constexpr int K = 1, ORDER = 1; __VA_ARGS__; } break;                            \
+        case 12: { constexpr int K = 1, ORDER = 2; __VA_ARGS__; } break;                            \
+        case 13: { constexpr int K = 1, ORDER = 3; __VA_ARGS__; } break;                            \
+        case 21: { constexpr int K = 2, ORDER = 1; __VA_ARGS__; } break;                            \
+        case 22: { constexpr int K = 2, ORDER = 2; __VA_ARGS__; } break;                            \
+        case 23: { constexpr int K = 2, ORDER = 3; __VA_ARGS__; } break;                            \
+        case 31: { constexpr int K = 3, ORDER = 1; __VA_ARGS__; } break;                            \
+        case 32: { constexpr int K = 3, ORDER = 2; __VA_ARGS__; } break;                            \
+        case 33: { constexpr int K = 3, ORDER = 3; __VA_ARGS__; } break;                            \
+        case 41: { constexpr int K = 4, ORDER = 1; __VA_ARGS__; } break;                            \
+        case 42: { constexpr int K = 4, ORDER = 2; __VA_ARGS__; } break;                            \
+        case 43: { constexpr int K = 4, ORDER = 3; __VA_ARGS__; } break;                            \
+        case 81: { constexpr int K = 8, ORDER = 1; __VA_ARGS__; } break;                            \
+        case 82: { constexpr int K = 8, ORDER = 2; __VA_ARGS__; } break;                            \
+        case 83: { constexpr int K = 8, ORDER = 3; __VA_ARGS__; } break;                            \
+        default: return fail(FN_ERR_UNSUPPORTED, "transform: unsupported m / order");               \
+    }
+
+// sums: [Syy, Stt, s[m], A[order][m], B[order][m], D[order][m]]  (fn_transform.cuh); a: order x m
+extern "C" int fn_transform_sums(fn_handle* h, int32_t order, const double* a, double* sums) {
+    if (!h || h->tr_m == 0) return fail(FN_ERR_STATE, "fn_transform_sums needs fn_transform_upload");
+    if (order < 1 || order > TR_MAX_ORDER || !a || !sums) return fail(FN_ERR_UNSUPPORTED, "transform order must be 1..%d", TR_MAX_ORDER);
+    const int m = h->tr_m;
+    for (int i = 0; i < order * m; ++i) if (!(fabs(a[i]) < INFINITY)) return fail(FN_ERR_ARG, "transform parameters must be finite");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int nacc = 2 + m * (1 + 3 * order);
+    CUDA_TRY(ensure_buf(h->b_ta, (size_t)order * m * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(h->b_ta.p, a, (size_t)order * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int threads = 256, nwarp = threads / 32;
+    long long warps_needed = h->tr_n > 0 ? h->tr_n : 1;
+    int grid = (int)std::min<long long>((warps_needed + nwarp - 1) / nwarp, (long long)h->sm_count * 4);
+    int rc = ensure_reduce(h, grid, nacc);
+    if (rc) return rc;
+    TransformParams tp;
+    tp.n = h->tr_n; tp.m = m; tp.c = h->tr_c; tp.order = order;
+    tp.x = (const double*)h->b_tx.p; tp.q = (const double*)h->b_tq.p; tp.a = (const double*)h->b_ta.p;
+    fill_reduce(h, tp.gr, nacc, -1, 0.0, false);
+    const size_t smem = ((size_t)nacc + 32 * nwarp) * sizeof(double);
+    int k = (m + 31) / 32;
+    if (k > 4) k = 8;
+    FN_DISPATCH_TRANSFORM(k, order, {
+        rc = set_smem(h, transform_kernel<K, ORDER>, smem);
+        if (rc) return rc;
+        transform_kernel<K, ORDER><<<grid, threads, smem, h->stream>>>(tp);
+    });
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    rc = wait_result(h, h->host_seq, nacc);
+    if (rc) return rc;
+    for (int i = 0; i < nacc; ++i) sums[i] = h->out_vals[i];
+    return 0;
+}
+
+extern "C" int fn_transform_apply(fn_handle* h, int32_t order, const double* a, const double* col_mean, double* y) {
+    if (!h || h->tr_m == 0) return fail(FN_ERR_STATE, "fn_transform_apply needs fn_transform_upload");
+    if (order < 1 || order > TR_MAX_ORDER || !a || !col_mean || !y) return fail(FN_ERR_ARG, "fn_transform_apply: bad arguments");
+    const int m = h->tr_m;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->tr_n * m * sizeof(double);
+    int rc = ensure_scratch(h, bytes ? bytes : 16);
+    if (rc) return rc;
+    CUDA_TRY(ensure_buf(h->b_ta, (size_t)order * m * sizeof(double)));
+    CUDA_TRY(ensure_buf(h->b_tmean, (size_t)m * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(h->b_ta.p, a, (size_t)order * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->b_tmean.p, col_mean, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    transform_apply_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->tr_n, m, order, (const double*)h->b_tx.p,
+                                                                   (const double*)h->b_ta.p, (const double*)h->b_tmean.p,
+                                                                   (double*)h->scratch_dev);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (bytes) D2H_TRY(y, h->scratch_dev, bytes);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}

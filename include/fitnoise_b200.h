@@ -149,6 +149,19 @@ int fn_comm_mailbox(fn_handle* h, int32_t world, int32_t max_values, void* ipc_h
 int fn_comm_connect(fn_handle* h, int32_t rank, int32_t world, const void* ipc_handles);
 int fn_comm_disconnect(fn_handle* h);
 
+/* fitnoise.transform (fittransform.py:65-219): moderated log transform of a count matrix,
+ * y = ln(P_j(x)) / (order ln 2) with a per-sample monic polynomial P_j of degree `order`.
+ *   fn_transform_upload  x: n x m counts, design: m x c (fittransform.py:76-85)
+ *   fn_transform_sums    one pass over x at parameters a (order x m, row i = coefficient of
+ *                        x^(order-1-i), Transform_polynomial._unpack_transform :180-186): returns
+ *                        [Syy, Stt, s[m], A[order][m], B[order][m], D[order][m]] from which the caller
+ *                        forms the objective ln(var_h1) - ln(var_h0) (:103-121) and its gradient
+ *                        (theano.gradient.grad, :137) -- raw sums so that shards of genes add up.
+ *   fn_transform_apply   y (n x m) = transform(x) - col_mean  (:161-163) */
+int fn_transform_upload(fn_handle* h, int64_t n, int32_t m, const double* x, int32_t c, const double* design);
+int fn_transform_sums(fn_handle* h, int32_t order, const double* a, double* sums);
+int fn_transform_apply(fn_handle* h, int32_t order, const double* a, const double* col_mean, double* y);
+
 /* Tuning knobs for experiments (0 = automatic): lanes per gene, threads per CTA, pipeline stages,
  * CTAs per SM. */
 int fn_set_tuning(fn_handle* h, int32_t lpg, int32_t threads, int32_t stages, int32_t ctas_per_sm);

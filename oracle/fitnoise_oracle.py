@@ -637,3 +637,75 @@ def fit_and_test(model, y, design, context=None, coef_idx=None, contrasts=None,
         out.update(contrasts=contrasted, contrast_covar=ccov, p_values=p, q_values=q)
     out["cfg"] = cfg
     return out
+
+
+# --------------------------------------------------------------------------------------
+# fitnoise.transform (fittransform.py).  PARITY UNPINNED: the reference evaluates this objective only
+# through Theano (no numpy path), which cannot be installed here, so no golden vector can be
+# generated from the reference.  This restatement follows fittransform.py line by line on explicit
+# n x m matrices; the tests check its gradient against central differences and the CUDA path
+# against it.
+# --------------------------------------------------------------------------------------
+
+def transform_apply(pack, x, order):
+    """Transform_polynomial._unpack_transform / _apply_transform, fittransform.py:180-194."""
+    m = x.shape[1]
+    poly = 1.0
+    for i in range(order):
+        poly = poly * x + pack[i * m:(i + 1) * m][None, :]
+    return np.log(poly) * (1.0 / (order * np.log(2.0)))
+
+
+def transform_cost(pack, x, design, order):
+    """vcost of Transform.fit, fittransform.py:103-121."""
+    q, r = np.linalg.qr(design, mode="complete")
+    q_null = q[:, design.shape[1]:]
+    y = transform_apply(pack, x, order)
+    centered = y - y.mean(axis=0)[None, :]
+    residual = centered @ q_null
+    return float(np.log((residual * residual).sum()) - np.log((centered * centered).sum()))
+
+
+def transform_cost_grad(pack, x, design, order):
+    """The cost and its gradient by matrix calculus on the reference's own quantities (what
+    theano.gradient.grad returns at fittransform.py:137)."""
+    pack = np.asarray(pack, dtype="float64")
+    n, m = x.shape
+    q, r = np.linalg.qr(design, mode="complete")
+    q_null = q[:, design.shape[1]:]
+    poly = 1.0
+    for i in range(order):
+        poly = poly * x + pack[i * m:(i + 1) * m][None, :]
+    scale = 1.0 / (order * np.log(2.0))
+    y = np.log(poly) * scale
+    centered = y - y.mean(axis=0)[None, :]
+    residual = centered @ q_null
+    v1, v0 = (residual * residual).sum(), (centered * centered).sum()
+    g_centered = 2.0 * (residual @ q_null.T) / v1 - 2.0 * centered / v0
+    g_y = g_centered - g_centered.mean(axis=0)[None, :]
+    grad = np.zeros(order * m)
+    for i in range(order):
+        dy = scale * x ** (order - 1 - i) / poly
+        grad[i * m:(i + 1) * m] = (g_y * dy).sum(axis=0)
+    return float(np.log(v1) - np.log(v0)), grad
+
+
+def transform_fit(x, design=None, order=2):
+    """Transform.fit's optimiser loop, fittransform.py:140-163."""
+    x = np.asarray(x, dtype="float64")
+    n, m = x.shape
+    if design is None:
+        design = np.ones((m, 1))
+    design = np.asarray(design, dtype="float64")
+    a = np.asarray([0.0] * (order - 1) * m + [1.0] * m)
+    bounds = [(0.0, None)] * (order - 1) * m + [(1e-10, None)] * m
+    last = None
+    for _ in range(100):
+        fit = scipy.optimize.minimize(lambda p: transform_cost_grad(p, x, design, order), a,
+                                      method="L-BFGS-B", jac=True, bounds=bounds)
+        a = fit.x
+        if last is not None and last - fit.fun <= 1e-6:
+            break
+        last = fit.fun
+    y = transform_apply(a, x, order)
+    return fit, y - y.mean(axis=0)

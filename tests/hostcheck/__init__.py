@@ -201,6 +201,34 @@ class HostEvaluator(object):
         q[order] = qs
         return q
 
+    # fitnoise.transform stand-in: the kernel's sums (csrc/fn_transform.cuh) in plain numpy
+    def transform_upload(self, x, design):
+        self.tx = np.asarray(x, dtype=np.float64)
+        q, _ = np.linalg.qr(np.asarray(design, dtype=np.float64))
+        self.tq = q
+
+    def _transform_parts(self, order, a):
+        a = np.asarray(a, dtype=np.float64).reshape(order, -1)
+        poly = 1.0
+        for i in range(order):
+            poly = poly * self.tx + a[i][None, :]
+        scale = 1.0 / (order * np.log(2.0))
+        return a, poly, np.log(poly) * scale, scale
+
+    def transform_sums(self, order, a):
+        a, poly, y, scale = self._transform_parts(order, a)
+        t = y @ self.tq
+        proj = t @ self.tq.T
+        A, B, D = [], [], []
+        for i in range(order):
+            w = scale * self.tx ** (order - 1 - i) / poly
+            A.append((y * w).sum(axis=0)); B.append(w.sum(axis=0)); D.append((proj * w).sum(axis=0))
+        return np.concatenate([[(y * y).sum(), (t * t).sum()], y.sum(axis=0)] + A + B + D)
+
+    def transform_apply(self, order, a, col_mean):
+        a, poly, y, scale = self._transform_parts(order, a)
+        return y - np.asarray(col_mean)[None, :]
+
     def weights(self, theta):
         theta = np.asarray(theta, dtype=np.float64).reshape(-1)
         fam = self.family

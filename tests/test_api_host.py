@@ -98,8 +98,6 @@ def test_errors():
             fitnoise.Dataset(y, {"counts": counts}), design)
     with pytest.raises(AssertionError):                           # factors need a SCALE1 variance model
         type("Bad", (fitnoise.Model_factors_mixin, fitnoise.Model_normal_per_sample), {})(1)._family(6)
-    with pytest.raises(NotImplementedError):
-        fitnoise.transform(y)
 
     class Custom(fitnoise.Model):
         def _get_dist(self, param, aux):

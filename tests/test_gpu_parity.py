@@ -481,3 +481,42 @@ def test_full_size_configs_against_host_build(config):
         assert np.array_equal(e.last_order.astype(np.int64), np.argsort(gpv, kind="stable")), "top-table order"
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("n,m,order", [(1, 3, 2), (500, 6, 1), (3000, 6, 2), (777, 33, 3), (2000, 96, 2),
+                                       (300, 130, 2), (120, 250, 1)])
+def test_transform_kernel_against_oracle(n, m, order):
+    """fitnoise.transform: objective and gradient from the CUDA sums kernel against the oracle's
+    dense matrix-calculus restatement of fittransform.py:103-137, and the applied transform."""
+    from fitnoise_b200 import fittransform
+    rng = np.random.default_rng(n + m + order)
+    x = rng.poisson(np.exp(rng.normal(3.0, 1.5, size=(n, 1))) * rng.uniform(0.5, 2.0, size=m)).astype(float)
+    c = min(3, m)
+    design = np.concatenate([np.ones((m, 1)), rng.normal(size=(m, c - 1))], axis=1)
+    pack = np.concatenate([rng.uniform(0.0, 2.0, size=(order - 1) * m), rng.uniform(0.5, 3.0, size=m)])
+    q, _ = np.linalg.qr(design)
+    e = _native.Engine(0)
+    try:
+        e.transform_upload(x, design)
+        sums = e.transform_sums(order, pack)
+        cost, grad, mu = fittransform._combine(sums, n, m, order, q @ q.T)
+        y = e.transform_apply(order, pack, mu)
+    finally:
+        e.close()
+    want = oracle.transform_apply(pack, x, order)
+    assert_close(y, want - want.mean(axis=0), 1e-10, atol=1e-12, what="applied transform")
+    if n > 1:
+        ocost, ograd = oracle.transform_cost_grad(pack, x, design, order)
+        assert_close(cost, ocost, 1e-10, what="objective")
+        assert_close(grad, ograd, 1e-7, atol=1e-11, what="gradient")
+
+
+def test_transform_fit_on_gpu():
+    x = np.random.default_rng(1).poisson(np.exp(np.random.default_rng(2).normal(3, 1.5, size=(5000, 1)))
+                                         * np.linspace(0.5, 2.0, 8)).astype(float)
+    design = np.stack([np.ones(8), (np.arange(8) >= 4) * 1.0], axis=1)
+    fitted = fitnoise.transform(x, design=design, order=2)
+    ofit, oy = oracle.transform_fit(x, design, 2)
+    assert abs(fitted.optimization_result.fun - ofit.fun) <= 2e-3 * abs(ofit.fun)
+    want = oracle.transform_apply(fitted.optimization_result.x, x, 2)
+    assert_close(fitted.y, want - want.mean(axis=0), 1e-10, atol=1e-12)
