@@ -1382,16 +1382,16 @@ extern "C" int fn_transform_sums(fn_handle* h, int32_t order, const double* a, d
     CUDA_TRY(cudaMemcpyAsync(h->b_ta.p, a, (size_t)order * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     const int threads = 256, nwarp = threads / 32;
     long long warps_needed = h->tr_n > 0 ? h->tr_n : 1;
-    int grid = (int)std::min<long long>((warps_needed + nwarp - 1) / nwarp, (long long)h->sm_count * 4);
+    int grid = (int)std::min<long long>((warps_needed + nwarp - 1) / nwarp, (long long)h->sm_count * 2);
     int rc = ensure_reduce(h, grid, nacc);
     if (rc) return rc;
     TransformParams tp;
     tp.n = h->tr_n; tp.m = m; tp.c = h->tr_c; tp.order = order;
     tp.x = (const double*)h->b_tx.p; tp.q = (const double*)h->b_tq.p; tp.a = (const double*)h->b_ta.p;
     fill_reduce(h, tp.gr, nacc, -1, 0.0, false);
-    const size_t smem = ((size_t)nacc + 32 * nwarp) * sizeof(double);
     int k = (m + 31) / 32;
     if (k > 4) k = 8;
+    const size_t smem = ((size_t)nacc + 32 * nwarp + 32 * k * FN_MAXC) * sizeof(double);
     FN_DISPATCH_TRANSFORM(k, order, {
         rc = set_smem(h, transform_kernel<K, ORDER>, smem);
         if (rc) return rc;

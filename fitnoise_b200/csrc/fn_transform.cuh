@@ -11,6 +11,8 @@
 // Mapping: a warp per gene; lane l owns samples l, l+32, ... (K per lane), read straight from
 // global memory (each read of a warp is one contiguous 256-byte run), kept in registers for the
 // second sweep; the per-sample sums live in the owning lane's registers for the whole kernel.
+// The design basis sits in shared memory (m x 8, zero padded) so that the register budget allows
+// two CTAs per SM: the kernel is bound by the fp64 pipe (one log and one division per count).
 #pragma once
 #include <cuda_runtime.h>
 #include "fn_kernels.cuh"
@@ -30,22 +32,26 @@ struct TransformParams {
 
 // K = samples per lane = ceil(m / 32); C = design columns (template width)
 template <int K, int ORDER>
-__global__ void __launch_bounds__(256) transform_kernel(const TransformParams p) {
+__global__ void __launch_bounds__(256, (K * ORDER > 9 ? 1 : 2)) transform_kernel(const TransformParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* vals = (double*)smem_raw;                       // nacc
     double* scratch = vals + (2 + p.m * (1 + 3 * ORDER));   // warps x per-lane values, reused
+    double* qs = scratch + 32 * (blockDim.x >> 5);          // (32 K) x FN_MAXC design basis, zero padded
     const int m = p.m, c = p.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const double inv_l = 1.0 / (ORDER * 0.6931471805599453094);
 
-    double a[K][ORDER], qrow[K][FN_MAXC];
+    for (int e = threadIdx.x; e < 32 * K * FN_MAXC; e += blockDim.x) {
+        const int j = e / FN_MAXC, t = e % FN_MAXC;
+        qs[e] = (j < m && t < c) ? p.q[j * c + t] : 0.0;
+    }
+    __syncthreads();
+    double a[K][ORDER];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int j = lane + 32 * k;
 #pragma unroll
         for (int i = 0; i < ORDER; ++i) a[k][i] = j < m ? p.a[i * m + j] : 1.0;
-#pragma unroll
-        for (int t = 0; t < FN_MAXC; ++t) qrow[k][t] = (j < m && t < c) ? p.q[j * c + t] : 0.0;
     }
     double s[K], A[K][ORDER], B[K][ORDER], D[K][ORDER];
 #pragma unroll
@@ -72,8 +78,9 @@ __global__ void __launch_bounds__(256) transform_kernel(const TransformParams p)
             pinv[k] = 1.0 / poly;
             y[k] = j < m ? log(poly) * inv_l : 0.0;
             syy += y[k] * y[k];
+            const double* qr = qs + (size_t)j * FN_MAXC;
 #pragma unroll
-            for (int q = 0; q < FN_MAXC; ++q) t[q] += qrow[k][q] * y[k];
+            for (int q = 0; q < FN_MAXC; ++q) if (q < c) t[q] += qr[q] * y[k];
         }
 #pragma unroll
         for (int q = 0; q < FN_MAXC; ++q) {
@@ -86,8 +93,9 @@ __global__ void __launch_bounds__(256) transform_kernel(const TransformParams p)
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             double proj = 0.0;                 // (Q Q' y_g)_j
+            const double* qr = qs + (size_t)(lane + 32 * k) * FN_MAXC;
 #pragma unroll
-            for (int q = 0; q < FN_MAXC; ++q) proj += qrow[k][q] * t[q];
+            for (int q = 0; q < FN_MAXC; ++q) if (q < c) proj += qr[q] * t[q];
             s[k] += y[k];
             double w = pinv[k] * inv_l;        // i = ORDER-1: x^0
 #pragma unroll
