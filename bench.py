@@ -352,18 +352,21 @@ def run_gpu(args):
         fit_test = None
         if world == 1 and not os.environ.get("FN_BENCH_SKIP_FIT"):
             engine.close()
-            t0 = time.perf_counter()
-            fitted = fitnoise.Model_independent().fit(y_np, design)
-            tested = fitted.test(coef=[1])
-            t_ind = time.perf_counter() - t0
-            n_sig = int((tested.q_values < 0.01).sum())
-            fitted._session.close()
+            t_ind = []
+            for _ in range(2):          # first call allocates the pooled engine's buffers; second is warm
+                t0 = time.perf_counter()
+                fitted = fitnoise.Model_independent().fit(y_np, design)
+                tested = fitted.test(coef=[1])
+                t_ind.append(time.perf_counter() - t0)
+                n_sig = int((tested.q_values < 0.01).sum())
+                fitted._session.close()
             t0 = time.perf_counter()
             fitted_t = fitnoise.Model_t().fit(y_np, design)
             tested_t = fitted_t.test(coef=[1])
             t_t = time.perf_counter() - t0
             fit_test = {
-                "Model_independent_fit_test_wall_s": t_ind, "q_lt_0.01": n_sig,
+                "Model_independent_fit_test_wall_s": t_ind[1], "Model_independent_first_call_wall_s": t_ind[0],
+                "q_lt_0.01": n_sig,
                 "Model_t_fit_test_wall_s": t_t, "Model_t_evaluations": int(fitted_t._evaluations),
                 "Model_t_df": float(fitted_t.param.df), "Model_t_sd": float(np.sqrt(fitted_t.param.variance)),
                 "includes": "H2D of y (768 MB) from pinned host memory, preparation, optimiser, noise "

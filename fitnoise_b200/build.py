@@ -1,21 +1,31 @@
-"""Build libfitnoise_b200.so (sm_100a) in-tree with nvcc.  Used by __graft_entry__.build()."""
+"""Build libfitnoise_b200.so (sm_100a) in-tree with nvcc.  Used by __graft_entry__.build().
+
+The per-gene kernels are templates over the design width; each width is its own translation unit
+(csrc/fn_width.cu with -DFN_W=<width>), compiled in parallel with csrc/fn_api.cu and linked into one
+shared library.  `nvcc -DFN_SINGLE_TU ... fn_api.cu` builds the same library from one command.
+"""
 import os
+import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libfitnoise_b200.so")
 
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
+WIDTHS = (1, 2, 3, 4, 6, 8, 12, 16)         # fn_host.hpp round_width()
+
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
-    "--cudart", "static",
+    "-Xcompiler", "-fPIC",
     "-diag-suppress", "550",
 ]
+LINK_FLAGS = ["-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def sources():
@@ -35,14 +45,27 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "fn_api.cu")]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    jobs = []
+    for w in sorted(WIDTHS, reverse=True):          # widest first: they take longest
+        jobs.append([nvcc] + NVCC_FLAGS + extra + ["-DFN_W=%d" % w, "-c", os.path.join(CSRC, "fn_width.cu"),
+                                                   "-o", os.path.join(OBJ_DIR, "fn_width_%d.o" % w)])
+
+    def run(cmd):
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
+        return proc.stderr
+
+    jobs.insert(1, [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, "fn_api.cu"), "-o", os.path.join(OBJ_DIR, "fn_api.o")])
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        logs = list(pool.map(run, jobs))
+    objs = [c[-1] for c in jobs]
+    log = run([nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + objs)
+    shutil.rmtree(OBJ_DIR, ignore_errors=True)     # only the .so travels to the GPU box
     if verbose:
-        sys.stderr.write(proc.stderr)
+        sys.stderr.write("".join(logs) + log)
     return LIB_PATH
 
 

@@ -22,6 +22,54 @@
 
 using namespace fn;
 
+// per-width kernel tables (fn_width_inst.cuh)
+#ifdef FN_SINGLE_TU
+#define FN_W 1
+#include "fn_width_inst.cuh"
+#undef FN_W
+#define FN_W 2
+#include "fn_width_inst.cuh"
+#undef FN_W
+#define FN_W 3
+#include "fn_width_inst.cuh"
+#undef FN_W
+#define FN_W 4
+#include "fn_width_inst.cuh"
+#undef FN_W
+#define FN_W 6
+#include "fn_width_inst.cuh"
+#undef FN_W
+#define FN_W 8
+#include "fn_width_inst.cuh"
+#undef FN_W
+#define FN_W 12
+#include "fn_width_inst.cuh"
+#undef FN_W
+#define FN_W 16
+#include "fn_width_inst.cuh"
+#undef FN_W
+#else
+namespace fn {
+const KernelSet* kernel_set_w1(); const KernelSet* kernel_set_w2(); const KernelSet* kernel_set_w3();
+const KernelSet* kernel_set_w4(); const KernelSet* kernel_set_w6(); const KernelSet* kernel_set_w8();
+const KernelSet* kernel_set_w12(); const KernelSet* kernel_set_w16();
+}
+#endif
+
+static const KernelSet* kernel_set(int width) {
+    switch (width) {
+        case 1: return kernel_set_w1();
+        case 2: return kernel_set_w2();
+        case 3: return kernel_set_w3();
+        case 4: return kernel_set_w4();
+        case 6: return kernel_set_w6();
+        case 8: return kernel_set_w8();
+        case 12: return kernel_set_w12();
+        case 16: return kernel_set_w16();
+        default: return nullptr;
+    }
+}
+
 static thread_local std::string g_error;
 
 static int fail(int code, const char* fmt, ...) {
@@ -328,8 +376,18 @@ static int set_smem(fn_handle* h, K kernel, size_t bytes) {
     const std::pair<int, const void*> key(h->device, (const void*)kernel);
     auto it = g_smem_set.find(key);
     if (it != g_smem_set.end() && it->second >= bytes) return 0;
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     g_smem_set[key] = bytes;
+    return 0;
+}
+
+// launch one of the per-width kernels (all take their parameter block by value as the only argument)
+static int launch_width_kernel(fn_handle* h, const void* kernel, int grid, int threads, size_t smem, void* params) {
+    if (!kernel) return fail(FN_ERR_UNSUPPORTED, "no kernel for this design width");
+    int rc = set_smem(h, kernel, smem);
+    if (rc) return rc;
+    void* args[] = {params};
+    CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), args, smem, h->stream));
     return 0;
 }
 
@@ -635,11 +693,11 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     pp.xn = h->xn; pp.xc = h->xc; pp.c_noise = c_noise; pp.c_ctrl = c_ctrl;
     pp.status_out = h->status; pp.cst_out = h->cst; pp.avg_out = h->avg; pp.gs_out = h->gs;
     fill_reduce(h, pp.gr, PREP_NACC, -1, 0.0, false);
-    FN_DISPATCH_WIDTH(width, {
-        rc = set_smem(h, prepare_kernel<C>, g.smem);
+    {
+        const KernelSet* ks = kernel_set(width);
+        rc = launch_width_kernel(h, ks ? ks->prepare : nullptr, g.grid, g.threads, g.smem, &pp);
         if (rc) return rc;
-        prepare_kernel<C><<<g.grid, g.threads, g.smem, h->stream>>>(pp);
-    });
+    }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     if (patseq) {
@@ -741,21 +799,11 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     ep.pg_p = per_gene ? h->pg_p : nullptr;
     fill_reduce(h, ep.gr, nacc, per_gene ? -1 : ACC_VALUE, per_gene ? 0.0 : 0.5 * h->cst_sum, exchange);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    FN_DISPATCH_WIDTH(h->width, {
-        if (h->fam.kind == KIND_SCALE1) {
-            rc = set_smem(h, eval_kernel<C, KIND_SCALE1>, g.smem);
-            if (rc) return rc;
-            eval_kernel<C, KIND_SCALE1><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
-        } else if (h->fam.kind == KIND_SCALE_PS) {
-            rc = set_smem(h, eval_kernel<C, KIND_SCALE_PS>, g.smem);
-            if (rc) return rc;
-            eval_kernel<C, KIND_SCALE_PS><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
-        } else {
-            rc = set_smem(h, eval_kernel<C, KIND_PATSEQ>, g.smem);
-            if (rc) return rc;
-            eval_kernel<C, KIND_PATSEQ><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
-        }
-    });
+    {
+        const KernelSet* ks = kernel_set(h->width);
+        rc = launch_width_kernel(h, ks ? ks->eval[h->fam.kind] : nullptr, g.grid, g.threads, g.smem, &ep);
+        if (rc) return rc;
+    }
     if (h->timing) { CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->timing_pending = true; }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
@@ -820,11 +868,11 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
     ep.pg_p = per_gene ? h->pg_p : nullptr;
     fill_reduce(h, ep.gr, nacc, per_gene ? -1 : ACC_VALUE, per_gene ? 0.0 : 0.5 * h->cst_sum, exchange);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    FN_DISPATCH_WIDTH(h->width, {
-        rc = set_smem(h, eval_factors_kernel<C>, g.smem);
+    {
+        const KernelSet* ks = kernel_set(h->width);
+        rc = launch_width_kernel(h, ks ? ks->eval_factors : nullptr, g.grid, g.threads, g.smem, &ep);
         if (rc) return rc;
-        eval_factors_kernel<C><<<g.grid, g.threads, g.smem, h->stream>>>(ep);
-    });
+    }
     if (h->timing) { CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->timing_pending = true; }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
@@ -1041,11 +1089,11 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     cp.ta = h->fam.kind != KIND_SCALE1 ? h->tab_dev : nullptr;
     cp.tb = h->fam.kind != KIND_SCALE1 ? h->tab_dev + m : nullptr;
     cp.coef = h->coef; cp.covar = h->covar; cp.dfpost = h->dfpost;
-    FN_DISPATCH_WIDTH(d.width, {
-        rc = set_smem(h, coef_kernel<C>, g.smem);
+    {
+        const KernelSet* ks = kernel_set(d.width);
+        rc = launch_width_kernel(h, ks ? ks->coef : nullptr, g.grid, g.threads, g.smem, &cp);
         if (rc) return rc;
-        coef_kernel<C><<<g.grid, g.threads, g.smem, h->stream>>>(cp);
-    });
+    }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     if (coef) D2H_TRY(coef, h->coef, (size_t)h->n * c * sizeof(double));
@@ -1333,7 +1381,7 @@ extern "C" int fn_transform_upload(fn_handle* h, int64_t n, int32_t m, const dou
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
     if (n < 0 || m < 1 || (!x && n > 0)) return fail(FN_ERR_ARG, "fn_transform_upload: bad arguments");
     if (m > 256) return fail(FN_ERR_UNSUPPORTED, "transform supports m <= 256 (m = %d)", m);
-    if (c < 1 || c > FN_MAXC || !design) return fail(FN_ERR_UNSUPPORTED, "design has %d columns; 1..%d supported", c, FN_MAXC);
+    if (c < 1 || c > TR_MAXC || !design) return fail(FN_ERR_UNSUPPORTED, "design has %d columns; 1..%d supported", c, TR_MAXC);
     Design d;
     if (!d.build(m, c, design)) return fail(FN_ERR_ARG, "design (%d x %d) is rank deficient", m, c);
     CUDA_TRY(cudaSetDevice(h->device));
@@ -1391,7 +1439,7 @@ extern "C" int fn_transform_sums(fn_handle* h, int32_t order, const double* a, d
     fill_reduce(h, tp.gr, nacc, -1, 0.0, false);
     int k = (m + 31) / 32;
     if (k > 4) k = 8;
-    const size_t smem = ((size_t)nacc + 32 * nwarp + 32 * k * FN_MAXC) * sizeof(double);
+    const size_t smem = ((size_t)nacc + 32 * nwarp + 32 * k * TR_MAXC) * sizeof(double);
     FN_DISPATCH_TRANSFORM(k, order, {
         rc = set_smem(h, transform_kernel<K, ORDER>, smem);
         if (rc) return rc;

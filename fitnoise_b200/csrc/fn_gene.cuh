@@ -260,23 +260,23 @@ FN_HD double leverage(const double* l, const double* x) {
 template <int C>
 FN_HD void chol_inverse(const double* l, double* ainv) {
     double li[Tri<C>::N];           // L^-1, lower triangular
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
     for (int j = 0; j < C; ++j) {
         li[FN_TRI(j, j)] = l[FN_TRI(j, j)];
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
         for (int i = j + 1; i < C; ++i) {
             double s = 0.0;
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
             for (int t = j; t < i; ++t) s -= l[FN_TRI(i, t)] * li[FN_TRI(t, j)];
             li[FN_TRI(i, j)] = s * l[FN_TRI(i, i)];
         }
     }
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
     for (int i = 0; i < C; ++i)
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
         for (int j = 0; j <= i; ++j) {
             double s = 0.0;
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
             for (int t = i; t < C; ++t) s += li[FN_TRI(t, i)] * li[FN_TRI(t, j)];
             ainv[FN_TRI(i, j)] = s;
         }
@@ -942,7 +942,7 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
 // ------------------------------------------------------------------------------------------
 // K3b: contrasts and their test (Model.test, fitnoise.py:368-396; Mv*.p_value distributions.py:52-57,150-155)
 // ------------------------------------------------------------------------------------------
-#define FN_MAXC 8
+#define FN_MAXC 16
 
 // coef (c), V (c x c, row-major), df.  contrasts is c x kc row-major.  Writes contrasted (kc),
 // optionally the kc x kc covariance C'VC, and the p-value of contrasted == 0.

@@ -11,7 +11,7 @@ namespace fn {
 // The template widths the kernels are instantiated for; a design with c columns runs in the
 // next width up, its extra columns zero (Normal<C>::pad makes that exact).
 inline int round_width(int c) {
-    static const int widths[] = {1, 2, 3, 4, 6, 8};
+    static const int widths[] = {1, 2, 3, 4, 6, 8, 12, 16};
     for (int w : widths) if (c <= w) return w;
     return -1;
 }
@@ -121,5 +121,7 @@ inline bool family_valid(const Family& f, int m, bool has_aux) {
         case 4: { constexpr int C = 4; __VA_ARGS__; } break;        \
         case 6: { constexpr int C = 6; __VA_ARGS__; } break;        \
         case 8: { constexpr int C = 8; __VA_ARGS__; } break;        \
+        case 12: { constexpr int C = 12; __VA_ARGS__; } break;      \
+        case 16: { constexpr int C = 16; __VA_ARGS__; } break;      \
         default: break;                                             \
     }

@@ -13,13 +13,23 @@ namespace fn {
 
 #ifdef FN_TRACE
 // Development-only phase timestamps (globaltimer ns) of CTA 0 and of the last CTA; see tools/micro.
-__device__ unsigned long long g_trace[64];
+static __device__ unsigned long long g_trace[64];
 #define FN_STAMP(slot) do { if (threadIdx.x == 0 && (blockIdx.x == 0)) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_trace[slot] = t__; } } while (0)
 #define FN_STAMP_ANY(slot) do { if (threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_trace[slot] = t__; } } while (0)
 #else
 #define FN_STAMP(slot) do { } while (0)
 #define FN_STAMP_ANY(slot) do { } while (0)
 #endif
+
+// The per-gene kernels are templates over the design width C.  Every width is instantiated in its
+// own translation unit (fn_width.cu, compiled with -DFN_W=<width>) so that the widths build in
+// parallel; the C-ABI layer launches them through this table (cudaLaunchKernel).
+struct KernelSet {
+    const void* prepare;          // prepare_kernel<C>
+    const void* eval[3];          // eval_kernel<C, KIND_SCALE1 | KIND_SCALE_PS | KIND_PATSEQ>
+    const void* eval_factors;     // eval_factors_kernel<C>
+    const void* coef;             // coef_kernel<C>
+};
 
 // accumulator layout of one CTA's partial sums
 enum { ACC_VALUE = 0, ACC_DV = 1, ACC_GA = 2, ACC_GB = 3, ACC_USED = 4, ACC_BAD = 5, ACC_FIXED = 6 };
@@ -296,12 +306,14 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
     grid_reduce(p.gr, red_out);
 }
 
+#ifndef FN_WIDTH_ONLY
 // PATSEQ: raw counts -> rc = 1/max(count, 1)   (fitnoise.py:648,749)
 __global__ void counts_to_rc_kernel(double* aux, long long total) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
         aux[i] = 1.0 / fmax(aux[i], 1.0);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // K2 -log likelihood + gradient
@@ -551,6 +563,7 @@ __global__ void __launch_bounds__(256) eval_factors_kernel(const EvalFactorsPara
     grid_reduce(p.gr, vals);
 }
 
+#ifndef FN_WIDTH_ONLY
 // noise p-values from (d2, p): Mvt.p_value F sf (distributions.py:150-155) / Mvnormal chi2 sf (:52-57)
 __global__ void noise_p_kernel(long long n, const double* d2, const int* pdf, int is_t, double v, double* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -560,6 +573,7 @@ __global__ void noise_p_kernel(long long n, const double* d2, const int* pdf, in
     if (!(d == d) || p <= 0) { out[i] = NAN; return; }
     out[i] = is_t ? f_sf(d / p, (double)p, v) : chi2_sf(d, (double)p);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // K3 coefficients
@@ -623,8 +637,9 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
         const double s2 = p.is_t ? (p.v + co.d2) / (p.v + co.p2) : 1.0;
         p.dfpost[gene] = p.is_t ? p.v + co.p2 : NAN;
         // back to the user's basis: coef = Rinv beta,  V = Rinv Ainv Rinv' s2
+        // (wide designs keep the outer loops rolled: C^3 terms unrolled cost minutes of compile time)
         double tmp[C * C];
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
         for (int i = 0; i < C; ++i) {
             if (i < c) {
                 double a = 0.0;
@@ -632,7 +647,7 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
                 for (int t = 0; t < C; ++t) if (t >= i && t < c) a += rinv[i * c + t] * beta[t];
                 cf[i] = a;
             }
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
             for (int j = 0; j < C; ++j) {
                 double a = 0.0;
 #pragma unroll
@@ -641,9 +656,9 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
                 tmp[i * C + j] = a;
             }
         }
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
         for (int i = 0; i < C; ++i)
-#pragma unroll
+#pragma unroll (C > 8 ? 1 : C)
             for (int j = 0; j < C; ++j) {
                 if (i < c && j < c) {
                     double a = 0.0;
@@ -668,6 +683,7 @@ struct TestParams {
     double* pval;                // n
 };
 
+#ifndef FN_WIDTH_ONLY
 __global__ void test_kernel(const TestParams p) {
     __shared__ double cm[FN_MAXC * FN_MAXC];
     for (int i = threadIdx.x; i < p.c * p.kc; i += blockDim.x) cm[i] = p.contrasts[i];
@@ -687,6 +703,7 @@ __global__ void test_kernel(const TestParams p) {
               p.ccov ? p.ccov + g * p.kc * p.kc : nullptr, pv);
     p.pval[g] = pv;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // get_weights: 1/sigma2 per observation (fitnoise.py:399-404); inf/NaN exactly where the reference's are
@@ -701,6 +718,7 @@ struct WeightParams {
     double* out;
 };
 
+#ifndef FN_WIDTH_ONLY
 __global__ void weights_kernel(const WeightParams p) {
     const long long total = p.n * p.m;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -723,5 +741,6 @@ __global__ void weights_kernel(const WeightParams p) {
         p.out[i] = w;
     }
 }
+#endif
 
 }  // namespace fn

@@ -12,7 +12,7 @@
 
 #if defined(__CUDACC__)
 #define FN_HD __host__ __device__ __forceinline__
-#define FN_HDN __host__ __device__ __noinline__
+#define FN_HDN inline __host__ __device__ __noinline__
 #else
 #define FN_HD inline
 #define FN_HDN inline

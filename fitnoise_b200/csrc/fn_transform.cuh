@@ -20,6 +20,7 @@
 namespace fn {
 
 #define TR_MAX_ORDER 3
+#define TR_MAXC 8             // design columns of the transform objective
 
 struct TransformParams {
     long long n;
@@ -36,13 +37,13 @@ __global__ void __launch_bounds__(256, (K * ORDER > 9 ? 1 : 2)) transform_kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* vals = (double*)smem_raw;                       // nacc
     double* scratch = vals + (2 + p.m * (1 + 3 * ORDER));   // warps x per-lane values, reused
-    double* qs = scratch + 32 * (blockDim.x >> 5);          // (32 K) x FN_MAXC design basis, zero padded
+    double* qs = scratch + 32 * (blockDim.x >> 5);          // (32 K) x TR_MAXC design basis, zero padded
     const int m = p.m, c = p.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const double inv_l = 1.0 / (ORDER * 0.6931471805599453094);
 
-    for (int e = threadIdx.x; e < 32 * K * FN_MAXC; e += blockDim.x) {
-        const int j = e / FN_MAXC, t = e % FN_MAXC;
+    for (int e = threadIdx.x; e < 32 * K * TR_MAXC; e += blockDim.x) {
+        const int j = e / TR_MAXC, t = e % TR_MAXC;
         qs[e] = (j < m && t < c) ? p.q[j * c + t] : 0.0;
     }
     __syncthreads();
@@ -65,9 +66,9 @@ __global__ void __launch_bounds__(256, (K * ORDER > 9 ? 1 : 2)) transform_kernel
     const long long gwarp = (long long)blockIdx.x * nwarp + warp, stride = (long long)gridDim.x * nwarp;
     for (long long g = gwarp; g < p.n; g += stride) {
         double x[K], y[K], pinv[K];
-        double t[FN_MAXC];
+        double t[TR_MAXC];
 #pragma unroll
-        for (int q = 0; q < FN_MAXC; ++q) t[q] = 0.0;
+        for (int q = 0; q < TR_MAXC; ++q) t[q] = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j = lane + 32 * k;
@@ -78,12 +79,12 @@ __global__ void __launch_bounds__(256, (K * ORDER > 9 ? 1 : 2)) transform_kernel
             pinv[k] = 1.0 / poly;
             y[k] = j < m ? log(poly) * inv_l : 0.0;
             syy += y[k] * y[k];
-            const double* qr = qs + (size_t)j * FN_MAXC;
+            const double* qr = qs + (size_t)j * TR_MAXC;
 #pragma unroll
-            for (int q = 0; q < FN_MAXC; ++q) if (q < c) t[q] += qr[q] * y[k];
+            for (int q = 0; q < TR_MAXC; ++q) if (q < c) t[q] += qr[q] * y[k];
         }
 #pragma unroll
-        for (int q = 0; q < FN_MAXC; ++q) {
+        for (int q = 0; q < TR_MAXC; ++q) {
             if (q < c) {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], off);
@@ -93,9 +94,9 @@ __global__ void __launch_bounds__(256, (K * ORDER > 9 ? 1 : 2)) transform_kernel
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             double proj = 0.0;                 // (Q Q' y_g)_j
-            const double* qr = qs + (size_t)(lane + 32 * k) * FN_MAXC;
+            const double* qr = qs + (size_t)(lane + 32 * k) * TR_MAXC;
 #pragma unroll
-            for (int q = 0; q < FN_MAXC; ++q) if (q < c) proj += qr[q] * t[q];
+            for (int q = 0; q < TR_MAXC; ++q) if (q < c) proj += qr[q] * t[q];
             s[k] += y[k];
             double w = pinv[k] * inv_l;        // i = ORDER-1: x^0
 #pragma unroll

@@ -68,7 +68,7 @@ int fn_synchronize(fn_handle* h);
  * loop of _fit_noise (fitnoise.py:211-233, 23-35) and Model_*._configured (fitnoise.py:538-552 ...
  * 843-861).  y: n x m.  aux: n x m precision WEIGHTS (SCALE kinds; w = 0 or NaN drops the
  * observation) or read COUNTS (PATSEQ), or NULL.  controls: n bytes (non-zero = control gene,
- * fitted with design_ctrl) or NULL.  Designs are m x c row-major, c <= 8, full column rank. */
+ * fitted with design_ctrl) or NULL.  Designs are m x c row-major, c <= 16 (c + n_factors <= 16), full column rank. */
 int fn_upload(fn_handle* h, int64_t n, int32_t m, const double* y, const double* aux,
               const fn_family* family, const uint8_t* controls,
               int32_t c_noise, const double* design_noise,

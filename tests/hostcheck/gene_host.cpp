@@ -156,7 +156,7 @@ int hc_coef(const Family* fam, long n, int m, const double* y, const double* aux
         for (int j = 0; j < m; ++j) { row[j] = y[g * m + j]; if (aux_raw) arow[j] = pr.aux[g * m + j]; }
         GeneView gv; gv.y = row.data(); gv.aux = aux_raw ? arow.data() : nullptr; gv.gs = pr.gs[g];
         gv.setup(m, 0, 1, 0);
-        double beta[8], ainv[36];
+        double beta[FN_MAXC], ainv[FN_MAXC * (FN_MAXC + 1) / 2];
         CoefOut co;
         FN_DISPATCH_WIDTH(d.width, coef_gene<C>(ec, gv, d.q.data(), d.c, nf, beta, ainv, co));
         double* cf = coef + g * c; double* cv = covar + g * c * c;
@@ -174,7 +174,7 @@ int hc_coef(const Family* fam, long n, int m, const double* y, const double* aux
             for (int t = i; t < c; ++t) acc += d.rinv[i * c + t] * beta[t];
             cf[i] = acc;
         }
-        double tmp[64];
+        double tmp[FN_MAXC * FN_MAXC];
         for (int i = 0; i < c; ++i) for (int j = 0; j < c; ++j) {
             double acc = 0.0;
             for (int t = i; t < c; ++t) { const int hi = t > j ? t : j, lo = t > j ? j : t; acc += d.rinv[i * c + t] * ainv[FN_TRI(hi, lo)]; }

@@ -254,7 +254,7 @@ def _random_case(rng, n, m, c, model):
 
 
 SHAPES = [(1, 3, 1), (17, 1, 1), (5, 2, 2), (300, 5, 3), (1025, 7, 4), (333, 16, 5), (257, 33, 6),
-          (200, 48, 8), (64, 100, 2), (40, 250, 3), (2049, 12, 7)]
+          (200, 48, 8), (64, 100, 2), (40, 250, 3), (2049, 12, 7), (150, 40, 10), (99, 24, 12), (130, 64, 16)]
 SHAPE_MODELS = ["Model_t", "Model_normal", "Model_independent", "Model_t_per_sample", "Model_t_patseq",
                 "Model_t_v1_patseq", "Model_normal_patseq_v3", "Model_t_patseq_per_sample",
                 "Model_t_patseq_v1_per_sample"]
@@ -262,7 +262,7 @@ SHAPE_MODELS = ["Model_t", "Model_normal", "Model_independent", "Model_t_per_sam
 
 @pytest.mark.parametrize("model", SHAPE_MODELS)
 def test_shapes_against_host_build(model):
-    """Every kernel over odd shapes (n = 1 ... 2049, m = 1 ... 250, c = 1 ... 8, ~5 % missing, zero
+    """Every kernel over odd shapes (n = 1 ... 2049, m = 1 ... 250, c = 1 ... 16, ~5 % missing, zero
     weights): the CUDA result against the host build of the same arithmetic (tests/hostcheck),
     which test_host_math.py pins to the reference goldens."""
     import hostcheck

@@ -108,6 +108,39 @@ def test_blocked_sample_order(model):
     assert_close(fitted.coef, ref["coef"], 1e-9, atol=1e-10)
 
 
+@pytest.mark.parametrize("c", [9, 12, 16])
+def test_wide_designs(c):
+    """Designs with 9 ... 16 columns run in the template widths 12 and 16."""
+    from oracle import fitnoise_oracle as oracle
+    from conftest import assert_close
+    import fitnoise_b200 as fitnoise
+    rng = np.random.default_rng(100 + c)
+    n, m = 25, 40
+    design = np.column_stack([np.ones(m), (np.arange(m) % 2) * 1.0, rng.normal(size=(m, c - 2))])
+    y = rng.normal(size=(n, m)) * 1.2 + 8.0
+    weights = np.exp(rng.normal(0, 0.3, size=(n, m)))
+    weights[rng.random((n, m)) < 0.05] = 0.0
+    theta = [6.0, 1.4]
+    contrasts = np.zeros((c, 3))
+    contrasts[1, 0] = 1.0; contrasts[c - 1, 1] = 1.0; contrasts[2, 2] = 1.0; contrasts[c - 2, 2] = -1.0
+    fitted = fitnoise.Model_t()._with(_engine_factory=hostcheck.HostEvaluator).fit(
+        fitnoise.Dataset(y, {"weights": weights}), design, force_param=theta)
+    tested = fitted.test(contrasts=contrasts)
+    ref = oracle.fit_and_test("Model_t", y, design, {"weights": weights}, contrasts=contrasts, force_param=theta)
+    score, d2, p = fitted._session.per_gene(fitted._theta)
+    want = np.full(n, np.nan)
+    for row, item in ref["prepared"].items():
+        want[row] = oracle.score_row(ref["cfg"], np.asarray(theta), row, *item)
+    assert_close(score, want, 1e-9, what="score")
+    value, grad, used, bad = fitted._objective(theta)
+    ov, og = oracle.total_score_grad(ref["cfg"], ref["prepared"], np.asarray(theta))
+    assert_close(value, ov, 1e-11)
+    assert_close(grad, og, 1e-8, atol=1e-9 * abs(ov))
+    assert_close(fitted.coef, ref["coef"], 1e-8, atol=1e-9)
+    assert_close(tested.p_values, ref["p_values"], 1e-8)
+    assert_close(tested.q_values, ref["q_values"], 1e-8)
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_objective_and_gradient_match_oracle(name):
     """Packed-theta objective (incl. the factor penalty and the chain rule through Q2) against the

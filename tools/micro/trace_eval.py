@@ -1,6 +1,6 @@
 """Phase timestamps inside the nll+grad kernel (development build with -DFN_TRACE).
 
-    nvcc ... -DFN_TRACE -o tools/micro/libfn_trace.so fitnoise_b200/csrc/fn_api.cu
+    nvcc ... -DFN_TRACE -DFN_SINGLE_TU -o tools/micro/libfn_trace.so fitnoise_b200/csrc/fn_api.cu
     python tools/micro/trace_eval.py [n] [m]
 """
 import ctypes, os, sys, time
