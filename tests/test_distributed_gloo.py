@@ -120,6 +120,44 @@ def test_fewer_genes_than_ranks(tmp_path):
     assert r[0]["value"] == r[1]["value"]
 
 
+def _transform_case():
+    import fitnoise_b200 as fitnoise
+    import hostcheck
+    rng = np.random.default_rng(9)
+    n, m = 301, 6
+    group = (np.arange(m) >= 3) * 1.0
+    mu = np.exp(rng.normal(3.0, 1.2, size=(n, 1)))
+    x = rng.poisson(mu * np.exp(0.4 * group)[None, :]).astype(float)
+    design = np.stack([np.ones(m), group], axis=1)
+    fitted = fitnoise.Transform_polynomial(2)._with(_engine_factory=hostcheck.HostEvaluator).fit(x, design)
+    return dict(y=fitted.y, pack=np.asarray(fitted.optimization_result.x), fun=fitted.optimization_result.fun)
+
+
+def _transform_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        np.save(os.path.join(out_dir, "tr%d.npy" % rank), _transform_case(), allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_transform_two_ranks(tmp_path):
+    """fitnoise.transform with the count matrix sharded over two ranks: the sums are all-reduced, so
+    both ranks follow the same optimiser path and gather the same transformed matrix."""
+    one = _transform_case()
+    port = _free_port()
+    mp.spawn(_transform_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(os.path.join(str(tmp_path), "tr%d.npy" % k), allow_pickle=True).item() for k in range(2)]
+    assert np.array_equal(r[0]["pack"], r[1]["pack"]) and np.array_equal(r[0]["y"], r[1]["y"])
+    assert r[0]["y"].shape == one["y"].shape
+    assert abs(r[0]["fun"] - one["fun"]) <= 1e-3 * abs(one["fun"])
+    assert np.corrcoef(r[0]["y"].reshape(-1), one["y"].reshape(-1))[0, 1] > 0.9999
+
+
 def test_shard_bounds():
     from fitnoise_b200 import parallel
     for n, w in [(10, 1), (10, 3), (7, 8), (1000001, 8), (0, 2)]:
