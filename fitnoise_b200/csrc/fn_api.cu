@@ -113,7 +113,8 @@ struct fn_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0;      // largest dynamic + static shared memory of one CTA
+    size_t smem_sm = 0;         // shared memory of one SM
 
     int64_t n = 0, n_pad = 0;
     int m = 0;
@@ -255,6 +256,7 @@ extern "C" int fn_create(int device, void* stream, fn_handle** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->smem_sm = prop.sharedMemPerMultiprocessor;
     if (stream) {
         h->stream = (cudaStream_t)stream;
     } else {
@@ -329,7 +331,11 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     // small problems: more, smaller CTAs so that every SM gets work
     if (h->tune_threads == 0 && h->n < (int64_t)h->sm_count * 256) threads = 128;
     if (threads < min_threads) threads = 256;      // per-sample column sums need one thread per sample
-    const size_t budget = (h->smem_optin - 2048) / ctas;       // per CTA
+    // The kernels hold up to 4.7 KB of static shared memory (reduction scratch, mbarriers) and the
+    // system reserves 1 KB per CTA: leave room for both, or fewer CTAs than planned fit on an SM
+    // (and a CTA at the very limit fails to launch).
+    const size_t static_reserve = 6 * 1024;
+    const size_t budget = h->smem_sm / ctas - static_reserve;   // dynamic bytes per CTA
     const size_t stage_target = 50 * 1024;
     int lpg = h->tune_lpg > 0 ? h->tune_lpg : 1;
     if (h->tune_lpg == 0) {
@@ -341,7 +347,7 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     const int genes = threads / lpg;
     const size_t stage = tile_stage_bytes(genes, m, aux, gs, cst);
     const size_t fixed = table_bytes + 256 + (size_t)genes * per_gene_extra;
-    if (fixed + stage > h->smem_optin - 1024)
+    if (fixed + stage > h->smem_optin - static_reserve)
         return fail(FN_ERR_UNSUPPORTED, "m = %d is too large for one tile stage in shared memory (%zu bytes)", m, fixed + stage);
     int stages = h->tune_stages > 0 ? h->tune_stages : 3;
     if (stages > FN_MAX_STAGES) stages = FN_MAX_STAGES;

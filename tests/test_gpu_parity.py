@@ -4,11 +4,13 @@ outputs (tests/golden) and with the oracle on seeded inputs.  Needs a B200: ``-m
 Tolerances (north_star): per-gene log-likelihood, coefficients and statistics 1e-9 relative;
 p-values 1e-8 relative; fitted hyper-parameters 1e-6 relative; BH bit-exact given p.
 """
+import os
+
 import numpy as np
 import pytest
 
 import fitnoise_b200 as fitnoise
-from conftest import assert_close, golden_context, golden_fit_kwargs, golden_names, load_golden
+from conftest import ROOT, assert_close, golden_context, golden_fit_kwargs, golden_names, load_golden
 from fitnoise_b200 import _native
 from helpers import check_against_golden, fit_golden, rank_deficient_rows, synthetic
 from oracle import fitnoise_oracle as oracle
@@ -254,7 +256,7 @@ def _random_case(rng, n, m, c, model):
 
 
 SHAPES = [(1, 3, 1), (17, 1, 1), (5, 2, 2), (300, 5, 3), (1025, 7, 4), (333, 16, 5), (257, 33, 6),
-          (200, 48, 8), (64, 100, 2), (40, 250, 3), (2049, 12, 7), (150, 40, 10), (99, 24, 12), (130, 64, 16)]
+          (200, 48, 8), (64, 100, 2), (40, 250, 3), (2049, 12, 7), (150, 40, 10), (99, 24, 12), (130, 64, 16), (20, 200, 16)]
 SHAPE_MODELS = ["Model_t", "Model_normal", "Model_independent", "Model_t_per_sample", "Model_t_patseq",
                 "Model_t_v1_patseq", "Model_normal_patseq_v3", "Model_t_patseq_per_sample",
                 "Model_t_patseq_v1_per_sample"]
@@ -308,6 +310,17 @@ def test_shapes_against_host_build(model):
             assert_close(e.weights(theta), host.weights(theta), 1e-12, what=what + " weights")
         finally:
             e.close()
+
+
+def test_random_sweep():
+    """A short run of tools/fuzz_parity.py: random models, shapes, missing rates, weights, control
+    genes and tile geometries against the host build (the long runs are kept in profiles/)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT, "tools", "fuzz_parity.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    done, skipped, failed = fuzz.run(60.0, 2024, max_cases=150)
+    assert failed == 0 and done - skipped >= 100
 
 
 def test_degenerate_inputs():

@@ -1,0 +1,148 @@
+"""Randomised parity sweep: CUDA kernels against the host build of the same arithmetic
+(tests/hostcheck, which the CPU suite pins to the reference goldens) over random shapes, models,
+missing-value rates, weights, controls and tile geometries, for a fixed time budget.
+
+    python tools/fuzz_parity.py [seconds] [seed]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import fitnoise_b200 as fitnoise  # noqa: E402
+from fitnoise_b200 import _native  # noqa: E402
+import hostcheck  # noqa: E402
+from conftest import assert_close  # noqa: E402
+from oracle import fitnoise_oracle as oracle  # noqa: E402
+
+MODELS = ["Model_t", "Model_normal", "Model_independent", "Model_t_per_sample", "Model_normal_per_sample",
+          "Model_t_patseq", "Model_t_patseq_v1", "Model_normal_patseq_v3", "Model_t_patseq_per_sample",
+          "Model_t_patseq_v1_per_sample"]
+
+
+def random_case(rng):
+    model = MODELS[rng.integers(len(MODELS))]
+    m = int(rng.choice([2, 3, 5, 6, 8, 11, 12, 16, 24, 31, 32, 48, 64, 96, 100, 128, 200]))
+    c = int(min(rng.choice([1, 2, 2, 3, 4, 5, 6, 8, 9, 12, 16]), max(1, m // 3)))     # keep the sub-designs well conditioned
+    n = int(rng.choice([1, 7, 63, 64, 65, 500, 1023, 3000, 20000]))
+    if m * n > 1.5e6:
+        n = int(1.5e6 // m)
+    design = np.concatenate([np.ones((m, 1)), rng.normal(size=(m, c - 1))], axis=1) if c > 1 else np.ones((m, 1))
+    missing = float(rng.choice([0.0, 0.0, 0.02, 0.15, 0.6]))
+    if missing > 0.5:
+        c = min(c, 3)            # k barely above c makes the sub-designs ill conditioned: not a parity question
+    y = rng.normal(size=(n, m)) * rng.uniform(0.5, 3.0) + rng.uniform(-5, 50)
+    y[rng.random((n, m)) < missing] = np.nan
+    fam = getattr(fitnoise, model)()._family(m)
+    aux = None
+    if fam.kind == _native.KIND_PATSEQ:
+        aux = rng.poisson(rng.uniform(2.0, 30.0), size=(n, m)).astype(float)
+        aux[np.isnan(y)] = 0
+        y[aux == 0] = np.nan
+        y = np.abs(y) + 1.0
+        theta = np.concatenate([[rng.uniform(2, 40)] if fam.dist == 1 else [], rng.uniform(50, 500, fam.na),
+                                rng.uniform(1e-3, 1e-2, fam.nb)])
+    else:
+        if rng.random() < 0.5:
+            aux = np.exp(rng.normal(0, 0.5, size=(n, m)))
+            aux[rng.random((n, m)) < 0.03] = 0.0
+        theta = np.concatenate([[rng.uniform(2, 40)] if fam.dist == 1 else [], rng.uniform(0.3, 3.0, fam.na)])
+    controls = None
+    control_design = None
+    if rng.random() < 0.3 and c > 1:
+        controls = rng.random(n) < 0.4
+        control_design = design[:, :-1]
+    tuning = None
+    if rng.random() < 0.4:
+        lpg = int(rng.choice([1, 2, 4, 8, 16]))
+        threads = int(rng.choice([128, 256]))
+        if (threads // lpg) % 16 == 0:
+            tuning = dict(lpg=lpg, threads=threads, stages=int(rng.integers(1, 5)), ctas_per_sm=int(rng.integers(1, 3)))
+    return dict(model=model, n=n, m=m, c=c, y=y, aux=aux, fam=fam, design=design, theta=theta,
+                controls=controls, control_design=control_design, tuning=tuning, missing=missing)
+
+
+def check(case):
+    what = "%(model)s n=%(n)d m=%(m)d c=%(c)d missing=%(missing)g tuning=%(tuning)s" % case
+    what += " aux=%s controls=%s" % (case["aux"] is not None, case["controls"] is not None)
+    host = hostcheck.HostEvaluator()
+    host.upload(case["y"], case["aux"], case["fam"], case["controls"], case["design"], case["control_design"])
+    e = _native.Engine(0)
+    try:
+        if case["tuning"]:
+            e.set_tuning(**case["tuning"])
+        try:
+            e.upload(case["y"], case["aux"], case["fam"], case["controls"], case["design"], case["control_design"])
+            gv, gg, gu, gb = e.nll_grad(case["theta"])
+        except _native.NativeError as err:
+            if case["tuning"] or "too large" in str(err) or "need m <=" in str(err):
+                return "skipped (%s): %s" % (err, what)          # geometry rejected: fine
+            raise
+        theta = case["theta"]
+        hs, hd, hp = host.per_gene(theta)
+        gs, gd, gp = e.per_gene(theta)
+        assert_close(gs, hs, 1e-9, what=what + " score")
+        assert np.array_equal(gp, hp), what
+        hv, hg, hu, _ = host.nll_grad(theta)
+        assert gu == hu, what + " used %d vs %d" % (gu, hu)
+        if hu:
+            assert_close(gv, hv, 1e-10, what=what + " value")
+            assert_close(gg, hg, 1e-7, atol=1e-9 * max(abs(hv), 1.0), what=what + " grad")
+        hn, ha = host.noise_stats(theta)
+        gn, ga = e.noise_stats(theta)
+        assert_close(gn, hn, 1e-8, what=what + " noise p")
+        assert_close(ga, ha, 1e-12, atol=1e-14, what=what + " averages")
+        hc, hcov, hdf = host.coef(theta, case["design"])
+        gc, gcov, gdf = e.coef(theta, case["design"])
+        assert_close(gc, hc, 1e-8, atol=1e-8, what=what + " coef")
+        assert_close(gcov, hcov, 1e-8, atol=1e-11, what=what + " covar")
+        assert_close(gdf, hdf, 1e-12, what=what + " df")
+        c = case["c"]
+        contrasts = np.eye(c)[:, : min(c, 2)]
+        hcon, _, hpv = host.test(contrasts)
+        gcon, gpv, gq = e.test_bh(contrasts)
+        assert_close(gcon, hcon, 1e-8, atol=1e-8, what=what + " contrasts")
+        assert_close(gpv, hpv, 1e-7, atol=1e-300, what=what + " p")
+        assert np.array_equal(gq, oracle.fdr(gpv)), what + " q"
+        assert_close(e.weights(theta), host.weights(theta), 1e-12, what=what + " weights")
+        return None
+    finally:
+        e.close()
+
+
+def run(budget, seed, max_cases=None):
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    done = skipped = failed = 0
+    while time.time() - t0 < budget and (max_cases is None or done < max_cases):
+        case = random_case(rng)
+        try:
+            msg = check(case)
+            if msg:
+                skipped += 1
+            done += 1
+        except AssertionError as err:
+            failed += 1
+            print("FAIL:", str(err)[:600], flush=True)
+        except Exception as err:
+            failed += 1
+            print("ERROR: %s: %s n=%d m=%d c=%d tuning=%s aux=%s controls=%s" % (
+                err, case["model"], case["n"], case["m"], case["c"], case["tuning"], case["aux"] is not None,
+                case["controls"] is not None), flush=True)
+    print("fuzz: %d cases, %d rejected geometries, %d failures, %.0f s, seed %d" % (done, skipped, failed, time.time() - t0, seed))
+    return done, skipped, failed
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    sys.exit(1 if run(budget, seed)[2] else 0)
+
+
+if __name__ == "__main__":
+    main()
