@@ -67,6 +67,75 @@ def random_case(rng):
                 controls=controls, control_design=control_design, tuning=tuning, missing=missing)
 
 
+def random_factor_case(rng):
+    """SCALE1 family with 1 ... 3 unknown factors (Model_*_factors): the augmented ridge system."""
+    model = ["Model_t_factors", "Model_normal_factors", "Model_independent_factors"][rng.integers(3)]
+    nf = int(rng.integers(1, 4))
+    m = int(rng.choice([6, 8, 12, 16, 24, 32, 48, 64, 80]))
+    c = int(min(rng.choice([1, 2, 3, 4, 6, 9, 12]), max(1, m // 3), 16 - nf))
+    n = int(rng.choice([1, 17, 64, 500, 3000, 20000]))
+    design = np.concatenate([np.ones((m, 1)), rng.normal(size=(m, c - 1))], axis=1) if c > 1 else np.ones((m, 1))
+    F = rng.normal(size=(m, nf)) * rng.uniform(0.2, 1.5)
+    y = rng.normal(size=(n, m)) + rng.normal(size=(n, nf)) @ F.T + rng.uniform(-3, 20)
+    missing = float(rng.choice([0.0, 0.03, 0.15]))
+    y[rng.random((n, m)) < missing] = np.nan
+    aux = None
+    if rng.random() < 0.5:
+        aux = np.exp(rng.normal(0, 0.4, size=(n, m)))
+        aux[rng.random((n, m)) < 0.02] = 0.0
+    fam = getattr(fitnoise, model)(nf)._family(m)
+    theta = np.concatenate([[rng.uniform(3, 30)] if fam.dist == 1 else [], rng.uniform(0.4, 2.5, fam.na)])
+    controls = control_design = None
+    if rng.random() < 0.3 and c > 1:
+        controls = rng.random(n) < 0.4
+        control_design = design[:, :-1]
+    tuning = None
+    if rng.random() < 0.4:
+        lpg = int(rng.choice([1, 2, 4, 8, 16]))
+        threads = int(rng.choice([128, 256]))
+        if (threads // lpg) % 16 == 0:
+            tuning = dict(lpg=lpg, threads=threads, stages=int(rng.integers(1, 5)), ctas_per_sm=int(rng.integers(1, 3)))
+    return dict(model=model, n=n, m=m, c=c, y=y, aux=aux, fam=fam, design=design, theta=theta, F=F, nf=nf,
+                controls=controls, control_design=control_design, tuning=tuning, missing=missing)
+
+
+def check_factors(case):
+    what = "%(model)s nf=%(nf)d n=%(n)d m=%(m)d c=%(c)d missing=%(missing)g tuning=%(tuning)s" % case
+    what += " aux=%s controls=%s" % (case["aux"] is not None, case["controls"] is not None)
+    theta, F = case["theta"], case["F"]
+    host = hostcheck.HostEvaluator()
+    host.upload(case["y"], case["aux"], case["fam"], case["controls"], case["design"], case["control_design"])
+    e = _native.Engine(0)
+    try:
+        if case["tuning"]:
+            e.set_tuning(**case["tuning"])
+        try:
+            e.upload(case["y"], case["aux"], case["fam"], case["controls"], case["design"], case["control_design"])
+            gv, gg, ggf, gu, gb = e.nll_grad_factors(theta, F)
+        except _native.NativeError as err:
+            if case["tuning"] or "too large" in str(err) or "<=" in str(err):
+                return "skipped (%s): %s" % (err, what)
+            raise
+        hv, hg, hgf, hu, _ = host.nll_grad_factors(theta, F)
+        assert gu == hu, what + " used %d vs %d" % (gu, hu)
+        if hu:
+            assert_close(gv, hv, 1e-10, what=what + " value")
+            assert_close(gg, hg, 1e-7, atol=1e-9 * max(abs(hv), 1.0), what=what + " grad")
+            assert_close(ggf, hgf, 1e-7, atol=1e-9 * max(abs(hv), 1.0), what=what + " grad factors")
+        hs, hd, hp = host.per_gene(theta)
+        gs, gd, gp = e.per_gene(theta)
+        assert_close(gs, hs, 1e-9, what=what + " score")
+        assert np.array_equal(gp, hp), what
+        hc, hcov, hdf = host.coef(theta, case["design"])
+        gc, gcov, gdf = e.coef(theta, case["design"])
+        assert_close(gc, hc, 1e-8, atol=1e-8, what=what + " coef")
+        assert_close(gcov, hcov, 1e-8, atol=1e-11, what=what + " covar")
+        assert_close(e.weights(theta), host.weights(theta), 1e-12, what=what + " weights")
+        return None
+    finally:
+        e.close()
+
+
 def check(case):
     what = "%(model)s n=%(n)d m=%(m)d c=%(c)d missing=%(missing)g tuning=%(tuning)s" % case
     what += " aux=%s controls=%s" % (case["aux"] is not None, case["controls"] is not None)
@@ -124,9 +193,10 @@ def run(budget, seed, max_cases=None):
     t0 = time.time()
     done = skipped = failed = 0
     while time.time() - t0 < budget and (max_cases is None or done < max_cases):
-        case = random_case(rng)
+        factors = rng.random() < 0.2
+        case = random_factor_case(rng) if factors else random_case(rng)
         try:
-            msg = check(case)
+            msg = check_factors(case) if factors else check(case)
             if msg:
                 skipped += 1
             done += 1
