@@ -323,8 +323,12 @@ extern "C" double fn_last_kernel_ms(fn_handle* h) {
 // ------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------
+// `one_big_stage`: the instruction-bound sweeps (weighted Model_normal/_t, unweighted per-sample
+// models) run 10-18 % faster with half the lanes per gene and ONE ~100 KB stage per CTA than with two
+// 50 KB stages: fewer lanes repeat the per-gene tail (reduction, factorisation, logarithm), and the
+// second CTA of the SM covers the load (measured: profiles/r01_sweep_weighted.log).
 static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_bytes, Geom& g, int min_threads = 0,
-                       size_t per_gene_extra = 0) {
+                       size_t per_gene_extra = 0, bool one_big_stage = false) {
     const int m = h->m;
     int ctas = h->tune_ctas > 0 ? h->tune_ctas : 2;
     int threads = h->tune_threads > 0 ? h->tune_threads : 256;
@@ -336,7 +340,8 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     // (and a CTA at the very limit fails to launch).
     const size_t static_reserve = 6 * 1024;
     const size_t budget = h->smem_sm / ctas - static_reserve;   // dynamic bytes per CTA
-    const size_t stage_target = 50 * 1024;
+    size_t stage_target = 50 * 1024;
+    if (one_big_stage && threads == 256 && budget > table_bytes + 256 + 64 * 1024) stage_target = budget - table_bytes - 256;
     int lpg = h->tune_lpg > 0 ? h->tune_lpg : 1;
     if (h->tune_lpg == 0) {
         while (lpg < 32 && threads / (lpg * 2) >= 16 &&
@@ -349,7 +354,7 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     const size_t fixed = table_bytes + 256 + (size_t)genes * per_gene_extra;
     if (fixed + stage > h->smem_optin - static_reserve)
         return fail(FN_ERR_UNSUPPORTED, "m = %d is too large for one tile stage in shared memory (%zu bytes)", m, fixed + stage);
-    int stages = h->tune_stages > 0 ? h->tune_stages : 3;
+    int stages = h->tune_stages > 0 ? h->tune_stages : ((one_big_stage && stage > 50 * 1024) ? 1 : 3);
     if (stages > FN_MAX_STAGES) stages = FN_MAX_STAGES;
     while (stages > 1 && fixed + (size_t)stages * stage > budget) --stages;
     if (fixed + (size_t)stages * stage > budget) ctas = 1;      // a single CTA per SM then
@@ -778,7 +783,8 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     const bool inplace = ia || ib;
     Geom g;
     const size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
-    int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0);
+    const bool one_big_stage = (h->fam.kind == KIND_SCALE1 && h->has_aux) || (h->fam.kind == KIND_SCALE_PS && !h->has_aux);
+    int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0, 0, one_big_stage);
     if (rc) return rc;
     if (inplace && m > g.threads) return fail(FN_ERR_UNSUPPORTED, "per-sample variance models need m <= threads per CTA (%d)", g.threads);
     const int nacc = eval_nacc(h);

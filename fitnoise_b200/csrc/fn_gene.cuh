@@ -53,6 +53,19 @@ FN_HD double lane_sum(double v, int lpg) {
 #endif
     return v;
 }
+// Sum N doubles over the lanes of a gene at once: one loop over the shuffle distances (the per-value
+// loops of lane_sum cost more in loop control than in shuffles when called seven times per gene).
+template <int N>
+FN_HD void lane_sum_n(double* v, int lpg) {
+#ifdef __CUDA_ARCH__
+    for (int off = lpg >> 1; off > 0; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    }
+#else
+    (void)v; (void)lpg;
+#endif
+}
 FN_HD int lane_sum_i(int v, int lpg) {
 #ifdef __CUDA_ARCH__
     for (int off = lpg >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -195,6 +208,15 @@ struct GeneView {
 template <int C> struct Tri { enum { N = C * (C + 1) / 2 }; };
 #define FN_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
+// 1/sqrt(x) for a positive pivot: the device's rsqrt (a few ulp) instead of a square root and a division.
+FN_HD double rsqrt_pos(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 // In-place Cholesky A = L L'.  On return a holds L below the diagonal and 1/L_ii on it;
 // det = prod of pivots (so ln det A = ln det).  Returns false when a pivot is <= rel_tol * A_ii.
 template <int C>
@@ -214,7 +236,7 @@ FN_HD bool chol(double* a, double& det, double rel_tol) {
                 const double orig = a[FN_TRI(i, i)];
                 if (!(s > rel_tol * orig) || !(s > 0.0)) { ok = false; s = 1.0; }
                 det *= s;
-                a[FN_TRI(i, i)] = 1.0 / sqrt(s);
+                a[FN_TRI(i, i)] = rsqrt_pos(s);
             }
         }
     }
@@ -308,12 +330,16 @@ struct Normal {
     }
     FN_HD void reduce(int lpg) {
         if (lpg == 1) return;
+#ifdef __CUDA_ARCH__
+        for (int off = lpg >> 1; off > 0; off >>= 1) {
 #pragma unroll
-        for (int i = 0; i < Tri<C>::N; ++i) a[i] = lane_sum(a[i], lpg);
+            for (int i = 0; i < Tri<C>::N; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], off);
 #pragma unroll
-        for (int i = 0; i < C; ++i) b[i] = lane_sum(b[i], lpg);
-        yy = lane_sum(yy, lpg);
-        k = lane_sum_i(k, lpg);
+            for (int i = 0; i < C; ++i) b[i] += __shfl_xor_sync(0xffffffffu, b[i], off);
+            yy += __shfl_xor_sync(0xffffffffu, yy, off);
+            k += __shfl_xor_sync(0xffffffffu, k, off);
+        }
+#endif
     }
     // columns c_real..C-1 of the design are zero padding: put 1 on their diagonal so that the
     // factorisation goes through with det and beta unchanged
@@ -513,7 +539,7 @@ FN_HD double finish_density(const EvalConst& ec, int p, double logdet, double d2
 // cost; they (and every weighted gene) take the masked sweep that also builds A.
 struct Scale1Mid {
     double d2;          // Mahalanobis distance at theta = 1
-    double logdet_a;    // ln det(X'WX) at theta = 1 (0 for a complete unweighted gene)
+    double det_a;       // det(X'WX) at theta = 1 (1 for a complete unweighted gene); its log is taken by scale1_finish
     int p;              // residual df
     int state;          // 0: gene not in the REML sum, 1: usable, 2: failed (non-finite)
 };
@@ -550,14 +576,19 @@ FN_HD void scale1_sweep(const EvalConst& ec, const GeneView& gv, const double* X
     if (has_aux || warp_any(eligible && !complete)) {
         Normal<C> nm;
         nm.init();
-        gv.for_each(eligible && !complete, [&](int j) {
+        // sigma2 = theta / w_prec at theta = 1: a sample counts when y is finite and its precision
+        // weight is neither 0 nor NaN (aux = 1/weights, fitnoise.py:540; Mv*.good)
+        auto visit = [&](int j) {
             const double y = gv.y[j];
-            const SampleVar sv = sample_var(ec, gv, j, y);
+            const double wp = has_aux ? gv.aux[j] : 1.0;
+            const bool valid = finite_d(y) && wp != 0.0 && wp == wp;
             double x[C];
             load_x<C>(X, j, x);
-            nm.add(sv.w, sv.valid ? y : 0.0, x);
-            nm.k += sv.valid ? 1 : 0;
-        });
+            nm.add(valid ? wp : 0.0, valid ? y : 0.0, x);
+            nm.k += valid ? 1 : 0;
+        };
+        if (C <= 4) gv.for_each_hot(eligible && !complete, visit);
+        else gv.for_each(eligible && !complete, visit);
         nm.reduce(gv.lpg);
         nm.pad(c_real);
         double det2;
@@ -593,7 +624,7 @@ FN_HD void scale1_sweep(const EvalConst& ec, const GeneView& gv, const double* X
     }
     mid.p = k - c_real;
     mid.d2 = d2 < 0.0 ? 0.0 : d2;
-    mid.logdet_a = complete ? 0.0 : log(det);
+    mid.det_a = complete ? 1.0 : det;
     mid.state = !eligible ? 0 : ((ok && mid.p > 0 && d2 == d2) ? 1 : 2);
 }
 
@@ -605,7 +636,7 @@ FN_HD void scale1_finish(const EvalConst& ec, const Scale1Mid& mid, double cst, 
     if (mid.state == 2) { out.value = NAN; return; }
     const int p = mid.p;
     const double d2 = mid.d2 * ec.itheta0;
-    const double logdet = p * ec.ltheta0 + mid.logdet_a + cst;
+    const double logdet = p * ec.ltheta0 + (mid.det_a == 1.0 ? 0.0 : log(mid.det_a)) + cst;
     double dv, kappa;
     out.value = finish_density(ec, p, logdet, d2, dv, kappa);
     out.dv = dv;

@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
         // gene of every lpg-th tile and the tail runs once per lpg tiles with all 32 lanes of a
         // warp working on different genes.
         Scale1Mid pend;
-        pend.state = 0; pend.d2 = 0.0; pend.logdet_a = 0.0; pend.p = 0;
+        pend.state = 0; pend.d2 = 0.0; pend.det_a = 1.0; pend.p = 0;
         double pend_cst = 0.0;
         long long pend_gene = -1;
         int sel = 0;

@@ -1,6 +1,6 @@
 """Minimal driver for ncu: upload a synthetic n x m matrix and run a few nll+grad evaluations.
 
-    python tools/profile_eval.py [n] [m] [model] [evals] [design columns]
+    python tools/profile_eval.py [n] [m] [model] [evals] [design columns] [weights]
 """
 import os
 import sys
@@ -30,6 +30,9 @@ aux = None
 if fam.kind == 2:                       # PAT-Seq: read counts; y = tail length, positive
     aux = torch.poisson(torch.full((n, m), 20.0, dtype=torch.float64, device=dev)) + 1.0
     y = y * 5.0 + 60.0
+    torch.cuda.synchronize()
+if len(sys.argv) > 6 and sys.argv[6] == "weights" and aux is None:      # precision weights (voom-like)
+    aux = torch.exp(0.5 * torch.randn((n, m), dtype=torch.float64, device=dev))
     torch.cuda.synchronize()
 e = _native.Engine(0)
 e.upload_dev(n, m, y.data_ptr(), aux.data_ptr() if aux is not None else 0, fam, 0, design)
