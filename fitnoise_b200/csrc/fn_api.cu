@@ -354,7 +354,7 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     const size_t fixed = table_bytes + 256 + (size_t)genes * per_gene_extra;
     if (fixed + stage > h->smem_optin - static_reserve)
         return fail(FN_ERR_UNSUPPORTED, "m = %d is too large for one tile stage in shared memory (%zu bytes)", m, fixed + stage);
-    int stages = h->tune_stages > 0 ? h->tune_stages : ((one_big_stage && stage > 50 * 1024) ? 1 : 3);
+    int stages = h->tune_stages > 0 ? h->tune_stages : 3;      // as many as fit, see below
     if (stages > FN_MAX_STAGES) stages = FN_MAX_STAGES;
     while (stages > 1 && fixed + (size_t)stages * stage > budget) --stages;
     if (fixed + (size_t)stages * stage > budget) ctas = 1;      // a single CTA per SM then

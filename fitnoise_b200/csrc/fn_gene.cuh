@@ -208,18 +208,21 @@ struct GeneView {
 template <int C> struct Tri { enum { N = C * (C + 1) / 2 }; };
 #define FN_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
-// 1/sqrt(x) for a positive pivot: the device's rsqrt (a few ulp) instead of a square root and a division.
+// 1/sqrt(x) for a positive pivot.  FAST: the device's rsqrt (1 ulp) instead of a correctly rounded
+// square root and division -- used where the factor only feeds sums over genes (the likelihood
+// kernels); the coefficient kernel, whose per-gene output can amplify the last bit by the condition
+// number of an almost collinear sub-design, keeps the two correctly rounded operations.
+template <bool FAST>
 FN_HD double rsqrt_pos(double x) {
 #ifdef __CUDA_ARCH__
-    return rsqrt(x);
-#else
-    return 1.0 / sqrt(x);
+    if (FAST) return rsqrt(x);
 #endif
+    return 1.0 / sqrt(x);
 }
 
 // In-place Cholesky A = L L'.  On return a holds L below the diagonal and 1/L_ii on it;
 // det = prod of pivots (so ln det A = ln det).  Returns false when a pivot is <= rel_tol * A_ii.
-template <int C>
+template <int C, bool FAST = false>
 FN_HD bool chol(double* a, double& det, double rel_tol) {
     bool ok = true;
     det = 1.0;
@@ -236,7 +239,7 @@ FN_HD bool chol(double* a, double& det, double rel_tol) {
                 const double orig = a[FN_TRI(i, i)];
                 if (!(s > rel_tol * orig) || !(s > 0.0)) { ok = false; s = 1.0; }
                 det *= s;
-                a[FN_TRI(i, i)] = rsqrt_pos(s);
+                a[FN_TRI(i, i)] = rsqrt_pos<FAST>(s);
             }
         }
     }
@@ -592,7 +595,7 @@ FN_HD void scale1_sweep(const EvalConst& ec, const GeneView& gv, const double* X
         nm.reduce(gv.lpg);
         nm.pad(c_real);
         double det2;
-        const bool ok2 = chol<C>(nm.a, det2, 0.0);
+        const bool ok2 = chol<C, true>(nm.a, det2, 0.0);
         double beta2[C];
 #pragma unroll
         for (int i = 0; i < C; ++i) beta2[i] = nm.b[i];
@@ -695,7 +698,7 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
     nm.reduce(gv.lpg);
     nm.pad(c_real);
     double det;
-    const bool ok = chol<C>(nm.a, det, 0.0);
+    const bool ok = chol<C, true>(nm.a, det, 0.0);
     double beta[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
@@ -821,7 +824,7 @@ FN_HD void eval_factors(const EvalConst& ec, const GeneView& gv, const double* Z
     nm.reduce(gv.lpg);
     ridge_and_pad<C>(nm.a, c_real, nf);
     double det;
-    const bool ok = chol<C>(nm.a, det, 0.0);
+    const bool ok = chol<C, true>(nm.a, det, 0.0);
     double sol[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) sol[i] = nm.b[i];
