@@ -692,7 +692,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     // K1
     Geom g;
     const size_t table_bytes = 2 * (size_t)m * width * sizeof(double);
-    int rc = choose_geom(h, h->has_aux, false, false, table_bytes, g);
+    int rc = choose_geom(h, h->has_aux, false, false, table_bytes, g, 0, 0, h->has_aux && fam.kind != KIND_PATSEQ);
     if (rc) return rc;
     rc = ensure_reduce(h, g.grid, PREP_NACC);
     if (rc) return rc;
@@ -1088,7 +1088,7 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
 
     Geom g;
     const size_t table_bytes = ((size_t)m * d.width + 2 * m) * sizeof(double);
-    rc = choose_geom(h, h->has_aux, h->gs != nullptr, false, table_bytes, g);
+    rc = choose_geom(h, h->has_aux, h->gs != nullptr, false, table_bytes, g, 0, 0, h->has_aux && h->fam.kind != KIND_PATSEQ);
     if (rc) return rc;
     CoefParams cp;
     cp.g = geom_params(h, g);
