@@ -285,23 +285,23 @@ FN_HD double leverage(const double* l, const double* x) {
 template <int C>
 FN_HD void chol_inverse(const double* l, double* ainv) {
     double li[Tri<C>::N];           // L^-1, lower triangular
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
     for (int j = 0; j < C; ++j) {
         li[FN_TRI(j, j)] = l[FN_TRI(j, j)];
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
         for (int i = j + 1; i < C; ++i) {
             double s = 0.0;
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
             for (int t = j; t < i; ++t) s -= l[FN_TRI(i, t)] * li[FN_TRI(t, j)];
             li[FN_TRI(i, j)] = s * l[FN_TRI(i, i)];
         }
     }
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
     for (int i = 0; i < C; ++i)
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
         for (int j = 0; j <= i; ++j) {
             double s = 0.0;
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
             for (int t = i; t < C; ++t) s += li[FN_TRI(t, i)] * li[FN_TRI(t, j)];
             ainv[FN_TRI(i, j)] = s;
         }

@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
         // back to the user's basis: coef = Rinv beta,  V = Rinv Ainv Rinv' s2
         // (wide designs keep the outer loops rolled: C^3 terms unrolled cost minutes of compile time)
         double tmp[C * C];
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
         for (int i = 0; i < C; ++i) {
             if (i < c) {
                 double a = 0.0;
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
                 for (int t = 0; t < C; ++t) if (t >= i && t < c) a += rinv[i * c + t] * beta[t];
                 cf[i] = a;
             }
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
             for (int j = 0; j < C; ++j) {
                 double a = 0.0;
 #pragma unroll
@@ -656,9 +656,9 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
                 tmp[i * C + j] = a;
             }
         }
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
         for (int i = 0; i < C; ++i)
-#pragma unroll (C > 8 ? 1 : C)
+#pragma unroll (C > 8 ? 1 : 64)
             for (int j = 0; j < C; ++j) {
                 if (i < c && j < c) {
                     double a = 0.0;
