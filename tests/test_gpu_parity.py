@@ -234,6 +234,59 @@ def test_full_size_properties():
         e.close()
 
 
+def test_more_than_2_31_elements():
+    """23,000,000 genes x 96 samples = 2.2e9 doubles (17.7 GB) resident on one GPU: element offsets
+    pass 2^31, so any 32-bit index in the kernels or the tile arithmetic would show up here.  Properties:
+    shard additivity, the per-gene results of the last genes against a small upload of the same rows, the
+    weights of the last gene."""
+    torch = pytest.importorskip("torch")
+    n, m = 23000000, 96
+    assert n * m > 2 ** 31
+    if torch.cuda.mem_get_info(0)[0] < 60e9:
+        pytest.skip("needs 60 GB of free device memory")
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    y = torch.randn((n, m), dtype=torch.float64, device=dev, generator=gen)
+    y[n - 3, 5] = float("nan")
+    torch.cuda.synchronize()
+    design = np.array([[1.0, 0.0]] * 48 + [[1.0, 1.0]] * 48)
+    fam = fitnoise.Model_t()._family(m)
+    theta = np.array([7.0, 1.1])
+    e = _native.Engine(0)
+    try:
+        e.upload_dev(n, m, y.data_ptr(), 0, fam, 0, design)
+        v_all, g_all, used, bad = e.nll_grad(theta)
+        assert used == n and bad == 0
+        score, d2, p = e.per_gene(theta)
+        assert_close(score.sum(), v_all, 1e-11, what="sum of per-gene scores")
+        coef, _, _ = e.coef(theta, design, want_covar=False)
+        con, pv, q = e.test_bh(np.array([[0.0], [1.0]]))
+        tail = y[n - 1000:].cpu().numpy()
+        half = n // 2 + 7
+        e.upload_dev(half, m, y.data_ptr(), 0, fam, 0, design)
+        v1, g1, u1, _ = e.nll_grad(theta)
+        e.upload_dev(n - half, m, y.data_ptr() + half * m * 8, 0, fam, 0, design)
+        v2, g2, u2, _ = e.nll_grad(theta)
+        assert u1 + u2 == n
+        assert_close(v1 + v2, v_all, 1e-11, what="shard additivity (value)")
+        assert_close(g1 + g2, g_all, 1e-8, atol=1e-11 * abs(v_all), what="shard additivity (gradient)")
+        e.upload(tail, None, fam, None, design)
+        s_tail, _, p_tail = e.per_gene(theta)
+        c_tail, _, _ = e.coef(theta, design, want_covar=False)
+        con_tail, pv_tail, _ = e.test_bh(np.array([[0.0], [1.0]]))
+        # (a gene's place in its tile sets the order of its sums: equal to rounding, not bitwise)
+        assert_close(score[n - 1000:], s_tail, 1e-12, what="scores of the last genes")
+        assert np.array_equal(p[n - 1000:], p_tail)
+        assert_close(coef[n - 1000:], c_tail, 1e-10, atol=1e-13, what="coefficients of the last genes")
+        assert_close(pv[n - 1000:], pv_tail, 1e-9, what="p-values of the last genes")
+        assert p[n - 3] == m - 1 - 2 and p[n - 1] == m - 2
+        assert np.array_equal(q, oracle.fdr(pv))
+    finally:
+        e.close()
+        del y
+
+
 def _random_case(rng, n, m, c, model):
     design = np.concatenate([np.ones((m, 1)), rng.normal(size=(m, c - 1))], axis=1) if c > 1 else np.ones((m, 1))
     y = rng.normal(size=(n, m)) * 1.5 + 10.0
