@@ -199,16 +199,19 @@ class Engine(object):
         """One REML objective + gradient evaluation over this engine's genes (all ranks' genes when
         the fused exchange is connected): (value, grad, n_used, n_bad).  Called once per optimiser
         step, so the ctypes scaffolding is built once and reused."""
-        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1)
-        P = len(theta)
         call = self.__dict__.get("_nll_call")
+        P = len(theta)
         if call is None or call[0] != P:
             value, used, bad = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
-            grad = np.zeros(max(P, 1))
-            call = self._nll_call = (P, value, used, bad, grad, ctypes.byref(value), ctypes.byref(used),
-                                     ctypes.byref(bad), grad.ctypes.data_as(c_double_p), self._lib.fn_nll_grad)
-        _, value, used, bad, grad, pvalue, pused, pbad, pgrad, fn = call
-        rc = fn(self._h, theta.ctypes.data_as(c_double_p), P, pvalue, pgrad, pused, pbad)
+            tbuf, grad = np.zeros(max(P, 1)), np.zeros(max(P, 1))
+            # pointers to persistent buffers: no per-call ctypes object construction
+            call = self._nll_call = (P, value, used, bad, grad, tbuf, ctypes.cast(tbuf.ctypes.data, c_double_p),
+                                     ctypes.c_int32(P), ctypes.byref(value), ctypes.cast(grad.ctypes.data, c_double_p),
+                                     ctypes.byref(used), ctypes.byref(bad), self._lib.fn_nll_grad)
+        _, value, used, bad, grad, tbuf, ptheta, cP, pvalue, pgrad, pused, pbad, fn = call
+        if P:
+            tbuf[:] = theta
+        rc = fn(self._h, ptheta, cP, pvalue, pgrad, pused, pbad)
         if rc != 0:
             self._check(rc)
         return value.value, grad[:P].copy(), used.value, bad.value
