@@ -265,8 +265,7 @@ def run_gpu(args):
                 engine.nll_grad_dev(THETA, reduce_buf.data_ptr())
                 dist.all_reduce(reduce_buf)
                 return reduce_buf.cpu().numpy()
-            value, grad, used, bad = engine.nll_grad(THETA)
-            return np.concatenate([[value], grad, [used, bad]])
+            return engine.nll_grad(THETA)          # (value, grad, n_used, n_bad): totals over all ranks, on the host
 
         def barrier():
             if world > 1:
@@ -293,7 +292,9 @@ def run_gpu(args):
             extra = int(t.item())
         for _ in range(extra):
             step()
-        assert int(first[P + 1]) == n * world and int(first[P + 2]) == 0, first
+        if reduce_mode == "nccl":
+            first = (first[0], first[1:P + 1], first[P + 1], first[P + 2])
+        assert int(first[2]) == n * world and int(first[3]) == 0, first
         launches0 = engine.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kernel_ms = []
