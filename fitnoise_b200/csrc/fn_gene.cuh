@@ -381,9 +381,11 @@ struct EvalConst {
 // (v,p)-only terms of -log density (distributions.py:139-146 t / :44-46 normal), and d/dv.
 FN_HD void density_tables(int is_t, double v, int p, double& t0, double& t1) {
     if (is_t) {
-        const double hp = 0.5 * (v + p);
-        t0 = -(lgamma(hp) - lgamma(0.5 * v) - (0.5 * p) * log(3.14159265358979323846 * v));
-        t1 = -0.5 * digamma(hp) + 0.5 * digamma(0.5 * v) + 0.5 * p / v;
+        double lg_hp, dg_hp, lg_v, dg_v;
+        lgamma_digamma(0.5 * (v + p), lg_hp, dg_hp);
+        lgamma_digamma(0.5 * v, lg_v, dg_v);
+        t0 = -(lg_hp - lg_v - (0.5 * p) * log(3.14159265358979323846 * v));
+        t1 = -0.5 * dg_hp + 0.5 * dg_v + 0.5 * p / v;
     } else {
         t0 = 0.5 * p * 1.8378770664093454836;      // p/2 ln(2 pi)
         t1 = 0.0;

@@ -201,10 +201,10 @@ __device__ __forceinline__ void block_sum(double* v, double* out, double* scratc
     __syncthreads();
 }
 
-// Per-evaluation tables t0[p], t1[p] (p = 0..m) of density_tables(), filled by the whole CTA.  The
-// two special functions of an entry go to different warps and the three p-independent terms are
-// computed once, so the latency is one lgamma or one digamma instead of two of each plus a log
-// (this sits on the critical path of every launch: ~3 us of a ~9 us small-data kernel before).
+// Per-evaluation tables t0[p], t1[p] (p = 0..m) of density_tables(), filled by the whole CTA: thread p
+// evaluates ln Gamma and psi of (v + p)/2 with one lgamma_digamma() call (two logarithms, one
+// division), the p-independent terms come from entry 0.  This sits on the critical path of every
+// launch (~2-3 us of a ~10 us small-data kernel with the library lgamma and a ten-division psi).
 __device__ __forceinline__ void fill_density_tables(int is_t, double v, int m, double* t0, double* t1) {
     __shared__ double common[3];
     if (!is_t) {
@@ -212,14 +212,11 @@ __device__ __forceinline__ void fill_density_tables(int is_t, double v, int m, d
         __syncthreads();
         return;
     }
-    const int n1 = m + 1, total = 2 * n1 + 3;
-    for (int w = threadIdx.x; w < total; w += blockDim.x) {
-        if (w < n1) t0[w] = lgamma(0.5 * (v + w));
-        else if (w < 2 * n1) t1[w - n1] = digamma(0.5 * (v + (w - n1)));
-        else if (w == 2 * n1) common[0] = lgamma(0.5 * v);
-        else if (w == 2 * n1 + 1) common[1] = digamma(0.5 * v);
-        else common[2] = log(3.14159265358979323846 * v);
-    }
+    // entry p (thread p): ln Gamma and psi of (v + p)/2 in one call; entry 0 is also the common v/2 term
+    for (int p = threadIdx.x; p <= m; p += blockDim.x) lgamma_digamma(0.5 * (v + p), t0[p], t1[p]);
+    if (threadIdx.x == blockDim.x - 1) common[2] = log(3.14159265358979323846 * v);
+    __syncthreads();
+    if (threadIdx.x == 0) { common[0] = t0[0]; common[1] = t1[0]; }
     __syncthreads();
     for (int p = threadIdx.x; p <= m; p += blockDim.x) {
         t0[p] = -(t0[p] - common[0] - (0.5 * p) * common[2]);

@@ -31,6 +31,25 @@ FN_HDN double digamma(double x) {
     return acc + log(x) - 0.5 * r - s;
 }
 
+// ln Gamma(x) and psi(x) together for x > 0.  Both shift x up to X = x + n >= 10 and share the product
+// P = x (x+1) ... (x+n-1):  ln Gamma(x) = ln Gamma(X) - ln P,  psi(x) = psi(X) - P'/P  (P' carried along
+// by P'_{k+1} = P'_k (x+k) + P_k), then Stirling / the asymptotic series at X (next terms < 1e-16).
+// One call costs two logarithms and one division; the per-launch density tables sit on the critical
+// path of every evaluation, where the library lgamma plus ten dependent divisions took ~2 us.
+FN_HD void lgamma_digamma(double x, double& lg, double& dg) {
+    double P = 1.0, dP = 0.0;
+    bool shifted = false;
+    while (x < 10.0) { dP = dP * x + P; P *= x; x += 1.0; shifted = true; }
+    const double r = 1.0 / x, r2 = r * r, lx = log(x);
+    const double sl = r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0 - r2 * (1.0 / 1680.0
+                    - r2 * (1.0 / 1188.0 - r2 * (691.0 / 360360.0 - r2 * (1.0 / 156.0)))))));
+    const double sd = r2 * (1.0 / 12.0 - r2 * (1.0 / 120.0 - r2 * (1.0 / 252.0 - r2 * (1.0 / 240.0
+                    - r2 * (1.0 / 132.0 - r2 * (691.0 / 32760.0 - r2 * (1.0 / 12.0)))))));
+    lg = (x - 0.5) * lx - x + 0.91893853320467274178 + sl;
+    dg = lx - 0.5 * r - sd;
+    if (shifted) { lg -= log(P); dg -= dP / P; }
+}
+
 // Continued fraction for the incomplete beta function (modified Lentz; Numerical Recipes 6.4).
 FN_HDN double betacf(double a, double b, double x) {
     const double tiny = 1e-300, eps = 1e-16;

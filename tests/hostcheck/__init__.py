@@ -63,6 +63,10 @@ def digamma(x):
     return _vec("hc_digamma", x)
 
 
+def lgamma_digamma(x):
+    return _vec("hc_lgamma2", x), _vec("hc_digamma2", x)
+
+
 def f_sf(f, dfn, dfd):
     return _vec("hc_f_sf", f, dfn, dfd)
 

@@ -20,6 +20,22 @@ def test_digamma():
     assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-12
 
 
+def test_lgamma_digamma_pair():
+    """The combined routine behind the per-launch density tables, over every argument the tables can
+    take: (v + p)/2 with v in [1e-10, 100] and p = 0 ... 2000."""
+    import mpmath
+    rng = np.random.default_rng(1)
+    x = np.concatenate([10 ** rng.uniform(-11, 3.1, 40000), np.arange(1, 400) * 0.5, [5e-11, 1e-3, 9.999999, 10.0, 1000.5]])
+    lg, dg = hostcheck.lgamma_digamma(x)
+    ref_l, ref_d = scipy.special.gammaln(x), scipy.special.digamma(x)
+    assert np.max(np.abs(lg - ref_l) / np.maximum(np.abs(ref_l), 1.0)) < 2e-14
+    assert np.max(np.abs(dg - ref_d) / np.maximum(np.abs(ref_d), 1e-3)) < 1e-12
+    for xv in [5e-11, 0.3, 1.5, 2.0, 9.5, 47.25, 180.0]:
+        l, d = hostcheck.lgamma_digamma(np.array([xv]))
+        assert abs(l[0] - float(mpmath.loggamma(xv))) <= 4e-15 * max(1.0, abs(float(mpmath.loggamma(xv))))
+        assert abs(d[0] - float(mpmath.digamma(xv))) <= 1e-13 * max(1.0, abs(float(mpmath.digamma(xv))))
+
+
 def test_f_sf_against_scipy():
     rng = np.random.default_rng(1)
     N = 100000
