@@ -10,7 +10,9 @@ genes x 96 samples, two-group design, on one GPU; the likelihood-and-gradient ev
 with Model_t (P = 2) because the literal Model_independent has no hyper-parameters and never
 evaluates a likelihood; the literal Model_independent fit + test wall time is reported
 beside it under "fit_test".  With N > 1 (torchrun, one rank per GPU) every rank holds its own
-1M x 96 shard (weak scaling) and each step ends with an NCCL all-reduce of the P+3 sums.
+1M x 96 shard (weak scaling) and each step ends with the sum of the P+3 partial results over the
+ranks: fused into the kernel epilogue over NVLink peer memory (default), or kernel + ncclAllReduce
+(FN_REDUCE=nccl, also the fallback when peer mapping is unavailable).
 
 `value`   : genes of all ranks / device time per step, inputs resident in HBM (y is 768 MB per GPU,
             six times the L2, so every step streams from DRAM; no extra L2 flush needed).
