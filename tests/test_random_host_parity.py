@@ -91,3 +91,43 @@ def test_random_cases_against_oracle(model):
         assert_close(fitted.get_weights(), oracle.get_weights(ref["cfg"], np.asarray(theta)), 1e-12, what=what + " weights")
         checked += 1
     assert checked == 12
+
+
+@pytest.mark.parametrize("model", ["Model_t_factors", "Model_normal_factors", "Model_independent_factors"])
+def test_random_factor_cases_against_oracle(model):
+    """Unknown-factor models: the augmented ridge system of the kernels against the oracle's dense
+    covariance diag(sigma2) + F F' (plus_covar), at a perturbed starting point."""
+    rng = np.random.default_rng(zlib.crc32(model.encode()))
+    for trial in range(6):
+        nf = int(rng.integers(1, 3))
+        m = int(rng.integers(8, 15))
+        c = int(rng.integers(1, 4))
+        n = int(rng.integers(6, 14))
+        design = np.column_stack([np.ones(m)] + [rng.normal(size=m) for _ in range(c - 1)])
+        F = rng.normal(size=(m, nf))
+        y = rng.normal(size=(n, m)) + rng.normal(size=(n, nf)) @ F.T + 10.0
+        y[rng.random((n, m)) < 0.05] = np.nan
+        context = {}
+        if rng.random() < 0.5 or model == "Model_independent_factors":
+            context = {"weights": np.exp(rng.normal(0, 0.4, size=(n, m)))}
+        cfg0 = oracle.Configured(model, y, context, nan_aware=True, n_factors=nf, design=design,
+                                 control_design=np.ones((m, 1)), controls=None)
+        init = np.asarray(cfg0.initial, dtype=float)
+        theta = init + rng.normal(0, 0.05, size=len(init)) * np.maximum(np.abs(init), 0.1)
+        for i, (lo, hi) in enumerate(cfg0.bounds):          # keep strictly inside the finite bounds
+            if lo is not None:
+                theta[i] = max(theta[i], lo * 1.001)
+            if hi is not None:
+                theta[i] = min(theta[i], hi * 0.999)
+        what = "%s trial %d nf=%d n=%d m=%d c=%d" % (model, trial, nf, n, m, c)
+        fitted = getattr(fitnoise, model)(nf)._with(_engine_factory=hostcheck.HostEvaluator).fit(
+            fitnoise.Dataset(y, context), design, force_param=theta)
+        ref = oracle.fit_and_test(model, y, design, context, coef_idx=[c - 1], force_param=theta,
+                                  nan_aware=True, skip_rank_deficient=True, n_factors=nf)
+        value, grad, used, bad = fitted._objective(theta)
+        ov, og = oracle.total_score_grad(ref["cfg"], ref["prepared"], np.asarray(theta))
+        assert used == len(ref["prepared"]) and bad == 0, what
+        assert_close(value, ov, 1e-10, what=what + " objective")
+        assert_close(grad, og, 1e-6, atol=1e-8 * max(abs(ov), 1.0), what=what + " gradient")
+        assert_close(fitted.coef, ref["coef"], 1e-7, atol=1e-8, what=what + " coef")
+        assert_close(fitted.noise_p_values, ref["noise_p_values"], 1e-7, atol=1e-300, what=what + " noise p")
