@@ -51,11 +51,16 @@ def t_noise(rng, n, m, df):
     return rng.normal(size=(n, m)) * np.sqrt(df / rng.chisquare(df, size=(n, 1)))
 
 
+ONLY = None          # set by `--only name,name`: write just these fixtures (the others stay as committed)
+
+
 def run_case(ref, name, model, y, design, theta, context=None, test_coef=None,
              test_contrasts=None, controls=None, control_design=None, noise_design=None,
              optimise=False, n_factors=0):
     """`theta` may be a function of the reference's configured initial vector (factor models: the
     pack coordinates depend on the reference's own Q2)."""
+    if ONLY is not None and name not in ONLY:
+        return
     context = context or {}
     base_cls = getattr(ref, model)
     cls = (lambda: base_cls(n_factors)) if n_factors else base_cls
@@ -334,11 +339,54 @@ def main():
     p2 = rng.random(37) ** 6
     p3 = np.array([np.nan, np.nan])
     p4 = np.array([0.5])
-    np.savez_compressed(os.path.join(HERE, "fdr.npz"),
-                        p1=p1, ref_q1=ref.fdr(p1), p2=p2, ref_q2=ref.fdr(p2),
-                        p3=p3, ref_q3=ref.fdr(p3), p4=p4, ref_q4=ref.fdr(p4))
-    print("fdr")
+    if ONLY is None or "fdr" in ONLY:
+        np.savez_compressed(os.path.join(HERE, "fdr.npz"),
+                            p1=p1, ref_q1=ref.fdr(p1), p2=p2, ref_q2=ref.fdr(p2),
+                            p3=p3, ref_q3=ref.fdr(p3), p4=p4, ref_q4=ref.fdr(p4))
+        print("fdr")
+
+    # 11. Designs with 9 ... 13 columns (the kernels' template widths 12 and 16).  Own generator, so
+    #     that the fixtures above keep their random draws.
+    rng2 = np.random.default_rng(20261020)
+
+    def wide(m, c):
+        cols = [np.ones(m), (np.arange(m) >= m // 2) * 1.0]
+        cols += [(np.arange(m) % 5 == k) * 1.0 for k in range(1, 4)]
+        cols += [rng2.normal(size=m) for _ in range(c - len(cols))]
+        return np.stack(cols[:c], axis=1)
+
+    n, m, c = 40, 30, 10
+    X = wide(m, c)
+    y = t_noise(rng2, n, m, 6.0) * 1.2 + 5.0
+    y[:6] += 2.5 * X[:, 1]
+    w = np.exp(rng2.normal(0, 0.4, size=(n, m)))
+    w[3, 4] = 0.0; w[8, 20:] = 0.0
+    contrasts = np.zeros((c, 2)); contrasts[1, 0] = 1.0; contrasts[c - 1, 1] = 1.0; contrasts[2, 1] = -1.0
+    run_case(ref, "t_design_c10", "Model_t", y, X, [6.0, 1.3], context={"weights": w}, test_contrasts=contrasts)
+
+    n, m, c = 36, 40, 13
+    X = wide(m, c)
+    y = rng2.normal(size=(n, m)) * 0.9 + 3.0
+    y[:5] -= 1.5 * X[:, 1]
+    y[4, 7] = np.nan; y[6, ::3] = np.nan; y[9, 5:] = np.nan; y[12, :] = np.nan
+    w = np.exp(rng2.normal(0, 0.3, size=(n, m)))
+    run_case(ref, "independent_design_c13", "Model_independent", y, X, [], context={"weights": w},
+             test_coef=[1, 12])
+
+    n, m, c = 40, 32, 9
+    X = wide(m, c)
+    counts = rng2.poisson(18.0, size=(n, m)).astype(float)
+    counts[rng2.random((n, m)) < 0.12] = 0
+    mu = rng2.uniform(30, 90, size=(n, 1))
+    y = mu + 4.0 * X[:, 1][None, :] * (np.arange(n) < 5)[:, None] \
+        + t_noise(rng2, n, m, 9.0) * np.sqrt(26.0 ** 2 / np.maximum(counts, 1) + (0.05 * mu) ** 2)
+    y[counts == 0] = np.nan
+    run_case(ref, "t_patseq_design_c9", "Model_t_patseq", y, X, [11.0, 650.0, 0.0028],
+             context={"counts": counts}, test_coef=[1])
 
 
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":
+        ONLY = set(sys.argv[2].split(","))
     main()
