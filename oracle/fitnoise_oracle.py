@@ -640,11 +640,13 @@ def fit_and_test(model, y, design, context=None, coef_idx=None, contrasts=None,
 
 
 # --------------------------------------------------------------------------------------
-# fitnoise.transform (fittransform.py).  PARITY UNPINNED: the reference evaluates this objective only
-# through Theano (no numpy path), which cannot be installed here, so no golden vector can be
-# generated from the reference.  This restatement follows fittransform.py line by line on explicit
-# n x m matrices; the tests check its gradient against central differences and the CUDA path
-# against it.
+# fitnoise.transform (fittransform.py).  PARITY PARTLY PINNED: the reference builds this objective from
+# Theano symbols and Theano cannot be installed here, so `Transform.fit` itself (its autodiff gradient
+# and its optimiser run) cannot be executed.  What does run without Theano is pinned by
+# tests/golden/transform_poly.npz (tests/test_transform.py): `_apply_transform`, `_unpack_transform`,
+# `_configured` are the reference's own code on arrays, and the objective is the reference's
+# expression (fittransform.py:103-121) evaluated with its own qr_complete / dot / log.  UNPINNED: the
+# gradient (checked against central differences instead) and the fitted parameters.
 # --------------------------------------------------------------------------------------
 
 def transform_apply(pack, x, order):

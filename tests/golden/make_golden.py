@@ -385,8 +385,45 @@ def main():
              context={"counts": counts}, test_coef=[1])
 
 
+def transform_fixture():
+    """fitnoise.transform: what of the reference runs without Theano.  `_unpack_transform`,
+    `_apply_transform`, `_configured` are called as they are; the objective is the reference's own
+    expression (fittransform.py:103-121) evaluated on arrays with the reference's `qr_complete`, `dot`
+    and `log` instead of Theano symbols."""
+    ref = refimport.load()
+    ft = refimport.load_transform()
+    rng = np.random.default_rng(20261021)
+    n, m = 60, 6
+    design = np.stack([np.ones(m), (np.arange(m) >= 3) * 1.0], axis=1)
+    depth = rng.uniform(0.5, 2.0, size=m)
+    mu = np.exp(rng.normal(3.0, 1.5, size=(n, 1)))
+    x = rng.poisson(mu * depth[None, :] * np.exp(0.5 * design[:, 1])[None, :]).astype(float)
+    out = dict(x=x, design=design)
+    q, r = ref.env.qr_complete(design)
+    q_null = q[:, design.shape[1]:]
+    for order in (1, 2, 3):
+        t = ft.Transform_polynomial(order)
+        cfg = t._with(x=x, design=design, null=q_null)._configured()
+        pack = np.concatenate([rng.uniform(0.0, 3.0, size=(order - 1) * m), rng.uniform(0.2, 5.0, size=m)])
+        vy = cfg._apply_transform(cfg._unpack_transform(m, pack), x)
+        vcentered = vy - vy.mean(axis=0)[None, :]
+        vresidual = ft.dot(vcentered, q_null)
+        cost = ft.log((vresidual * vresidual).flatten().sum()) - ft.log((vcentered * vcentered).flatten().sum())
+        out["pack%d" % order] = pack
+        out["ref_y%d" % order] = vy
+        out["ref_cost%d" % order] = float(cost)
+        out["ref_initial%d" % order] = np.asarray(cfg._param_initial, dtype=float)
+        out["ref_lower%d" % order] = np.array([b[0] for b in cfg._param_bounds], dtype=float)
+        out["ref_upper_is_none%d" % order] = np.array([b[1] is None for b in cfg._param_bounds])
+    np.savez_compressed(os.path.join(HERE, "transform_poly.npz"), **out)
+    print("transform_poly")
+
+
 if __name__ == "__main__":
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "--transform":
+        transform_fixture()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "--only":
         ONLY = set(sys.argv[2].split(","))
     main()

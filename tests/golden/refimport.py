@@ -14,7 +14,9 @@ Python 3 after two purely syntactic rewrites applied to the source TEXT at impor
 
 No reference source is written to disk or copied into this repository; the four modules
 are read from ``/root/reference/fitnoise`` and exec'd into synthetic module objects.
-``fittransform`` (needs Theano) is not loaded.
+``fittransform`` builds its objective from Theano symbols and cannot be RUN without Theano, but the
+module imports, and its numpy-compatible methods (``_unpack_transform``, ``_apply_transform``,
+``_configured``) work on plain arrays: ``load_transform()`` gives access to those.
 """
 import os
 import re
@@ -68,3 +70,22 @@ def load():
     pkg.fdr = pkg.p_adjust.fdr
     pkg.as_jsonic = pkg.env.as_jsonic
     return pkg
+
+
+def load_transform():
+    """The reference's ``fittransform`` module (its ``fit`` needs Theano; the polynomial transform
+    itself, its parameter layout, initial values and bounds are plain numpy)."""
+    pkg = load()
+    name = _PKG + ".fittransform"
+    if name in sys.modules:
+        return sys.modules[name]
+    path = os.path.join(REFERENCE_ROOT, "fitnoise", "fittransform.py")
+    with open(path) as f:
+        source = _py3(f.read())
+    mod = types.ModuleType(name)
+    mod.__package__ = _PKG
+    mod.__file__ = path
+    sys.modules[name] = mod
+    setattr(pkg, "fittransform", mod)
+    exec(compile(source, path, "exec"), mod.__dict__)
+    return mod

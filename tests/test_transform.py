@@ -1,7 +1,10 @@
-"""fitnoise.transform (moderated log transform): the oracle's gradient against central
-differences, and the package's host logic + sums formulation against the oracle.  CPU only; the
-CUDA kernel is checked in test_gpu_parity.py.  Parity with the reference itself is UNPINNED for this
-function: the reference evaluates it only through Theano, which is not installable here."""
+"""fitnoise.transform (moderated log transform): the oracle against what of the reference runs
+without Theano (tests/golden/transform_poly.npz: the polynomial transform, the parameter layout,
+initial values and bounds are the reference's own code on arrays; the objective is the reference's
+expression evaluated with its own qr/dot/log), the oracle's gradient against central differences,
+and the package's host logic + sums formulation against the oracle.  CPU only; the CUDA kernel is
+checked in test_gpu_parity.py.  The reference's Theano-built gradient and its optimiser run cannot
+be reproduced here (no Theano): that part stays unpinned."""
 import numpy as np
 import pytest
 
@@ -20,6 +23,29 @@ def counts(n, m, seed=0):
     effect = np.where(rng.random((n, 1)) < 0.1, rng.normal(0, 1.0, size=(n, 1)), 0.0)
     return rng.poisson(mu * depth[None, :] * np.exp(effect * group[None, :])).astype(float), \
         np.stack([np.ones(m), group], axis=1)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_oracle_and_package_against_reference_pieces(order):
+    from conftest import load_golden
+    g = load_golden("transform_poly")
+    x, design, pack = g["x"], g["design"], g["pack%d" % order]
+    assert_close(oracle.transform_apply(pack, x, order), g["ref_y%d" % order], 1e-14, what="transform")
+    assert_close(oracle.transform_cost(pack, x, design, order), float(g["ref_cost%d" % order]), 1e-12, what="objective")
+    # the package: same initial values and bounds, same objective through the sums formulation
+    cfg = fitnoise.Transform_polynomial(order)._with(x=x, design=design)._configured()
+    assert np.array_equal(np.asarray(cfg._param_initial, dtype=float), g["ref_initial%d" % order])
+    assert np.array_equal(np.array([b[0] for b in cfg._param_bounds], dtype=float), g["ref_lower%d" % order])
+    assert np.array_equal(np.array([b[1] is None for b in cfg._param_bounds]), g["ref_upper_is_none%d" % order])
+    host = hostcheck.HostEvaluator()
+    host.transform_upload(x, design)
+    q, _ = np.linalg.qr(design, mode="complete")
+    qd = q[:, :design.shape[1]]
+    cost, grad, mu = fittransform._combine(host.transform_sums(order, pack), x.shape[0], x.shape[1], order, qd @ qd.T)
+    assert_close(cost, float(g["ref_cost%d" % order]), 1e-11, what="objective from the kernel's sums")
+    y = host.transform_apply(order, pack, mu)
+    want = g["ref_y%d" % order]
+    assert_close(y, want - want.mean(axis=0), 1e-12, atol=1e-13, what="centred transformed data")
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
