@@ -340,12 +340,18 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     // (and a CTA at the very limit fails to launch).
     const size_t static_reserve = 6 * 1024;
     const size_t budget = h->smem_sm / ctas - static_reserve;   // dynamic bytes per CTA
-    size_t stage_target = 50 * 1024;
-    if (one_big_stage && threads == 256 && budget > table_bytes + 256 + 64 * 1024) stage_target = budget - table_bytes - 256;
-    int lpg = h->tune_lpg > 0 ? h->tune_lpg : 1;
-    if (h->tune_lpg == 0) {
-        while (lpg < 32 && threads / (lpg * 2) >= 16 &&
-               tile_stage_bytes(threads / lpg, m, aux, gs, cst) + (size_t)(threads / lpg) * per_gene_extra > stage_target) lpg *= 2;
+    auto lanes_for = [&](size_t stage_target) {
+        int l = 1;
+        while (l < 32 && threads / (l * 2) >= 16 &&
+               tile_stage_bytes(threads / l, m, aux, gs, cst) + (size_t)(threads / l) * per_gene_extra > stage_target) l *= 2;
+        return l;
+    };
+    int lpg = h->tune_lpg > 0 ? h->tune_lpg : lanes_for(50 * 1024);
+    if (h->tune_lpg == 0 && one_big_stage && threads == 256 && budget > table_bytes + 256 + 64 * 1024) {
+        // only when every CTA still gets enough tiles to balance the grid (large n)
+        const int big = lanes_for(budget - table_bytes - 256);
+        const long long tiles = (h->n + threads / big - 1) / (threads / big);
+        if (tiles >= 8LL * h->sm_count * ctas) lpg = big;
     }
     if (lpg > 32 || threads % lpg || (threads / lpg) % 16)
         return fail(FN_ERR_ARG, "invalid geometry: threads %d lpg %d (genes per tile must be a multiple of 16)", threads, lpg);
