@@ -594,3 +594,32 @@ def test_transform_fit_on_gpu():
     assert abs(fitted.optimization_result.fun - ofit.fun) <= 2e-3 * abs(ofit.fun)
     want = oracle.transform_apply(fitted.optimization_result.x, x, 2)
     assert_close(fitted.y, want - want.mean(axis=0), 1e-10, atol=1e-12)
+
+
+def test_integration_stub_from_the_docs():
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would add) runs as
+    written against the built library and returns what the package's own binding returns."""
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# fitnoise/_b200.py.*?)```", text, re.S).group(1)
+    block = block.replace('ctypes.CDLL("libfitnoise_b200.so")', 'ctypes.CDLL(%r)' % _native.library_path())
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    rng = np.random.default_rng(8)
+    n, m = 500, 6
+    y = rng.normal(size=(n, m))
+    y[3, 2] = np.nan
+    design = np.array([[1.0, 0.0]] * 3 + [[1.0, 1.0]] * 3)
+    fam = ns["Family"](kind=0, na=1, nb=0, tail_own=0, v3=0, dist=1, nf=0, fixed_df=0.0)      # Model_t
+    h = ns["Handle"](0)
+    info = h.upload(y, None, fam, None, design, np.ones((m, 1)))
+    value, grad = h.nll_grad(np.array([6.0, 1.2]))
+    e = _native.Engine(0)
+    try:
+        info2 = e.upload(y, None, fitnoise.Model_t()._family(m), None, design)
+        v2, g2, used, bad = e.nll_grad([6.0, 1.2])
+    finally:
+        e.close()
+    assert info.n_eligible == info2.n_eligible == n and used == n
+    assert value == v2 and np.array_equal(grad, g2)
+    ns["_check"](ns["_lib"].fn_destroy(h.h))
