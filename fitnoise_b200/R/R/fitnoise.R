@@ -41,8 +41,9 @@ fitnoise.fit <- function(data, design, model = "Model_t()", noise.design = NULL,
     if (!is.null(weights)) context["weights"] <- .as_float_matrix(weights)
     if (!is.null(counts)) context["counts"] <- .as_float_matrix(counts)
     dataset <- fn$Dataset(.as_float_matrix(data), context)
-    prototype <- reticulate::py_eval(model, convert = FALSE,
-                                     globals = reticulate::py_get_attr(fn, "__dict__"))
+    # Python's own eval with the package namespace as globals (reticulate::py_eval takes no namespace)
+    builtins <- reticulate::import_builtins(convert = FALSE)
+    prototype <- builtins$eval(model, reticulate::py_get_attr(fn, "__dict__"))
     fit <- prototype$fit(
         dataset,
         design = .as_float_matrix(design),
