@@ -384,6 +384,24 @@ def main():
     run_case(ref, "t_patseq_design_c9", "Model_t_patseq", y, X, [11.0, 650.0, 0.0028],
              context={"counts": counts}, test_coef=[1])
 
+    # 12. Many genes: 1500 distinct missing patterns per family, straight from the reference.
+    n, m = 1500, 12
+    y = rng2.normal(size=(n, m)) * 1.1 + 6.0
+    y[:150, 6:] += rng2.normal(0, 2.0, size=(150, 1))
+    y[rng2.random((n, m)) < 0.15] = np.nan
+    w = np.exp(rng2.normal(0, 0.5, size=(n, m)))
+    w[rng2.random((n, m)) < 0.03] = 0.0
+    run_case(ref, "independent_many_rows", "Model_independent", y, two_group(m), [], context={"weights": w},
+             test_coef=[1])
+    counts = rng2.poisson(8.0, size=(n, m)).astype(float)
+    counts[rng2.random((n, m)) < 0.15] = 0
+    mu = rng2.uniform(30, 90, size=(n, 1))
+    y = mu + 5.0 * two_group(m)[:, 1][None, :] * (np.arange(n) < 100)[:, None] \
+        + t_noise(rng2, n, m, 8.0) * np.sqrt(25.0 ** 2 / np.maximum(counts, 1) + (0.06 * mu) ** 2)
+    y[counts == 0] = np.nan
+    run_case(ref, "t_patseq_many_rows", "Model_t_patseq", y, two_group(m), [9.5, 600.0, 0.0035],
+             context={"counts": counts}, test_coef=[1])
+
 
 def transform_fixture():
     """fitnoise.transform: what of the reference runs without Theano.  `_unpack_transform`,
