@@ -27,6 +27,7 @@ EXPORTS = [
     "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
     "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked", "fn_nll_grad_factors", "fn_set_factors", "fn_time_nll_grad",
     "fn_transform_upload", "fn_transform_sums", "fn_transform_apply",
+    "fn_resident_begin", "fn_resident_end", "fn_resident_stats", "fn_source_hash",
 ]
 
 
@@ -58,22 +59,32 @@ def library_path():
 
 
 def load_library():
-    """Load (building first if the sources are newer) the CUDA library.  Raises when it is missing
-    and cannot be built -- never substitutes another implementation."""
+    """Load the CUDA library, building it first when it is missing or was built from other sources
+    than the ones in this tree (content hash, fitnoise_b200.build.source_hash).  Raises when it
+    cannot be built -- never substitutes another implementation, never loads a stale binary."""
     global _LIB
     if _LIB is not None:
         return _LIB
     path = library_path()
-    if not os.path.exists(path):
+    if _build.needs_build():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on the box
-            raise NativeError("libfitnoise_b200.so is not built and cannot be built here (%s). "
+            raise NativeError("libfitnoise_b200.so is %s and cannot be built here (%s). "
                               "Run `python __graft_entry__.py` / fitnoise_b200.build.build(); "
-                              "there is no CPU fallback." % exc)
+                              "there is no CPU fallback." % (
+                                  "out of date" if os.path.exists(path) else "not built", exc))
     lib = ctypes.CDLL(path)
     lib.fn_last_error.restype = ctypes.c_char_p
     lib.fn_version.restype = ctypes.c_char_p
+    lib.fn_source_hash.restype = ctypes.c_char_p
+    if lib.fn_source_hash().decode() != _build.source_hash():
+        raise NativeError("libfitnoise_b200.so was built from different sources than fitnoise_b200/csrc "
+                          "(ABI may not match the Python declarations); rebuild it")
+    lib.fn_resident_begin.argtypes = [ctypes.c_void_p]
+    lib.fn_resident_end.argtypes = [ctypes.c_void_p]
+    lib.fn_resident_stats.restype = ctypes.c_int64
+    lib.fn_resident_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.fn_launch_count.restype = ctypes.c_int64
     lib.fn_launch_count.argtypes = [ctypes.c_void_p]
     lib.fn_last_kernel_ms.restype = ctypes.c_double
@@ -215,6 +226,22 @@ class Engine(object):
         if rc != 0:
             self._check(rc)
         return value.value, grad[:P].copy(), used.value, bad.value
+
+    # ---- resident evaluation kernel -----------------------------------------------------------
+    def resident_begin(self):
+        """Keep ONE evaluation kernel on the GPU until resident_end(): nll_grad then costs no kernel
+        launch (include/fitnoise_b200.h, fn_resident_begin)."""
+        self._check(self._lib.fn_resident_begin(self._h))
+
+    def resident_end(self):
+        if getattr(self, "_h", None):
+            self._check(self._lib.fn_resident_end(self._h))
+
+    def resident_stats(self):
+        """(resident now?, resident kernels launched, evaluations they executed)"""
+        launches, evals = ctypes.c_int64(), ctypes.c_int64()
+        on = self._lib.fn_resident_stats(self._h, ctypes.byref(launches), ctypes.byref(evals))
+        return bool(on), launches.value, evals.value
 
     def nll_grad_factors(self, theta, factors):
         """Factor models: (value, grad of [df, variance], d/dF (m x nf), n_used, n_bad)."""

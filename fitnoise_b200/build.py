@@ -29,15 +29,35 @@ LINK_FLAGS = ["-shared", "--cudart", "static", "-gencode", "arch=compute_100a,co
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h")))
+
+
+HEADER = os.path.join(os.path.dirname(HERE), "include", "fitnoise_b200.h")
+HASH_PATH = os.path.join(LIB_DIR, "source_hash.txt")
+
+
+def source_hash():
+    """sha1 over the contents of csrc/* and the public header: compiled into the library
+    (fn_source_hash) so that a binary built from other sources is recognised whatever the mtimes."""
+    import hashlib
+    digest = hashlib.sha1()
+    for path in sources() + [HEADER]:
+        digest.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            digest.update(f.read())
+    return digest.hexdigest()
+
+
+def built_hash():
+    try:
+        with open(HASH_PATH) as f:
+            return f.read().strip()
+    except OSError:
+        return None
 
 
 def needs_build():
-    if not os.path.exists(LIB_PATH):
-        return True
-    built = os.path.getmtime(LIB_PATH)
-    inc = os.path.join(os.path.dirname(HERE), "include", "fitnoise_b200.h")
-    return any(os.path.getmtime(p) > built for p in sources() + [inc])
+    return not os.path.exists(LIB_PATH) or built_hash() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -46,6 +66,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ_DIR, exist_ok=True)
+    digest = source_hash()
     extra = ["-Xptxas", "-v"] if verbose else []
     jobs = []
     for w in sorted(WIDTHS, reverse=True):          # widest first: they take longest
@@ -58,12 +79,15 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
         return proc.stderr
 
-    jobs.insert(1, [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, "fn_api.cu"), "-o", os.path.join(OBJ_DIR, "fn_api.o")])
+    jobs.insert(1, [nvcc] + NVCC_FLAGS + extra + ["-DFN_SOURCE_HASH=\"%s\"" % digest, "-c", os.path.join(CSRC, "fn_api.cu"),
+                    "-o", os.path.join(OBJ_DIR, "fn_api.o")])
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
         logs = list(pool.map(run, jobs))
     objs = [c[-1] for c in jobs]
     log = run([nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + objs)
     shutil.rmtree(OBJ_DIR, ignore_errors=True)     # only the .so travels to the GPU box
+    with open(HASH_PATH, "w") as f:
+        f.write(digest + "\n")
     if verbose:
         sys.stderr.write("".join(logs) + log)
     return LIB_PATH

@@ -181,12 +181,35 @@ struct fn_handle {
     int tr_m = 0, tr_c = 0;
 
     unsigned long long host_seq = 0;   // completion-flag sequence of the pinned result buffer
+    // histogram of residual df over the genes in the REML sum (prepare kernel): the (v, p)-only terms of
+    // the objective are added on the host from it (table_terms)
+    DevBuf b_phist;
+    std::vector<long long> p_hist;
+    double psum_expected = 0.0;
+    // resident evaluation kernel (fn_resident_begin / _end): command block and state
+    bool resident = false;
+    int res_words = 0;
+    unsigned long long* cmd_host = nullptr;        // pinned, mapped
+    unsigned long long* cmd_host_devptr = nullptr;
+    unsigned long long* exit_host = nullptr;       // pinned, mapped (one word)
+    unsigned long long* exit_host_devptr = nullptr;
+    unsigned long long* cmd_dev = nullptr;
+    size_t cmd_cap = 0;                            // words the three buffers hold
+    int64_t resident_launches = 0, resident_evals = 0;
     // fused multi-GPU exchange (fn_comm_*): mailboxes mapped with CUDA IPC
     int comm_world = 0, comm_rank = 0, comm_slot = 0;
     unsigned long long comm_seq = 0;
     Slot* comm_own = nullptr;
     Slot* comm_peer[FN_MAX_RANKS] = {nullptr};
 };
+
+static int leave_resident(fn_handle* h);     // stop the resident evaluation kernel, if one is running
+
+#define LEAVE_RESIDENT(h)                          \
+    do {                                           \
+        int rc_res__ = leave_resident(h);          \
+        if (rc_res__) return rc_res__;             \
+    } while (0)
 
 template <class T>
 static void dfree(T*& p) {
@@ -220,7 +243,7 @@ static void release_data(fn_handle* h) {
 
 static void free_buffers(fn_handle* h) {
     release_data(h);
-    DevBuf* all[] = {&h->b_y, &h->b_aux, &h->b_gs, &h->b_cst, &h->b_avg, &h->b_status, &h->b_xn, &h->b_xc, &h->b_tab,
+    DevBuf* all[] = {&h->b_phist, &h->b_y, &h->b_aux, &h->b_gs, &h->b_cst, &h->b_avg, &h->b_status, &h->b_xn, &h->b_xc, &h->b_tab,
                      &h->b_pg_score, &h->b_pg_d2, &h->b_pg_p, &h->b_noise_p, &h->b_coef, &h->b_covar, &h->b_dfpost,
                      &h->b_xcoef, &h->b_rinv, &h->b_zn, &h->b_zc, &h->b_fsq, &h->b_tx, &h->b_tq, &h->b_ta, &h->b_tmean};
     for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
@@ -233,7 +256,13 @@ static void free_buffers(fn_handle* h) {
 }
 
 extern "C" const char* fn_last_error(void) { return g_error.c_str(); }
-extern "C" const char* fn_version(void) { return "fitnoise_b200 0.1 (sm_100a)"; }
+extern "C" const char* fn_version(void) { return "fitnoise_b200 0.2 (sm_100a)"; }
+#ifndef FN_SOURCE_HASH
+#define FN_SOURCE_HASH "unknown"
+#endif
+// hash of the sources this library was built from (fitnoise_b200/build.py); the Python binding
+// compares it with the sources it sees and refuses a stale binary
+extern "C" const char* fn_source_hash(void) { return FN_SOURCE_HASH; }
 
 extern "C" int fn_device_count(void) {
     int n = 0;
@@ -281,8 +310,12 @@ extern "C" int fn_comm_disconnect(fn_handle* h);
 extern "C" int fn_destroy(fn_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    leave_resident(h);
     cudaStreamSynchronize(h->stream);
     fn_comm_disconnect(h);
+    if (h->cmd_host) cudaFreeHost(h->cmd_host);
+    if (h->exit_host) cudaFreeHost(h->exit_host);
+    dfree(h->cmd_dev);
     if (h->bh_exec) { cudaGraphExecDestroy(h->bh_exec); h->bh_exec = nullptr; }
     free_buffers(h);
     dfree(h->partials); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
@@ -296,14 +329,17 @@ extern "C" int fn_destroy(fn_handle* h) {
 
 extern "C" int fn_synchronize(fn_handle* h) {
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 extern "C" int fn_set_tuning(fn_handle* h, int32_t lpg, int32_t threads, int32_t stages, int32_t ctas) {
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    LEAVE_RESIDENT(h);
     if (lpg && (lpg & (lpg - 1))) return fail(FN_ERR_ARG, "lpg must be a power of two");
-    if (threads && (threads % 32 || threads > 256)) return fail(FN_ERR_ARG, "threads must be a multiple of 32, <= 256");
+    if (threads && ((threads & (threads - 1)) || threads < 32 || threads > 256))
+        return fail(FN_ERR_ARG, "threads must be 32, 64, 128 or 256 (genes per tile must divide the %d-row padding)", FN_ROW_PAD);
     h->tune_lpg = lpg; h->tune_threads = threads; h->tune_stages = stages; h->tune_ctas = ctas;
     return 0;
 }
@@ -353,8 +389,10 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
         const long long tiles = (h->n + threads / big - 1) / (threads / big);
         if (tiles >= 8LL * h->sm_count * ctas) lpg = big;
     }
-    if (lpg > 32 || threads % lpg || (threads / lpg) % 16)
-        return fail(FN_ERR_ARG, "invalid geometry: threads %d lpg %d (genes per tile must be a multiple of 16)", threads, lpg);
+    // genes per tile must divide FN_ROW_PAD (the per-gene arrays are padded to that many rows, so a
+    // full-size bulk copy of the last tile stays inside the allocations): a power of two >= 16
+    if (lpg > 32 || threads % lpg || (threads / lpg) < 16 || ((threads / lpg) & (threads / lpg - 1)) || FN_ROW_PAD % (threads / lpg))
+        return fail(FN_ERR_ARG, "invalid geometry: threads %d lpg %d (genes per tile must be a power of two, 16..%d)", threads, lpg, FN_ROW_PAD);
     const int genes = threads / lpg;
     const size_t stage = tile_stage_bytes(genes, m, aux, gs, cst);
     const size_t fixed = table_bytes + 256 + (size_t)genes * per_gene_extra;
@@ -438,21 +476,41 @@ static int ensure_scratch(fn_handle* h, size_t bytes) {
     return 0;
 }
 
+static int resident_relaunch(fn_handle* h, unsigned long long next_seq);
+
+static inline bool host_slot_ready(const volatile Slot* slot, unsigned long long seq, double* value) {
+    // two aligned 8-byte loads; the pair is accepted only if it is consistent (fn_kernels.cuh, Slot)
+    const unsigned long long bits = slot->bits;
+    const unsigned long long tag = slot->tag;
+    if ((bits ^ tag) != seq_mix(seq)) return false;
+    memcpy(value, &bits, sizeof bits);
+    return true;
+}
+
 // Wait for the kernel that carries `seq` to publish its totals in the pinned result slots and copy
-// them to h->out_vals.  Every slot is one 16-byte {value, seq} store of the last CTA, so a slot that
-// shows `seq` also shows its value; spinning on host memory sees the result one PCIe write after
-// the last CTA finishes -- several microseconds sooner than cudaStreamSynchronize returns.  Falls
-// back to the stream's status to notice a failed launch.
+// them to h->out_vals.  Every slot is one {bits, tag} pair of the last CTA that authenticates itself
+// against `seq`; spinning on host memory sees the result one PCIe write after the last CTA finishes
+// -- several microseconds sooner than cudaStreamSynchronize returns.  Falls back to the stream's
+// status to notice a failed launch, and -- resident mode -- a kernel that left on its idle timeout
+// before it saw the command, in which case it is launched again (the command is still in place).
 static int wait_result(fn_handle* h, unsigned long long seq, int nacc) {
     h->out_vals.resize(nacc);
     unsigned long long spins = 0;
+    int relaunches = 0;
     for (int i = 0; i < nacc; ++i) {
-        volatile Slot* slot = &h->out_host[i];
-        while (slot->seq != seq) {
+        const volatile Slot* slot = &h->out_host[i];
+        double value;
+        while (!host_slot_ready(slot, seq, &value)) {
             if ((++spins & 0x3fff) == 0) {
                 cudaError_t e = cudaStreamQuery(h->stream);
                 if (e == cudaSuccess) {
-                    if (slot->seq == seq) break;
+                    if (host_slot_ready(slot, seq, &value)) break;
+                    if (h->resident && relaunches < 8) {
+                        ++relaunches;
+                        int rc = resident_relaunch(h, seq);
+                        if (rc) return rc;
+                        continue;
+                    }
                     return fail(FN_ERR_CUDA, "kernel finished without publishing its result");
                 }
                 if (e != cudaErrorNotReady) return fail(FN_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
@@ -461,8 +519,7 @@ static int wait_result(fn_handle* h, unsigned long long seq, int nacc) {
             __builtin_ia32_pause();
 #endif
         }
-        std::atomic_thread_fence(std::memory_order_acquire);
-        h->out_vals[i] = slot->value;
+        h->out_vals[i] = value;
     }
     return 0;
 }
@@ -470,19 +527,19 @@ static int wait_result(fn_handle* h, unsigned long long seq, int nacc) {
 // after a plain stream synchronisation the slots of the last launch are complete
 static void collect_result(fn_handle* h, int nacc) {
     h->out_vals.resize(nacc);
-    for (int i = 0; i < nacc; ++i) h->out_vals[i] = h->out_host[i].value;
+    for (int i = 0; i < nacc; ++i) memcpy(&h->out_vals[i], (const void*)&h->out_host[i].bits, sizeof(double));
 }
 
-static void fill_reduce(fn_handle* h, GridReduce& gr, int nacc, int add_index, double add_value, bool exchange) {
+static void fill_reduce(fn_handle* h, GridReduce& gr, StepVars& sv, int nacc, bool exchange) {
     gr.partials = h->partials; gr.ticket = h->ticket; gr.out_dev = h->out_dev;
     gr.out_host = h->out_host_devptr; gr.nacc = nacc;
-    gr.add_index = add_index; gr.add_value = add_value;
-    gr.host_seq = ++h->host_seq;
-    gr.comm.world = 0; gr.comm.rank = 0; gr.comm.slot_count = 0; gr.comm.seq = 0; gr.comm.timeout_ns = 0;
+    sv.host_seq = ++h->host_seq;
+    sv.comm_seq = 0; sv.add_on = 0; sv.add_value = 0.0; sv.add_dv = 0.0; sv.add_psum = 0.0;
+    gr.comm.world = 0; gr.comm.rank = 0; gr.comm.slot_count = 0; gr.comm.timeout_ns = 0;
     for (int r = 0; r < FN_MAX_RANKS; ++r) gr.comm.mailbox[r] = nullptr;
     if (exchange && h->comm_world > 1) {
         gr.comm.world = h->comm_world; gr.comm.rank = h->comm_rank; gr.comm.slot_count = h->comm_slot;
-        gr.comm.seq = ++h->comm_seq;
+        sv.comm_seq = ++h->comm_seq;
         gr.comm.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
         for (int r = 0; r < h->comm_world; ++r) gr.comm.mailbox[r] = h->comm_peer[r];
     }
@@ -528,7 +585,10 @@ static int copy_h2d(fn_handle* h, void* dst, const void* src, size_t bytes) {
             for (size_t c = w; c < nchunks; c += W, turn ^= 1) {
                 const int slot = 2 * w + turn;
                 const size_t off = c * chunk, len = (off + chunk <= bytes) ? chunk : bytes - off;
-                if (c >= (size_t)(2 * W) && cudaEventSynchronize(h->stage_ev[slot]) != cudaSuccess) { status[w] = 1; return; }
+                // the slot's previous DMA (of this call OR of an earlier copy_h2d whose transfers are
+                // still queued on the stream) must have read the buffer before it is overwritten; an
+                // event that was never recorded returns at once
+                if (cudaEventSynchronize(h->stage_ev[slot]) != cudaSuccess) { status[w] = 1; return; }
                 memcpy(h->stage_buf[slot], (const char*)src + off, len);
                 if (cudaMemcpyAsync((char*)dst + off, h->stage_buf[slot], len, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
                     cudaEventRecord(h->stage_ev[slot], h->stream) != cudaSuccess) { status[w] = 1; return; }
@@ -601,6 +661,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
                          const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
                          fn_prep_info* info, cudaMemcpyKind kind) {
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    LEAVE_RESIDENT(h);
     // n == 0 is allowed: an empty shard (fewer genes than GPUs) still takes part in every exchange
     if ((!y && n > 0) || !family || !design_noise) return fail(FN_ERR_ARG, "fn_upload: y, family and design_noise are required");
     if (n < 0 || m < 1) return fail(FN_ERR_ARG, "fn_upload: bad shape (n=%lld, m=%d)", (long long)n, m);
@@ -697,11 +758,13 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
 
     // K1
     Geom g;
-    const size_t table_bytes = 2 * (size_t)m * width * sizeof(double);
+    const size_t table_bytes = 2 * (size_t)m * width * sizeof(double) + (((size_t)m + 1) * sizeof(unsigned int) + 15) / 16 * 16;
     int rc = choose_geom(h, h->has_aux, false, false, table_bytes, g, 0, 0, h->has_aux && fam.kind != KIND_PATSEQ);
     if (rc) return rc;
     rc = ensure_reduce(h, g.grid, PREP_NACC);
     if (rc) return rc;
+    CUDA_TRY(ensure_buf(h->b_phist, ((size_t)m + 1) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(h->b_phist.p, 0, ((size_t)m + 1) * sizeof(unsigned long long), h->stream));
     PrepParams pp;
     pp.g = geom_params(h, g);
     pp.src.y = h->y; pp.src.aux = h->aux; pp.src.gs = nullptr; pp.src.cst = nullptr; pp.src.status = h->status;
@@ -709,7 +772,8 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     pp.fam = fam;
     pp.xn = h->xn; pp.xc = h->xc; pp.c_noise = c_noise; pp.c_ctrl = c_ctrl;
     pp.status_out = h->status; pp.cst_out = h->cst; pp.avg_out = h->avg; pp.gs_out = h->gs;
-    fill_reduce(h, pp.gr, PREP_NACC, -1, 0.0, false);
+    pp.p_hist = (unsigned long long*)h->b_phist.p;
+    fill_reduce(h, pp.gr, pp.sv, PREP_NACC, false);
     {
         const KernelSet* ks = kernel_set(width);
         rc = launch_width_kernel(h, ks ? ks->prepare : nullptr, g.grid, g.threads, g.smem, &pp);
@@ -722,8 +786,13 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
         ++h->launches;
         CUDA_TRY(cudaGetLastError());
     }
+    h->p_hist.assign((size_t)m + 1, 0);
+    static_assert(sizeof(long long) == sizeof(unsigned long long), "histogram word size");
+    CUDA_TRY(cudaMemcpyAsync(h->p_hist.data(), h->b_phist.p, ((size_t)m + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     collect_result(h, PREP_NACC);
+    h->psum_expected = 0.0;
+    for (int pdf = 0; pdf <= m; ++pdf) h->psum_expected += (double)pdf * (double)h->p_hist[pdf];
     h->cst_sum = h->out_vals[PREP_CSTSUM];
     if (info) {
         const double cnt = h->out_vals[PREP_VARCNT];
@@ -762,14 +831,17 @@ struct ThetaState {
     std::vector<double> ta, tb;
 };
 
-static int stage_theta(fn_handle* h, const double* theta, int32_t P, ThetaState& ts) {
+// theta -> the scalars and tables the kernels take.  `device_tables`: also copy the two per-sample
+// tables (length m each) to h->tab_dev -- the coefficient / weight kernels read them from there, the
+// evaluation kernel only when a theta block is per-sample (shared blocks travel as scalars).
+static int stage_theta(fn_handle* h, const double* theta, int32_t P, ThetaState& ts, bool device_tables) {
     if (!h || !h->loaded) return fail(FN_ERR_STATE, "no data uploaded");
     if (P != theta_length(h->fam)) return fail(FN_ERR_ARG, "theta has %d entries, the family needs %d", P, theta_length(h->fam));
     if (P > 0 && !theta) return fail(FN_ERR_ARG, "theta is NULL");
     if (!unpack_theta(h->fam, h->m, theta, ts.v, ts.is_t, ts.theta0, ts.ta, ts.tb))
         return fail(FN_ERR_ARG, "theta must be finite and positive");
-    CUDA_TRY(cudaSetDevice(h->device));
-    if (h->fam.kind != KIND_SCALE1) {
+    if (device_tables && h->fam.kind != KIND_SCALE1) {
+        CUDA_TRY(cudaSetDevice(h->device));
         // the previous evaluation was synchronised (or is ordered on the same stream before the copy)
         memcpy(h->tab_host, ts.ta.data(), h->m * sizeof(double));
         memcpy(h->tab_host + h->m, ts.tb.data(), h->m * sizeof(double));
@@ -778,14 +850,33 @@ static int stage_theta(fn_handle* h, const double* theta, int32_t P, ThetaState&
     return 0;
 }
 
+static bool per_sample_a(const fn_handle* h) { return h->fam.na == h->m && h->fam.kind != KIND_SCALE1; }
+static bool per_sample_b(const fn_handle* h) { return h->fam.nb == h->m && h->fam.kind != KIND_SCALE1; }
+
 static int eval_nacc(const fn_handle* h) {
-    const bool ia = h->fam.na == h->m && h->fam.kind != KIND_SCALE1, ib = h->fam.nb == h->m;
-    return ACC_FIXED + ((ia || ib) ? 2 * h->m : 0);
+    return ACC_FIXED + ((per_sample_a(h) || per_sample_b(h)) ? 2 * h->m : 0);
 }
 
-static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool exchange) {
+// The terms of the objective that depend on (v, p) only, summed over this handle's genes with the
+// preparation kernel's histogram N_p of residual df:  sum_p N_p t0[p]  and  d/dv = sum_p N_p t1[p]
+// (density_tables: distributions.py:139-146 t / :44-46 normal).  A handful of distinct p occur in
+// practice (one when nothing is missing), so this costs well under a microsecond on the host and
+// the kernels need no per-evaluation table of ln Gamma / psi.
+static void table_terms(const fn_handle* h, const ThetaState& ts, StepVars& sv) {
+    double value = 0.5 * h->cst_sum, dv = 0.0;
+    for (size_t pdf = 0; pdf < h->p_hist.size(); ++pdf) {
+        if (!h->p_hist[pdf]) continue;
+        double t0, t1;
+        density_tables(ts.is_t, ts.v, (int)pdf, t0, t1);
+        value += (double)h->p_hist[pdf] * t0;
+        dv += (double)h->p_hist[pdf] * t1;
+    }
+    sv.add_on = 1; sv.add_value = value; sv.add_dv = dv; sv.add_psum = -h->psum_expected;
+}
+
+static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool exchange, bool resident = false) {
     const int m = h->m;
-    const bool ia = h->fam.na == m && h->fam.kind != KIND_SCALE1, ib = h->fam.nb == m;
+    const bool ia = per_sample_a(h), ib = per_sample_b(h);
     const bool inplace = ia || ib;
     Geom g;
     const size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
@@ -793,6 +884,19 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0, 0, one_big_stage);
     if (rc) return rc;
     if (inplace && m > g.threads) return fail(FN_ERR_UNSUPPORTED, "per-sample variance models need m <= threads per CTA (%d)", g.threads);
+    const KernelSet* ks = kernel_set(h->width);
+    const void* kernel = ks ? ks->eval[h->fam.kind] : nullptr;
+    if (!kernel) return fail(FN_ERR_UNSUPPORTED, "no kernel for this design width");
+    if (resident) {
+        // every CTA of a resident kernel must be on the GPU at once (they wait for each other's sums)
+        rc = set_smem(h, kernel, g.smem);
+        if (rc) return rc;
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, g.threads, g.smem));
+        if (per_sm < 1) return fail(FN_ERR_UNSUPPORTED, "the evaluation kernel does not fit on an SM");
+        const long long cap = (long long)per_sm * h->sm_count;
+        if (g.grid > cap) g.grid = (int)cap;
+    }
     const int nacc = eval_nacc(h);
     rc = ensure_reduce(h, g.grid, nacc);
     if (rc) return rc;
@@ -809,23 +913,159 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     ep.xn = h->xn; ep.xc = h->xc; ep.c_noise = h->dn.c; ep.c_ctrl = h->dc.c;
     ep.kind = h->fam.kind; ep.tail_own = h->fam.tail_own; ep.v3 = h->fam.v3; ep.is_t = ts.is_t;
     ep.v = ts.v; ep.theta0 = ts.theta0;
-    ep.ta = h->fam.kind != KIND_SCALE1 ? h->tab_dev : nullptr;
-    ep.tb = h->fam.kind != KIND_SCALE1 ? h->tab_dev + m : nullptr;
+    ep.ta0 = ts.ta.empty() ? 0.0 : ts.ta[0];
+    ep.tb0 = ts.tb.empty() ? 0.0 : ts.tb[0];
+    ep.ta = ia ? h->tab_dev : nullptr;
+    ep.tb = ib ? h->tab_dev + m : nullptr;
     ep.inplace_a = ia; ep.inplace_b = ib;
     ep.pg_score = per_gene ? h->pg_score : nullptr;
     ep.pg_d2 = per_gene ? h->pg_d2 : nullptr;
     ep.pg_p = per_gene ? h->pg_p : nullptr;
-    fill_reduce(h, ep.gr, nacc, per_gene ? -1 : ACC_VALUE, per_gene ? 0.0 : 0.5 * h->cst_sum, exchange);
-    if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    {
-        const KernelSet* ks = kernel_set(h->width);
-        rc = launch_width_kernel(h, ks ? ks->eval[h->fam.kind] : nullptr, g.grid, g.threads, g.smem, &ep);
-        if (rc) return rc;
+    ep.rc.cmd_host = nullptr; ep.rc.cmd_dev = nullptr; ep.rc.exit_host = nullptr;
+    ep.rc.next_seq = 0; ep.rc.idle_timeout_ns = 0; ep.rc.words = 0;
+    if (resident) {
+        // host_seq / comm_seq advance per command, not per launch
+        const unsigned long long hs = h->host_seq, cs = h->comm_seq;
+        fill_reduce(h, ep.gr, ep.sv, nacc, exchange);
+        h->host_seq = hs; h->comm_seq = cs;
+        ep.rc.cmd_host = h->cmd_host_devptr; ep.rc.cmd_dev = h->cmd_dev; ep.rc.exit_host = h->exit_host_devptr;
+        ep.rc.next_seq = h->host_seq + 1;
+        const char* env = getenv("FN_RESIDENT_IDLE_MS");
+        const double idle_ms = env ? atof(env) : 20.0;
+        ep.rc.idle_timeout_ns = (unsigned long long)((idle_ms > 0.01 ? idle_ms : 0.01) * 1e6);
+        ep.rc.words = h->res_words;
+    } else {
+        fill_reduce(h, ep.gr, ep.sv, nacc, exchange);
+        if (!per_gene) table_terms(h, ts, ep.sv);
     }
-    if (h->timing) { CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->timing_pending = true; }
+    if (h->timing && !resident) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    rc = launch_width_kernel(h, kernel, g.grid, g.threads, g.smem, &ep);
+    if (rc) return rc;
+    if (h->timing && !resident) { CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->timing_pending = true; }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// resident evaluation kernel
+// ------------------------------------------------------------------------------------------
+static int resident_words(const fn_handle* h) {
+    return CW_TAB + (per_sample_a(h) ? h->m : 0) + (per_sample_b(h) ? h->m : 0) + 1;
+}
+
+static int resident_launch(fn_handle* h) {
+    ThetaState ts;                       // theta arrives with each command
+    ts.is_t = h->fam.dist != DIST_NORMAL;
+    *(volatile unsigned long long*)h->exit_host = 0;
+    // a flag left behind by an earlier resident kernel (its QUIT, or the seq it gave up on) must not be
+    // taken for this kernel's first command
+    CUDA_TRY(cudaMemsetAsync(h->cmd_dev, 0, FN_CMD_DEV_PAYLOAD * sizeof(unsigned long long), h->stream));
+    int rc = launch_eval(h, ts, false, true, true);
+    if (rc) return rc;
+    ++h->resident_launches;
+    return 0;
+}
+
+static int resident_relaunch(fn_handle* h, unsigned long long next_seq) {
+    // the kernel has left (idle timeout); the command `next_seq` is still in the block
+    if (h->host_seq + 1 != next_seq && h->host_seq != next_seq) return fail(FN_ERR_STATE, "resident kernel: sequence mismatch");
+    const unsigned long long keep = h->host_seq;
+    h->host_seq = next_seq - 1;
+    int rc = resident_launch(h);
+    h->host_seq = keep;
+    return rc;
+}
+
+extern "C" int fn_resident_begin(fn_handle* h) {
+    if (!h || !h->loaded) return fail(FN_ERR_STATE, "no data uploaded");
+    if (h->fam.nf > 0) return fail(FN_ERR_UNSUPPORTED, "factor models are evaluated one launch at a time");
+    if (h->resident) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int words = resident_words(h);
+    if ((size_t)words > h->cmd_cap) {
+        if (h->cmd_host) { cudaFreeHost(h->cmd_host); h->cmd_host = nullptr; }
+        if (h->cmd_dev) { cudaFree(h->cmd_dev); h->cmd_dev = nullptr; }
+        const size_t cap = (size_t)words + 64;
+        CUDA_TRY(cudaHostAlloc(&h->cmd_host, cap * sizeof(unsigned long long), cudaHostAllocMapped));
+        memset(h->cmd_host, 0, cap * sizeof(unsigned long long));
+        CUDA_TRY(cudaHostGetDevicePointer(&h->cmd_host_devptr, h->cmd_host, 0));
+        CUDA_TRY(cudaMalloc(&h->cmd_dev, (FN_CMD_DEV_PAYLOAD + cap) * sizeof(unsigned long long)));
+        h->cmd_cap = cap;
+    }
+    if (!h->exit_host) {
+        CUDA_TRY(cudaHostAlloc(&h->exit_host, 64, cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(&h->exit_host_devptr, h->exit_host, 0));
+    }
+    h->res_words = words;
+    int rc = resident_launch(h);
+    if (rc) return rc;
+    h->resident = true;
+    return 0;
+}
+
+// Write one command; the sequence number goes last (the kernel accepts the block only with a
+// matching checksum, so it can never act on a half-written one).
+static void resident_command(fn_handle* h, int op, unsigned long long seq, unsigned long long comm_seq,
+                             const ThetaState* ts, const StepVars* sv) {
+    volatile unsigned long long* w = h->cmd_host;
+    auto bits = [](double x) { unsigned long long b; memcpy(&b, &x, sizeof b); return b; };
+    const int words = h->res_words;
+    w[CW_OP] = (unsigned long long)op;
+    w[CW_COMM_SEQ] = comm_seq;
+    w[CW_V] = bits(ts ? ts->v : 0.0);
+    w[CW_THETA0] = bits(ts ? ts->theta0 : 1.0);
+    w[CW_ADD_VALUE] = bits(sv ? sv->add_value : 0.0);
+    w[CW_ADD_DV] = bits(sv ? sv->add_dv : 0.0);
+    w[CW_ADD_PSUM] = bits(sv ? sv->add_psum : 0.0);
+    w[CW_TA0] = bits(ts && !ts->ta.empty() ? ts->ta[0] : 0.0);
+    w[CW_TB0] = bits(ts && !ts->tb.empty() ? ts->tb[0] : 0.0);
+    int at = CW_TAB;
+    if (per_sample_a(h)) for (int j = 0; j < h->m; ++j) w[at++] = bits(ts ? ts->ta[j] : 0.0);
+    if (per_sample_b(h)) for (int j = 0; j < h->m; ++j) w[at++] = bits(ts ? ts->tb[j] : 0.0);
+    unsigned long long sum = cmd_mix(seq, CW_SEQ);
+    for (int i = 1; i < words - 1; ++i) sum += cmd_mix(w[i], i);
+    w[words - 1] = sum;
+    std::atomic_thread_fence(std::memory_order_release);
+    w[CW_SEQ] = seq;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
+extern "C" int fn_resident_end(fn_handle* h) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    if (!h->resident) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const unsigned long long seq = ++h->host_seq;
+    resident_command(h, OP_QUIT, seq, 0, nullptr, nullptr);
+    h->resident = false;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int leave_resident(fn_handle* h) { return (h && h->resident) ? fn_resident_end(h) : 0; }
+
+extern "C" int64_t fn_resident_stats(fn_handle* h, int64_t* launches, int64_t* evaluations) {
+    if (!h) return 0;
+    if (launches) *launches = h->resident_launches;
+    if (evaluations) *evaluations = h->resident_evals;
+    return h->resident ? 1 : 0;
+}
+
+// one evaluation by the resident kernel: the totals are in h->out_vals afterwards
+static int resident_eval(fn_handle* h, const ThetaState& ts) {
+    StepVars sv;
+    table_terms(h, ts, sv);
+    const unsigned long long seq = ++h->host_seq;
+    const unsigned long long comm_seq = h->comm_world > 1 ? ++h->comm_seq : 0;
+    if (*(volatile unsigned long long*)h->exit_host == seq) {
+        // the kernel left on its idle timeout while waiting for this very command
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        int rc = resident_relaunch(h, seq);
+        if (rc) return rc;
+    }
+    resident_command(h, OP_EVAL, seq, comm_seq, &ts, &sv);
+    ++h->resident_evals;
+    return wait_result(h, seq, eval_nacc(h));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -835,6 +1075,7 @@ static int set_factors(fn_handle* h, const double* F) {
     const int m = h->m, nf = h->fam.nf, width = h->width;
     if (nf <= 0) return fail(FN_ERR_STATE, "the uploaded family has no factors");
     if (!F) return fail(FN_ERR_ARG, "factors is NULL");
+    { int rcl = leave_resident(h); if (rcl) return rcl; }
     for (int i = 0; i < m * nf; ++i) if (!(fabs(F[i]) < INFINITY)) return fail(FN_ERR_ARG, "factors must be finite");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));        // the previous kernel may still read the tables
@@ -856,6 +1097,16 @@ static int set_factors(fn_handle* h, const double* F) {
 extern "C" int fn_set_factors(fn_handle* h, const double* factors) {
     if (!h || !h->loaded) return fail(FN_ERR_STATE, "no data uploaded");
     return set_factors(h, factors);
+}
+
+#define FN_ERR_COMM -5
+// A peer that did not deliver its sums within the exchange timeout makes the kernel publish NaN for
+// every total: an error, not an objective value.
+static int check_totals(fn_handle* h, const double* acc) {
+    if (h->comm_world > 1 && acc[ACC_USED] != acc[ACC_USED])
+        return fail(FN_ERR_COMM, "multi-GPU exchange failed: a peer rank did not deliver its sums in time "
+                                 "(rank %d of %d); the ranks must call fn_nll_grad the same number of times", h->comm_rank, h->comm_world);
+    return 0;
 }
 
 static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene, bool exchange) {
@@ -884,7 +1135,8 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
     ep.pg_score = per_gene ? h->pg_score : nullptr;
     ep.pg_d2 = per_gene ? h->pg_d2 : nullptr;
     ep.pg_p = per_gene ? h->pg_p : nullptr;
-    fill_reduce(h, ep.gr, nacc, per_gene ? -1 : ACC_VALUE, per_gene ? 0.0 : 0.5 * h->cst_sum, exchange);
+    fill_reduce(h, ep.gr, ep.sv, nacc, exchange);
+    if (!per_gene) table_terms(h, ts, ep.sv);
     if (h->timing) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     {
         const KernelSet* ks = kernel_set(h->width);
@@ -900,7 +1152,7 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
 extern "C" int fn_nll_grad_factors(fn_handle* h, const double* theta, int32_t P, const double* factors,
                                    double* value, double* grad, double* grad_factors, int64_t* n_used, int64_t* n_bad) {
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = stage_theta(h, theta, P, ts, false);
     if (rc) return rc;
     rc = set_factors(h, factors);
     if (rc) return rc;
@@ -910,6 +1162,8 @@ extern "C" int fn_nll_grad_factors(fn_handle* h, const double* theta, int32_t P,
     rc = wait_result(h, h->host_seq, nacc);
     if (rc) return rc;
     const double* acc = h->out_vals.data();
+    rc = check_totals(h, acc);
+    if (rc) return rc;
     if (value) *value = acc[ACC_VALUE];
     if (grad) {
         int at = 0;
@@ -918,7 +1172,7 @@ extern "C" int fn_nll_grad_factors(fn_handle* h, const double* theta, int32_t P,
     }
     if (grad_factors) for (int i = 0; i < m * nf; ++i) grad_factors[i] = acc[ACC_FIXED + i];
     if (n_used) *n_used = (int64_t)acc[ACC_USED];
-    if (n_bad) *n_bad = (int64_t)acc[ACC_BAD];
+    if (n_bad) *n_bad = (int64_t)acc[ACC_BAD] + (acc[ACC_PSUM] != 0.0 ? 1 : 0);
     return 0;
 }
 
@@ -936,7 +1190,10 @@ static void assemble(const fn_handle* h, const double* acc, const double* ta, do
     if (f.nb == 1) out[at++] = acc[ACC_GB];
     else if (f.nb == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + m + j];
     out[at++] = acc[ACC_USED];
-    out[at++] = acc[ACC_BAD];
+    // a residual-df total that differs from the preparation kernel's histogram means that a sample
+    // retained at the start has a non-finite variance at this theta: the reference's fixed `retain`
+    // (fitnoise.py:26-28) would feed that variance to the density and get a non-finite score
+    out[at++] = acc[ACC_BAD] + (acc[ACC_PSUM] != 0.0 ? 1.0 : 0.0);
 }
 
 #ifdef FN_TRACE
@@ -953,18 +1210,28 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
                            int64_t* n_used, int64_t* n_bad) {
     FN_HOST_STAMP(0);
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = stage_theta(h, theta, P, ts, !h->resident && (per_sample_a(h) || per_sample_b(h)));
     if (rc) return rc;
     if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
     FN_HOST_STAMP(1);
-    rc = launch_eval(h, ts, false, true);
-    if (rc) return rc;
-    FN_HOST_STAMP(2);
-    rc = wait_result(h, h->host_seq, eval_nacc(h));
-    if (rc) return rc;
+    if (h->resident) {
+        rc = resident_eval(h, ts);
+        if (rc) return rc;
+    } else {
+        rc = launch_eval(h, ts, false, true);
+        if (rc) return rc;
+        FN_HOST_STAMP(2);
+        rc = wait_result(h, h->host_seq, eval_nacc(h));
+        if (rc) return rc;
+    }
     FN_HOST_STAMP(3);
-    std::vector<double> out(P + 3);
-    assemble(h, h->out_vals.data(), ts.ta.data(), out.data());
+    rc = check_totals(h, h->out_vals.data());
+    if (rc) return rc;
+    double out_small[64];
+    std::vector<double> out_big;
+    double* out = out_small;
+    if (P + 3 > 64) { out_big.resize(P + 3); out = out_big.data(); }
+    assemble(h, h->out_vals.data(), ts.ta.data(), out);
     if (value) *value = out[0];
     if (grad) for (int i = 0; i < P; ++i) grad[i] = out[1 + i];
     if (n_used) *n_used = (int64_t)out[P + 1];
@@ -976,7 +1243,9 @@ extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double*
 // CUDA events (no host wait and no idle gap in between, so launch latency is not counted).
 extern "C" int fn_time_nll_grad(fn_handle* h, const double* theta, int32_t P, int32_t reps, double* ms_per_launch) {
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = leave_resident(h);
+    if (rc) return rc;
+    rc = stage_theta(h, theta, P, ts, true);
     if (rc) return rc;
     if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
     if (reps < 1 || !ms_per_launch) return fail(FN_ERR_ARG, "fn_time_nll_grad: bad arguments");
@@ -1008,13 +1277,15 @@ __global__ void assemble_kernel(const double* acc, double* out, Family f, int m,
     if (f.nb == 1) out[at++] = acc[ACC_GB];
     else if (f.nb == m) for (int j = 0; j < m; ++j) out[at++] = acc[ACC_FIXED + m + j];
     out[at++] = acc[ACC_USED];
-    out[at++] = acc[ACC_BAD];
+    out[at++] = acc[ACC_BAD] + (acc[ACC_PSUM] != 0.0 ? 1.0 : 0.0);
 }
 
 extern "C" int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, double* out_dev) {
     if (!out_dev) return fail(FN_ERR_ARG, "out_dev is NULL");
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = leave_resident(h);
+    if (rc) return rc;
+    rc = stage_theta(h, theta, P, ts, true);
     if (rc) return rc;
     if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
     rc = launch_eval(h, ts, false, false);
@@ -1027,7 +1298,9 @@ extern "C" int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, dou
 
 extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double* score, double* d2, int32_t* p) {
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = leave_resident(h);
+    if (rc) return rc;
+    rc = stage_theta(h, theta, P, ts, true);
     if (rc) return rc;
     rc = h->fam.nf > 0 ? launch_eval_factors(h, ts, true, false) : launch_eval(h, ts, true, false);
     if (rc) return rc;
@@ -1040,7 +1313,9 @@ extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double*
 
 extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, double* noise_p, double* averages) {
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = leave_resident(h);
+    if (rc) return rc;
+    rc = stage_theta(h, theta, P, ts, true);
     if (rc) return rc;
     rc = h->fam.nf > 0 ? launch_eval_factors(h, ts, true, false) : launch_eval(h, ts, true, false);
     if (rc) return rc;
@@ -1066,7 +1341,9 @@ extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, doub
 extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, const double* design,
                        double* coef, double* covar, double* dfpost) {
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = leave_resident(h);
+    if (rc) return rc;
+    rc = stage_theta(h, theta, P, ts, true);
     if (rc) return rc;
     if (!design || c < 1 || c > FN_MAXC) return fail(FN_ERR_UNSUPPORTED, "design has %d columns; 1..%d supported", c, FN_MAXC);
     const int m = h->m;
@@ -1127,6 +1404,7 @@ static size_t bh_work_bytes(int64_t n);
 static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov,
                      double* pval, double* qval, uint32_t* order) {
     if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_test needs a preceding fn_coef");
+    LEAVE_RESIDENT(h);
     const int c = h->coef_c;
     if (kc < 1 || kc > FN_MAXC || !contrasts) return fail(FN_ERR_UNSUPPORTED, "contrasts has %d columns; 1..%d supported", kc, FN_MAXC);
     CUDA_TRY(cudaSetDevice(h->device));
@@ -1181,6 +1459,7 @@ extern "C" int fn_test_bh(fn_handle* h, int32_t kc, const double* contrasts, dou
 
 extern "C" int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* dfpost) {
     if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_coef_fetch needs a preceding fn_coef");
+    LEAVE_RESIDENT(h);
     const int c = h->coef_c;
     CUDA_TRY(cudaSetDevice(h->device));
     if (coef) D2H_TRY(coef, h->coef, (size_t)h->n * c * sizeof(double));
@@ -1192,7 +1471,9 @@ extern "C" int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* 
 
 extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* weights) {
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts);
+    int rc = leave_resident(h);
+    if (rc) return rc;
+    rc = stage_theta(h, theta, P, ts, true);
     if (rc) return rc;
     if (!weights) return fail(FN_ERR_ARG, "weights is NULL");
     const size_t bytes = (size_t)h->n * h->m * sizeof(double);
@@ -1298,6 +1579,7 @@ extern "C" int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
     if (n < 0 || n >= (1LL << 32)) return fail(FN_ERR_UNSUPPORTED, "fn_bh: n out of range");
     if (n == 0) return 0;
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = ensure_scratch(h, bh_work_bytes(n));
     if (rc) return rc;
@@ -1317,6 +1599,7 @@ static int bh_host(fn_handle* h, int64_t n, const double* p, double* q, uint32_t
     if (n < 0 || n >= (1LL << 32)) return fail(FN_ERR_UNSUPPORTED, "fn_bh: n out of range");
     if (n == 0) return 0;
     if (!p || !q) return fail(FN_ERR_ARG, "fn_bh: NULL array");
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     int rc = ensure_scratch(h, 2 * up(n * 8) + bh_work_bytes(n));
@@ -1340,6 +1623,7 @@ static int bh_host(fn_handle* h, int64_t n, const double* p, double* q, uint32_t
 extern "C" int fn_comm_mailbox(fn_handle* h, int32_t world, int32_t max_values, void* ipc_handle_out) {
     if (!h || !ipc_handle_out) return fail(FN_ERR_ARG, "fn_comm_mailbox: NULL argument");
     if (world < 2 || world > FN_MAX_RANKS) return fail(FN_ERR_ARG, "fn_comm_mailbox: world must be 2..%d", FN_MAX_RANKS);
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->comm_own) { cudaFree(h->comm_own); h->comm_own = nullptr; }
     h->comm_slot = ((max_values + 15) / 16) * 16;
@@ -1358,13 +1642,21 @@ extern "C" int fn_comm_mailbox(fn_handle* h, int32_t world, int32_t max_values, 
 extern "C" int fn_comm_connect(fn_handle* h, int32_t rank, int32_t world, const void* ipc_handles) {
     if (!h || !ipc_handles || !h->comm_own) return fail(FN_ERR_STATE, "fn_comm_connect: call fn_comm_mailbox first");
     if (world < 2 || world > FN_MAX_RANKS || rank < 0 || rank >= world) return fail(FN_ERR_ARG, "fn_comm_connect: bad rank/world");
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     for (int r = 0; r < world; ++r) {
         if (r == rank) { h->comm_peer[r] = h->comm_own; continue; }
         cudaIpcMemHandle_t handle;
         memcpy(&handle, (const char*)ipc_handles + (size_t)r * sizeof handle, sizeof handle);
         void* ptr = nullptr;
-        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess));
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            // close the mappings opened so far: comm_world stays 0, so fn_comm_disconnect would not
+            for (int q = 0; q < r; ++q)
+                if (q != rank && h->comm_peer[q]) cudaIpcCloseMemHandle(h->comm_peer[q]);
+            for (int q = 0; q < FN_MAX_RANKS; ++q) h->comm_peer[q] = nullptr;
+            return fail(FN_ERR_CUDA, "cudaIpcOpenMemHandle of rank %d's mailbox failed: %s", r, cudaGetErrorString(e));
+        }
         h->comm_peer[r] = (Slot*)ptr;
     }
     h->comm_rank = rank; h->comm_world = world; h->comm_seq = 0;
@@ -1374,6 +1666,7 @@ extern "C" int fn_comm_connect(fn_handle* h, int32_t rank, int32_t world, const 
 extern "C" int fn_comm_disconnect(fn_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    leave_resident(h);
     cudaStreamSynchronize(h->stream);
     for (int r = 0; r < h->comm_world; ++r)
         if (r != h->comm_rank && h->comm_peer[r]) cudaIpcCloseMemHandle(h->comm_peer[r]);
@@ -1402,6 +1695,7 @@ extern "C" int fn_transform_upload(fn_handle* h, int64_t n, int32_t m, const dou
     if (c < 1 || c > TR_MAXC || !design) return fail(FN_ERR_UNSUPPORTED, "design has %d columns; 1..%d supported", c, TR_MAXC);
     Design d;
     if (!d.build(m, c, design)) return fail(FN_ERR_ARG, "design (%d x %d) is rank deficient", m, c);
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     std::vector<double> q((size_t)m * c);
@@ -1442,6 +1736,7 @@ extern "C" int fn_transform_sums(fn_handle* h, int32_t order, const double* a, d
     if (order < 1 || order > TR_MAX_ORDER || !a || !sums) return fail(FN_ERR_UNSUPPORTED, "transform order must be 1..%d", TR_MAX_ORDER);
     const int m = h->tr_m;
     for (int i = 0; i < order * m; ++i) if (!(fabs(a[i]) < INFINITY)) return fail(FN_ERR_ARG, "transform parameters must be finite");
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     const int nacc = 2 + m * (1 + 3 * order);
     CUDA_TRY(ensure_buf(h->b_ta, (size_t)order * m * sizeof(double)));
@@ -1454,7 +1749,7 @@ extern "C" int fn_transform_sums(fn_handle* h, int32_t order, const double* a, d
     TransformParams tp;
     tp.n = h->tr_n; tp.m = m; tp.c = h->tr_c; tp.order = order;
     tp.x = (const double*)h->b_tx.p; tp.q = (const double*)h->b_tq.p; tp.a = (const double*)h->b_ta.p;
-    fill_reduce(h, tp.gr, nacc, -1, 0.0, false);
+    fill_reduce(h, tp.gr, tp.sv, nacc, false);
     int k = (m + 31) / 32;
     if (k > 4) k = 8;
     const size_t smem = ((size_t)nacc + 32 * nwarp + 32 * k * TR_MAXC) * sizeof(double);
@@ -1475,6 +1770,7 @@ extern "C" int fn_transform_apply(fn_handle* h, int32_t order, const double* a, 
     if (!h || h->tr_m == 0) return fail(FN_ERR_STATE, "fn_transform_apply needs fn_transform_upload");
     if (order < 1 || order > TR_MAX_ORDER || !a || !col_mean || !y) return fail(FN_ERR_ARG, "fn_transform_apply: bad arguments");
     const int m = h->tr_m;
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t bytes = (size_t)h->tr_n * m * sizeof(double);
     int rc = ensure_scratch(h, bytes ? bytes : 16);

@@ -519,18 +519,24 @@ struct EvalOut {
 FN_HD void eval_zero(EvalOut& o) { o.value = 0.0; o.dv = 0.0; o.ga = 0.0; o.gb = 0.0; o.d2 = NAN; o.p = 0; o.used = 0; }
 
 // value, dv and kappa from (p, ln det S, d2)
+// The terms that depend on (v, p) only come from the tables ec.t0 / ec.t1 when the caller wants
+// complete per-gene values.  The sum over genes does not need them per gene: sum_g t0[p_g] =
+// sum_p N_p t0[p] with N_p the theta-independent histogram of residual df that the preparation
+// kernel counts once per fit, so the evaluation kernels run with ec.t0 == nullptr and the C-ABI
+// layer adds the few table terms on the host (fn_api.cu, table_terms).
 FN_HD double finish_density(const EvalConst& ec, int p, double logdet, double d2, double& dv, double& kappa) {
+    const double t0 = ec.t0 ? ec.t0[p] : 0.0;
     if (ec.is_t) {
         const double v = ec.v;
         const double l1p = log1p(d2 * ec.iv);
         const double hp = 0.5 * (v + p);
         kappa = hp / (v + d2);
-        dv = ec.t1[p] + 0.5 * l1p - kappa * d2 * ec.iv;
-        return ec.t0[p] + 0.5 * logdet + hp * l1p;
+        dv = (ec.t1 ? ec.t1[p] : 0.0) + 0.5 * l1p - kappa * d2 * ec.iv;
+        return t0 + 0.5 * logdet + hp * l1p;
     }
     kappa = 0.5;
     dv = 0.0;
-    return ec.t0[p] + 0.5 * (logdet + d2);
+    return t0 + 0.5 * (logdet + d2);
 }
 
 // KIND_SCALE1: sigma2_j = theta0 / w_prec_j.  All sums are taken at theta = 1 and rescaled;

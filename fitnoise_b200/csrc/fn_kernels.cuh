@@ -31,29 +31,38 @@ struct KernelSet {
     const void* coef;             // coef_kernel<C>
 };
 
-// accumulator layout of one CTA's partial sums
-enum { ACC_VALUE = 0, ACC_DV = 1, ACC_GA = 2, ACC_GB = 3, ACC_USED = 4, ACC_BAD = 5, ACC_FIXED = 6 };
+// accumulator layout of one CTA's partial sums.  ACC_PSUM: sum of the residual df of the genes that
+// contributed -- checked against the preparation kernel's histogram (see StepVars::add_psum).
+enum { ACC_VALUE = 0, ACC_DV = 1, ACC_GA = 2, ACC_GB = 3, ACC_USED = 4, ACC_BAD = 5, ACC_PSUM = 6, ACC_FIXED = 7 };
 
 #define FN_MAX_RANKS 16
 
-// Hand-over slots.  A result value travels together with the sequence number of the evaluation that
-// produced it, as ONE aligned 16-byte store {value, seq}: whoever reads a slot (the host spinning on
-// pinned memory, a peer GPU polling its mailbox) and finds the expected seq has the value too, so no
-// system-scope fence has to separate "data" from "flag" (each such fence over PCIe / NVLink costs
-// microseconds, and the whole evaluation of a small data set takes ~15).
+// Hand-over slots.  A result travels as {bits, tag} with tag = bits ^ seq_mix(seq), written with
+// ONE aligned 16-byte store.  Whoever reads a slot (the host spinning on pinned memory, a peer GPU
+// polling its mailbox) accepts it when (tag ^ bits) == seq_mix(expected seq).  No fence separates
+// "data" from "flag" (each system-scope fence over PCIe / NVLink costs microseconds and a whole
+// small-data evaluation takes ~10), and -- unlike a {value, seq} pair -- nothing depends on the
+// 16-byte store being single-copy atomic, which the PTX memory model does not promise for a vector
+// access: a torn read pairs the bits of one evaluation with the tag of another and fails the
+// check unless both evaluations produced the very same bits, in which case the value is right
+// anyway.  Only 8-byte single-copy atomicity is assumed (guaranteed for aligned accesses).
 struct __align__(16) Slot {
-    double value;
-    unsigned long long seq;
+    unsigned long long bits;
+    unsigned long long tag;
 };
 
+FN_HD unsigned long long seq_mix(unsigned long long seq) { return seq * 0x9E3779B97F4A7C15ull; }   // odd: 0 only for seq 0
+
 __device__ __forceinline__ void slot_store(Slot* s, double value, unsigned long long seq) {
-    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(s), "l"(__double_as_longlong(value)), "l"(seq) : "memory");
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(s), "l"(bits), "l"(bits ^ seq_mix(seq)) : "memory");
 }
-__device__ __forceinline__ Slot slot_load(const Slot* s) {
-    long long v; unsigned long long q;
-    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(q) : "l"(s) : "memory");
-    Slot r; r.value = __longlong_as_double(v); r.seq = q;
-    return r;
+// true (and the value) once the slot carries evaluation `seq`
+__device__ __forceinline__ bool slot_try_load(const Slot* s, unsigned long long seq, double& value) {
+    unsigned long long b, t;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(b), "=l"(t) : "l"(s) : "memory");
+    value = __longlong_as_double((long long)b);
+    return (b ^ t) == seq_mix(seq);
 }
 
 // Cross-GPU exchange fused into the kernel epilogue (multi-GPU, one process per GPU).
@@ -67,7 +76,6 @@ __device__ __forceinline__ Slot slot_load(const Slot* s) {
 struct PeerComm {
     int world, rank;                       // world <= 1: no exchange
     int slot_count;                        // slots per (parity, sender)
-    unsigned long long seq;                // evaluation number, identical on every rank, >= 1
     unsigned long long timeout_ns;         // give up waiting for a peer after this long
     Slot* mailbox[FN_MAX_RANKS];           // mailbox[r]: rank r's mailbox as mapped in this process
 };
@@ -78,10 +86,18 @@ struct GridReduce {
     double* out_dev;         // nacc doubles
     Slot* out_host;          // mapped pinned: nacc slots, or nullptr
     int nacc;
-    int add_index;           // out[add_index] += add_value (theta-independent part of the objective)
-    double add_value;
-    unsigned long long host_seq;   // seq of this launch in the out_host slots
     PeerComm comm;
+};
+
+// What changes from one evaluation to the next (kernel parameters of a one-evaluation launch, the
+// command block of the resident kernel).
+struct StepVars {
+    unsigned long long host_seq;   // seq of this evaluation in the out_host slots
+    unsigned long long comm_seq;   // evaluation number of the exchange, identical on every rank, >= 1
+    int add_on;                    // 1: add the three terms below to this rank's sums before the exchange
+    double add_value;              // theta-independent part of the objective + sum_p N_p t0[p]
+    double add_dv;                 // sum_p N_p t1[p]
+    double add_psum;               // -sum_p p N_p: the exchanged ACC_PSUM total must come out as exactly 0
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -93,7 +109,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Sum `nacc` per-CTA values over the grid in a fixed order; the last CTA to arrive does it, then
 // (multi-GPU) exchanges the sums with the peer GPUs, and finally hands the totals to the host.
 // `vals` is this CTA's shared array of nacc doubles (already complete, visible after a barrier).
-__device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* vals) {
+// Safe to call once per evaluation from a resident kernel: the ticket is back at zero before any
+// total leaves the GPU, and the next evaluation only starts after the host has seen every total.
+__device__ __forceinline__ void grid_reduce(const GridReduce& gr, const StepVars& sv, const double* vals) {
     __shared__ int is_last;
     __shared__ double gsum[256];
     const int T = blockDim.x, nacc = gr.nacc;
@@ -108,25 +126,31 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
     __syncthreads();
     if (!is_last) return;
     FN_STAMP_ANY(8);
+    if (threadIdx.x == 0) *gr.ticket = 0;
     __threadfence();
+    __syncthreads();
     const unsigned int G = gridDim.x;
     const PeerComm& pc = gr.comm;
     const bool exchange = pc.world > 1;
-    const int parity = (int)(pc.seq & 1ull);
+    const int parity = (int)(sv.comm_seq & 1ull);
     // total of component i over the grid, by thread i (nacc <= T) or by a strided loop
     auto publish = [&](int i, double s) {
-        if (i == gr.add_index) s += gr.add_value;
+        if (sv.add_on) {
+            if (i == ACC_VALUE) s += sv.add_value;
+            else if (i == ACC_DV) s += sv.add_dv;
+            else if (i == ACC_PSUM) s += sv.add_psum;
+        }
         if (exchange) {
             const size_t mine = ((size_t)parity * pc.world + pc.rank) * pc.slot_count + i;
-            for (int r = 0; r < pc.world; ++r) slot_store(&pc.mailbox[r][mine], s, pc.seq);
+            for (int r = 0; r < pc.world; ++r) slot_store(&pc.mailbox[r][mine], s, sv.comm_seq);
         } else {
             gr.out_dev[i] = s;
-            if (gr.out_host) slot_store(&gr.out_host[i], s, gr.host_seq);
+            if (gr.out_host) slot_store(&gr.out_host[i], s, sv.host_seq);
         }
     };
     if (nacc * 32 <= T) {
         // one warp per component: lane l adds blocks l, l+32, ... (independent loads), then a shuffle
-        // tree; no shared memory, no barrier.  The usual case (6 accumulators, 256 threads).
+        // tree; no shared memory, no barrier.  The usual case (7 accumulators, 256 threads).
         const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (i < nacc) {
             double s = 0.0;
@@ -156,28 +180,28 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const double* 
             publish(i, s);
         }
     }
-    if (threadIdx.x == 0) *gr.ticket = 0;
     FN_STAMP_ANY(9);
     if (!exchange) return;
 
-    // every component: wait for all senders' slots of this evaluation in my own mailbox, add in rank order
+    // every component: wait for all senders' slots of this evaluation in my own mailbox, add in rank
+    // order.  A peer that never shows up turns EVERY total into NaN, which the host reports as an error.
     for (int i = threadIdx.x; i < nacc; i += T) {
         double s = 0.0;
         bool failed = false;
         const unsigned long long t0 = global_ns();
         for (int r = 0; r < pc.world; ++r) {
             const Slot* slot = &pc.mailbox[pc.rank][((size_t)parity * pc.world + r) * pc.slot_count + i];
-            Slot got = slot_load(slot);
-            while (got.seq != pc.seq) {
+            double got;
+            while (!slot_try_load(slot, sv.comm_seq, got)) {
                 if (global_ns() - t0 > pc.timeout_ns) { failed = true; break; }
-                __nanosleep(64);
-                got = slot_load(slot);
+                __nanosleep(40);
             }
-            s += got.value;
+            if (failed) break;
+            s += got;
         }
         if (failed) s = NAN;
         gr.out_dev[i] = s;
-        if (gr.out_host) slot_store(&gr.out_host[i], s, gr.host_seq);
+        if (gr.out_host) slot_store(&gr.out_host[i], s, sv.host_seq);
     }
 }
 
@@ -257,7 +281,9 @@ struct PrepParams {
     double* cst_out;         // n_pad
     double* avg_out;         // n_pad
     double* gs_out;          // n_pad or nullptr (PATSEQ: avgtail^2)
+    unsigned long long* p_hist;   // m + 1 counters (zeroed by the caller): eligible genes by residual df k - c
     GridReduce gr;
+    StepVars sv;
 };
 
 template <int C>
@@ -271,7 +297,9 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
     tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);
     double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
     double* xc = xn + m * C;
+    unsigned int* hist = (unsigned int*)(xc + m * C);          // m + 1 counters of this CTA
     for (int i = threadIdx.x; i < m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
+    for (int i = threadIdx.x; i <= m; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
 
     const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
@@ -287,8 +315,9 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
         gv.y = (double*)st + (size_t)gl * m;
         gv.aux = p.src.aux ? (double*)(st + L.aux_off) + (size_t)gl * m : nullptr;
         const bool control = (st[L.status_off + gl] & 2) != 0;
+        const int c_real = control ? p.c_ctrl : p.c_noise;
         PrepOut po;
-        prepare_gene<C>(p.fam, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, po);
+        prepare_gene<C>(p.fam, gv, control ? xc : xn, c_real, po);
         if (lane == 0 && gene < p.g.n) {
             p.status_out[gene] = (uint8_t)((po.eligible ? 1 : 0) | (control ? 2 : 0));
             p.cst_out[gene] = po.cst;
@@ -296,11 +325,17 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
             if (p.gs_out) p.gs_out[gene] = po.avg_tail * po.avg_tail;
             if (po.nfinite > 0) { acc[PREP_VARSUM] += po.yss / po.nfinite; acc[PREP_VARCNT] += 1.0; }
             acc[PREP_BAD] += po.bad_counts;
-            if (po.eligible) { acc[PREP_CSTSUM] += po.cst; acc[PREP_ELIG] += 1.0; }
+            if (po.eligible) {
+                acc[PREP_CSTSUM] += po.cst; acc[PREP_ELIG] += 1.0;
+                atomicAdd(&hist[po.k - c_real], 1u);            // 0 < k - c <= m
+            }
         }
     });
+    __syncthreads();
+    for (int i = threadIdx.x; i <= m; i += blockDim.x)
+        if (hist[i]) atomicAdd(&p.p_hist[i], (unsigned long long)hist[i]);
     block_sum<PREP_NACC>(acc, red_out, red_scratch);
-    grid_reduce(p.gr, red_out);
+    grid_reduce(p.gr, p.sv, red_out);
 }
 
 #ifndef FN_WIDTH_ONLY
@@ -308,36 +343,141 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
 __global__ void counts_to_rc_kernel(double* aux, long long total) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
-        aux[i] = 1.0 / fmax(aux[i], 1.0);
+        aux[i] = (aux[i] == aux[i]) ? 1.0 / fmax(aux[i], 1.0) : NAN;       // numpy.maximum keeps NaN: the sample is dropped
 }
 #endif
 
 // ------------------------------------------------------------------------------------------
 // K2 -log likelihood + gradient
 // ------------------------------------------------------------------------------------------
+// The kernel runs in one of two forms:
+//   * one launch = one evaluation (rc.cmd_host == nullptr): theta and the step variables are kernel
+//     parameters;
+//   * RESIDENT (rc.cmd_host != nullptr): launched once per optimisation, it stays on the GPU and
+//     executes one evaluation per COMMAND that the host writes into a block of mapped pinned
+//     memory.  An evaluation then costs no launch call and no launch latency: CTA 0 polls the
+//     command block over PCIe, copies it to device memory and releases a flag the other CTAs spin
+//     on (L2); every CTA already holds its first tiles in shared memory (TileRing, wrap mode).
+//     The kernel leaves on a QUIT command, or by itself after `idle_timeout_ns` without a command
+//     (the host notices and relaunches), so a host that dies or forgets it cannot pin the GPU.
+// Command block (64-bit words; the host writes the sequence number last, the checksum covers every
+// other word, so a half-written block is never accepted):
+enum { CW_SEQ = 0, CW_OP = 1, CW_COMM_SEQ = 2, CW_V = 3, CW_THETA0 = 4, CW_ADD_VALUE = 5, CW_ADD_DV = 6,
+       CW_ADD_PSUM = 7, CW_TA0 = 8, CW_TB0 = 9, CW_TAB = 10 };      // then ntab table words, then the checksum
+enum { OP_EVAL = 1, OP_QUIT = 2, OP_QUIT_IDLE = 3 };
+#define FN_CMD_DEV_PAYLOAD 16       // cmd_dev[0] is the flag (own 128-byte line), the words follow from here
+
+FN_HD unsigned long long cmd_mix(unsigned long long w, int i) {
+    return (w + 0x632BE59BD9B4E019ull) * (0x9E3779B97F4A7C15ull + 2ull * (unsigned long long)i);
+}
+
+struct ResidentCtl {
+    const unsigned long long* cmd_host;   // device pointer of the mapped pinned command block, or nullptr
+    unsigned long long* cmd_dev;          // device memory: flag + copy of the current command
+    unsigned long long* exit_host;        // mapped pinned: set to the expected seq when the kernel leaves on idle
+    unsigned long long next_seq;          // seq of the first command this launch handles
+    unsigned long long idle_timeout_ns;
+    int words;                            // command length in words, checksum included
+};
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Warp 0 of CTA 0: wait for command `expect` in host memory, copy it to cmd_dev and release the flag.
+__device__ __forceinline__ void resident_fetch(const ResidentCtl& rc, unsigned long long expect) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long t0 = global_ns();
+    bool idle = false;
+    for (;;) {
+        unsigned long long s = 0;
+        if (lane == 0) s = ld_sys_u64(rc.cmd_host + CW_SEQ);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s == expect) {
+            unsigned long long sum = 0;
+            for (int i = lane; i < rc.words - 1; i += 32) {
+                const unsigned long long w = ld_sys_u64(rc.cmd_host + i);
+                __stcg(rc.cmd_dev + FN_CMD_DEV_PAYLOAD + i, w);
+                sum += cmd_mix(w, i);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            unsigned long long chk = 0;
+            if (lane == 0) chk = ld_sys_u64(rc.cmd_host + rc.words - 1);
+            chk = __shfl_sync(0xffffffffu, chk, 0);
+            if (sum == chk) break;
+            continue;                                  // the host is still writing: read it again
+        }
+        if (global_ns() - t0 > rc.idle_timeout_ns) { idle = true; break; }
+    }
+    if (idle && lane == 0) {
+        __stcg(rc.cmd_dev + FN_CMD_DEV_PAYLOAD + CW_OP, (unsigned long long)OP_QUIT_IDLE);
+        *rc.exit_host = expect;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_gpu_u64(rc.cmd_dev, expect);
+}
+
+// Every CTA: block until command `expect` is in cmd_dev; returns its opcode (uniform over the CTA).
+__device__ __forceinline__ int resident_wait(const ResidentCtl& rc, unsigned long long expect) {
+    __shared__ int op_s;
+    if (blockIdx.x == 0 && threadIdx.x < 32) resident_fetch(rc, expect);
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = global_ns();
+        int op = -1;
+        while (ld_acquire_gpu_u64(rc.cmd_dev) != expect) {
+            // CTA 0 always publishes within idle_timeout_ns; this bound only matters if CTA 0 is gone
+            if (global_ns() - t0 > rc.idle_timeout_ns + 5000000000ull) { op = OP_QUIT_IDLE; break; }
+            __nanosleep(20);
+        }
+        if (op < 0) op = (int)__ldcg(rc.cmd_dev + FN_CMD_DEV_PAYLOAD + CW_OP);
+        op_s = op;
+    }
+    __syncthreads();
+    const int op = op_s;
+    __syncthreads();
+    return op;
+}
+
 struct EvalParams {
     GeomParams g;
     TileSrc src;             // y, aux (precision weights / rc), gs, cst (per-gene mode only), status
     const double* xn; const double* xc;
     int c_noise, c_ctrl;
     int kind, tail_own, v3, is_t;
-    double v, theta0;
-    const double* ta; const double* tb;     // device tables of length m (general kinds)
+    double v, theta0;        // one-launch form (resident: from the command)
+    double ta0, tb0;         // shared theta_a / theta_b (general kinds); per-sample blocks come from ta / tb
+    const double* ta; const double* tb;     // device tables of length m, or nullptr (shared: ta0 / tb0)
     int inplace_a, inplace_b;               // per-sample theta blocks
     double* pg_score; double* pg_d2; int* pg_p;     // per-gene outputs (nullptr in sum mode)
     GridReduce gr;           // nacc = ACC_FIXED (+ 2m when a block is per-sample)
+    StepVars sv;             // one-launch form
+    ResidentCtl rc;
 };
 
 template <int C, int KIND>
-__global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(256, (C <= 8 ? 2 : 1)) eval_kernel(const EvalParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[FN_MAX_STAGES];
     __shared__ double red_scratch[32 * ACC_FIXED];
     const int m = p.g.m;
+    const bool resident = p.rc.cmd_host != nullptr;
+    const bool per_gene = p.pg_score != nullptr;
     FN_STAMP(0);
     const TileLayout L = tile_layout(p.src);
-    tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);     // first tiles are in flight
-    FN_STAMP(1);
+    TileRing ring;
+    ring_setup(ring, bars, p.g.stages, p.g.n_tiles, resident);
     // tables behind the stage area: xn, xc (m*C each), ta, tb (m each), t0, t1 (m+1 each),
     // vals (ACC_FIXED + 2m), colscr (2*blockDim when a theta block is per-sample)
     double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
@@ -349,127 +489,167 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams p) {
     double* vals = t1 + (m + 1);
     double* colscr = vals + (ACC_FIXED + 2 * m);
     const bool inplace = p.inplace_a || p.inplace_b;
-
     for (int i = threadIdx.x; i < m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        ta[i] = p.ta ? p.ta[i] : 0.0;
-        tb[i] = p.tb ? p.tb[i] : 0.0;
-    }
-    fill_density_tables(p.is_t, p.v, m, t0, t1);
-    FN_STAMP(2);
-
-    EvalConst ec;
-    ec.kind = KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
-    ec.ta = ta; ec.tb = tb; ec.t0 = t0; ec.t1 = t1; ec.finish_setup();
+    __syncthreads();                                   // barrier initialisation + designs visible
+    ring.begin(smem_raw, bars, p.src, L);              // the first tiles are in flight
+    FN_STAMP(1);
 
     const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
     GeneView gv;
     gv.setup(m, lane, p.g.lpg, gl);
-    double acc[ACC_FIXED];
-#pragma unroll
-    for (int i = 0; i < ACC_FIXED; ++i) acc[i] = 0.0;
     // per-sample gradient columns: thread (sub, col) sums column col over genes sub, sub+nsub, ...
     const int nsub = inplace ? blockDim.x / m : 0;
     const int col = inplace ? threadIdx.x % m : 0, sub = inplace ? threadIdx.x / m : 0;
-    double col_a = 0.0, col_b = 0.0;
 
-    // accumulate one finished gene into the thread's partial sums / the per-gene outputs
-    auto account = [&](const EvalOut& eo, long long gene) {
-        if (gene >= p.g.n) return;
-        if (eo.used) {
-            if (eo.value == eo.value) {
-                acc[ACC_VALUE] += eo.value; acc[ACC_DV] += eo.dv;
-                acc[ACC_GA] += eo.ga; acc[ACC_GB] += eo.gb; acc[ACC_USED] += 1.0;
-            } else {
-                acc[ACC_BAD] += 1.0;
+    unsigned long long expect = p.rc.next_seq;
+    for (;;) {
+        // ---- this evaluation's theta and step variables -----------------------------------
+        EvalConst ec;
+        StepVars sv;
+        const double* tab_src_a = p.ta;
+        const double* tab_src_b = p.tb;
+        double ta0 = p.ta0, tb0 = p.tb0;
+        if (resident) {
+            if (resident_wait(p.rc, expect) != OP_EVAL) break;
+            const unsigned long long* w = p.rc.cmd_dev + FN_CMD_DEV_PAYLOAD;
+            ec.v = __longlong_as_double((long long)__ldcg(w + CW_V));
+            ec.theta0 = __longlong_as_double((long long)__ldcg(w + CW_THETA0));
+            sv.host_seq = expect;
+            sv.comm_seq = __ldcg(w + CW_COMM_SEQ);
+            sv.add_on = 1;
+            sv.add_value = __longlong_as_double((long long)__ldcg(w + CW_ADD_VALUE));
+            sv.add_dv = __longlong_as_double((long long)__ldcg(w + CW_ADD_DV));
+            sv.add_psum = __longlong_as_double((long long)__ldcg(w + CW_ADD_PSUM));
+            ta0 = __longlong_as_double((long long)__ldcg(w + CW_TA0));
+            tb0 = __longlong_as_double((long long)__ldcg(w + CW_TB0));
+            if (p.ta) tab_src_a = (const double*)(w + CW_TAB);
+            if (p.tb) tab_src_b = (const double*)(w + CW_TAB) + (p.ta ? m : 0);
+        } else {
+            ec.v = p.v; ec.theta0 = p.theta0;
+            sv = p.sv;
+        }
+        if (KIND != KIND_SCALE1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                ta[i] = tab_src_a ? __ldcg(tab_src_a + i) : ta0;
+                tb[i] = tab_src_b ? __ldcg(tab_src_b + i) : tb0;
             }
         }
-        if (p.pg_score) {
-            p.pg_score[gene] = eo.used ? eo.value : NAN;
-            p.pg_d2[gene] = eo.d2;
-            p.pg_p[gene] = eo.p;
-        }
-    };
+        if (per_gene) fill_density_tables(p.is_t, ec.v, m, t0, t1);      // ends with a barrier
+        else if (KIND != KIND_SCALE1) __syncthreads();
+        FN_STAMP(2);
+        ec.kind = KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t;
+        ec.ta = ta; ec.tb = tb;
+        ec.t0 = per_gene ? t0 : nullptr; ec.t1 = per_gene ? t1 : nullptr;
+        ec.finish_setup();
 
-    if constexpr (KIND == KIND_SCALE1) {
-        // The lpg lanes of a gene all end the sweep holding the same (p, d2).  Instead of every
-        // lane running the density tail (log1p, divisions) for the same gene, lane l keeps the
-        // gene of every lpg-th tile and the tail runs once per lpg tiles with all 32 lanes of a
-        // warp working on different genes.
-        Scale1Mid pend;
-        pend.state = 0; pend.d2 = 0.0; pend.det_a = 1.0; pend.p = 0;
-        double pend_cst = 0.0;
-        long long pend_gene = -1;
-        int sel = 0;
-        auto finalize = [&]() {
-            if (pend_gene >= 0) {
-                EvalOut eo;
-                scale1_finish(ec, pend, pend_cst, eo);
-                account(eo, pend_gene);
-                pend_gene = -1;
-            }
-        };
-        tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, false, [&](unsigned char* st, long long tile) {
-            gv.y = (double*)st + gl * m;
-            gv.aux = p.src.aux ? (double*)(st + L.aux_off) + gl * m : nullptr;
-            const uint8_t status = st[L.status_off + gl];
-            const bool control = (status & 2) != 0;
-            Scale1Mid mid;
-            scale1_sweep<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, (status & 1) != 0, mid);
-            if (lane == sel) {
-                pend = mid;
-                pend_cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
-                pend_gene = tile * p.g.genes + gl;
-            }
-            if (++sel == p.g.lpg) { sel = 0; finalize(); }
-        });
-        FN_STAMP(3);
-        finalize();
-        FN_STAMP(4);
-    } else {
-    // PATSEQ keeps 1/sigma2 in the aux tile between its two sweeps: the stage is always written
-    tile_loop(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles, inplace || KIND == KIND_PATSEQ, [&](unsigned char* st, long long tile) {
-        const long long gene = tile * p.g.genes + gl;
-        double* ys = (double*)st;
-        double* auxs = (double*)(st + L.aux_off);
-        gv.y = ys + (size_t)gl * m;
-        gv.aux = p.src.aux ? auxs + (size_t)gl * m : nullptr;
-        gv.gs = p.src.gs ? ((const double*)(st + L.gs_off))[gl] : 0.0;
-        const uint8_t status = st[L.status_off + gl];
-        const bool control = (status & 2) != 0;
-        const bool eligible = (status & 1) != 0;
-        const double cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
-        EvalOut eo;
-        eval_general<C, KIND>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst,
-                              p.inplace_a != 0, p.inplace_b != 0, eo);
-        if (lane == 0) account(eo, gene);
-        if (inplace) {
-            __syncthreads();
-            if (sub < nsub) {
-                for (int g = sub; g < p.g.genes; g += nsub) {
-                    if (p.inplace_a) col_a += ys[(size_t)g * m + col];
-                    if (p.inplace_b) col_b += auxs[(size_t)g * m + col];
+        double acc[ACC_FIXED];
+#pragma unroll
+        for (int i = 0; i < ACC_FIXED; ++i) acc[i] = 0.0;
+        double col_a = 0.0, col_b = 0.0;
+
+        // accumulate one finished gene into the thread's partial sums / the per-gene outputs
+        auto account = [&](const EvalOut& eo, long long gene) {
+            if (gene >= p.g.n) return;
+            if (eo.used) {
+                if (eo.value == eo.value) {
+                    acc[ACC_VALUE] += eo.value; acc[ACC_DV] += eo.dv;
+                    acc[ACC_GA] += eo.ga; acc[ACC_GB] += eo.gb; acc[ACC_USED] += 1.0;
+                    acc[ACC_PSUM] += (double)eo.p;
+                } else {
+                    acc[ACC_BAD] += 1.0;
                 }
             }
-        }
-    });
-    }
+            if (per_gene) {
+                p.pg_score[gene] = eo.used ? eo.value : NAN;
+                p.pg_d2[gene] = eo.d2;
+                p.pg_p[gene] = eo.p;
+            }
+        };
 
-    block_sum<ACC_FIXED>(acc, vals, red_scratch);
-    FN_STAMP(5);
-    if (inplace) {
-        colscr[threadIdx.x] = col_a;
-        colscr[blockDim.x + threadIdx.x] = col_b;
-        __syncthreads();
-        if (threadIdx.x < m) {
-            double sa = 0.0, sb = 0.0;
-            for (int s = 0; s < nsub; ++s) { sa += colscr[s * m + threadIdx.x]; sb += colscr[blockDim.x + s * m + threadIdx.x]; }
-            vals[ACC_FIXED + threadIdx.x] = sa;
-            vals[ACC_FIXED + m + threadIdx.x] = sb;
+        if constexpr (KIND == KIND_SCALE1) {
+            // The lpg lanes of a gene all end the sweep holding the same (p, d2).  Instead of every
+            // lane running the density tail (log1p, divisions) for the same gene, lane l keeps the
+            // gene of every lpg-th tile and the tail runs once per lpg tiles with all 32 lanes of a
+            // warp working on different genes.
+            Scale1Mid pend;
+            pend.state = 0; pend.d2 = 0.0; pend.det_a = 1.0; pend.p = 0;
+            double pend_cst = 0.0;
+            long long pend_gene = -1;
+            int sel = 0;
+            auto finalize = [&]() {
+                if (pend_gene >= 0) {
+                    EvalOut eo;
+                    scale1_finish(ec, pend, pend_cst, eo);
+                    account(eo, pend_gene);
+                    pend_gene = -1;
+                }
+            };
+            ring.pass(smem_raw, bars, p.src, L, false, [&](unsigned char* st, long long tile) {
+                gv.y = (double*)st + gl * m;
+                gv.aux = p.src.aux ? (double*)(st + L.aux_off) + gl * m : nullptr;
+                const uint8_t status = st[L.status_off + gl];
+                const bool control = (status & 2) != 0;
+                Scale1Mid mid;
+                scale1_sweep<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, (status & 1) != 0, mid);
+                if (lane == sel) {
+                    pend = mid;
+                    pend_cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
+                    pend_gene = tile * p.g.genes + gl;
+                }
+                if (++sel == p.g.lpg) { sel = 0; finalize(); }
+            });
+            FN_STAMP(3);
+            finalize();
+            FN_STAMP(4);
+        } else {
+            // PATSEQ keeps 1/sigma2 in the aux tile between its two sweeps: the stage is always written
+            ring.pass(smem_raw, bars, p.src, L, inplace || KIND == KIND_PATSEQ, [&](unsigned char* st, long long tile) {
+                const long long gene = tile * p.g.genes + gl;
+                double* ys = (double*)st;
+                double* auxs = (double*)(st + L.aux_off);
+                gv.y = ys + (size_t)gl * m;
+                gv.aux = p.src.aux ? auxs + (size_t)gl * m : nullptr;
+                gv.gs = p.src.gs ? ((const double*)(st + L.gs_off))[gl] : 0.0;
+                const uint8_t status = st[L.status_off + gl];
+                const bool control = (status & 2) != 0;
+                const bool eligible = (status & 1) != 0;
+                const double cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
+                EvalOut eo;
+                eval_general<C, KIND>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst,
+                                      p.inplace_a != 0, p.inplace_b != 0, eo);
+                if (lane == 0) account(eo, gene);
+                if (inplace) {
+                    __syncthreads();
+                    if (sub < nsub) {
+                        for (int g = sub; g < p.g.genes; g += nsub) {
+                            if (p.inplace_a) col_a += ys[(size_t)g * m + col];
+                            if (p.inplace_b) col_b += auxs[(size_t)g * m + col];
+                        }
+                    }
+                }
+            });
         }
-        __syncthreads();
+
+        block_sum<ACC_FIXED>(acc, vals, red_scratch);
+        FN_STAMP(5);
+        if (inplace) {
+            colscr[threadIdx.x] = col_a;
+            colscr[blockDim.x + threadIdx.x] = col_b;
+            __syncthreads();
+            if (threadIdx.x < m) {
+                double sa = 0.0, sb = 0.0;
+                for (int q = 0; q < nsub; ++q) { sa += colscr[q * m + threadIdx.x]; sb += colscr[blockDim.x + q * m + threadIdx.x]; }
+                vals[ACC_FIXED + threadIdx.x] = sa;
+                vals[ACC_FIXED + m + threadIdx.x] = sb;
+            }
+            __syncthreads();
+        }
+        grid_reduce(p.gr, sv, vals);
+        if (!resident) break;
+        __syncthreads();             // vals / scratch are reused by the next evaluation
+        ++expect;
     }
-    grid_reduce(p.gr, vals);
+    ring.drain(bars);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -484,6 +664,7 @@ struct EvalFactorsParams {
     double v, theta0;
     double* pg_score; double* pg_d2; int* pg_p;
     GridReduce gr;           // nacc = ACC_FIXED + m * nf  (d/dF follows the fixed accumulators)
+    StepVars sv;
 };
 
 template <int C>
@@ -502,11 +683,13 @@ __global__ void __launch_bounds__(256) eval_factors_kernel(const EvalFactorsPara
     double* colscr = vals + (ACC_FIXED + ncol);
     double* gscr = colscr + blockDim.x;              // genes x m x nf: d/dF terms of the current tile
     for (int i = threadIdx.x; i < m * C; i += blockDim.x) { zn[i] = p.zn[i]; zc[i] = p.zc[i]; }
-    fill_density_tables(p.is_t, p.v, m, t0, t1);
+    const bool per_gene = p.pg_score != nullptr;
+    if (per_gene) fill_density_tables(p.is_t, p.v, m, t0, t1);
+    else __syncthreads();
 
     EvalConst ec;
     ec.kind = KIND_SCALE1; ec.tail_own = 0; ec.v3 = 0; ec.is_t = p.is_t; ec.v = p.v; ec.theta0 = p.theta0;
-    ec.ta = nullptr; ec.tb = nullptr; ec.t0 = t0; ec.t1 = t1; ec.finish_setup();
+    ec.ta = nullptr; ec.tb = nullptr; ec.t0 = per_gene ? t0 : nullptr; ec.t1 = per_gene ? t1 : nullptr; ec.finish_setup();
 
     const int gl = threadIdx.x / p.g.lpg, lane = threadIdx.x % p.g.lpg;
     GeneView gv;
@@ -533,6 +716,7 @@ __global__ void __launch_bounds__(256) eval_factors_kernel(const EvalFactorsPara
             if (eo.used) {
                 if (eo.value == eo.value) {
                     acc[ACC_VALUE] += eo.value; acc[ACC_DV] += eo.dv; acc[ACC_GA] += eo.ga; acc[ACC_USED] += 1.0;
+                    acc[ACC_PSUM] += (double)eo.p;
                 } else {
                     acc[ACC_BAD] += 1.0;
                 }
@@ -557,7 +741,7 @@ __global__ void __launch_bounds__(256) eval_factors_kernel(const EvalFactorsPara
         vals[ACC_FIXED + threadIdx.x] = s;
     }
     __syncthreads();
-    grid_reduce(p.gr, vals);
+    grid_reduce(p.gr, p.sv, vals);
 }
 
 #ifndef FN_WIDTH_ONLY

@@ -137,4 +137,75 @@ __device__ __forceinline__ void tile_loop(unsigned char* smem, uint64_t* bars, i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tile ring with state that outlives one pass over the CTA's tiles (the resident evaluation kernel).
+//
+// The CTA's tiles are b, b+G, ... (`cnt` of them).  `pass()` consumes them once.  With `wrap` the
+// producer keeps running ahead ACROSS passes: while the tail of pass k is consumed, the first
+// stages-1 tiles of pass k+1 are already being copied -- they are theta-independent input -- so
+// a resident kernel that waits for its next command finds its first tiles in shared memory when the
+// command arrives.  Without `wrap` a pass issues exactly its own tiles (the one-launch-per-
+// evaluation form; `begin()` must then be called before every pass).
+// ------------------------------------------------------------------------------------------
+struct TileRing {
+    int slot, pre;           // slot to consume next; slot consumed last (the one the producer refills)
+    uint32_t parity;         // phase parity of `slot`
+    long long cnt;           // tiles of this CTA per pass
+    long long first, step;   // tile index of the CTA's first tile, distance between its tiles
+    int stages;
+    bool wrap;
+
+    __device__ __forceinline__ long long tile_at(long long i) const { return first + (i % cnt) * step; }
+
+    // all threads; barriers must have been initialised (mbar_init + fence) and published by a __syncthreads
+    __device__ __forceinline__ void begin(unsigned char* smem, uint64_t* bars, const TileSrc& src, const TileLayout& L) {
+        if (threadIdx.x == 0 && cnt > 0) {
+            for (int s = 0; s < stages - 1; ++s) {
+                if (!wrap && s >= cnt) break;
+                const int sl = (slot + s) % stages;
+                tile_issue(src, L, smem + (size_t)sl * L.stage_bytes, &bars[sl], tile_at(s));
+            }
+        }
+    }
+
+    template <class Body>
+    __device__ __forceinline__ void pass(unsigned char* smem, uint64_t* bars, const TileSrc& src, const TileLayout& L,
+                                         bool wrote_smem, Body body) {
+        for (long long i = 0; i < cnt; ++i) {
+            if (threadIdx.x == 0) {
+                const long long ahead = i + (long long)(stages - 1);
+                if (wrap || ahead < cnt) tile_issue(src, L, smem + (size_t)pre * L.stage_bytes, &bars[pre], tile_at(ahead));
+            }
+            mbar_wait(&bars[slot], parity);
+            body(smem + (size_t)slot * L.stage_bytes, first + i * step);
+            if (wrote_smem) fence_proxy_async();
+            __syncthreads();
+            pre = slot;
+            if (++slot == stages) { slot = 0; parity ^= 1u; }
+        }
+    }
+
+    // wrap mode, before the CTA exits: wait for the copies that are still in flight (stages-1 tiles)
+    __device__ __forceinline__ void drain(uint64_t* bars) {
+        if (!wrap || cnt <= 0) return;
+        int sl = slot;
+        uint32_t par = parity;
+        for (int s = 0; s < stages - 1; ++s) {
+            mbar_wait(&bars[sl], par);
+            if (++sl == stages) { sl = 0; par ^= 1u; }
+        }
+    }
+};
+
+__device__ __forceinline__ void ring_setup(TileRing& r, uint64_t* bars, int stages, long long n_tiles, bool wrap) {
+    r.slot = 0; r.pre = stages - 1; r.parity = 0; r.stages = stages; r.wrap = wrap;
+    r.first = blockIdx.x; r.step = gridDim.x;
+    r.cnt = (long long)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+}
+
 }  // namespace fn

@@ -29,6 +29,7 @@ struct TransformParams {
     const double* q;        // m x c orthonormal design basis (device)
     const double* a;        // order x m polynomial coefficients (device)
     GridReduce gr;          // nacc = 2 + m (1 + 3 order): [Syy, Stt, s[m], A[order][m], B[order][m], D[order][m]]
+    StepVars sv;
 };
 
 // K = samples per lane = ceil(m / 32); C = design columns (template width)
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256, (K * ORDER > 9 ? 1 : 2)) transform_kernel
         }
     }
     (void)nacc;
-    grid_reduce(p.gr, vals);
+    grid_reduce(p.gr, p.sv, vals);
 }
 
 // y = ln(P(x)) / (order ln 2) - column mean   (fittransform.py:161-163)

@@ -12,6 +12,7 @@ Noise-model plug-ins keep the reference's interface (``_unpack``, ``_describe_no
 descriptor the kernels consume.  A subclass that overrides ``_get_dist`` without a ``_family`` is
 rejected -- there is no per-gene Python/CPU fallback.
 """
+import contextlib
 import sys
 
 import numpy as np
@@ -84,19 +85,21 @@ def _row_means(y):
     return np.where(count > 0, total / np.maximum(count, 1), np.nan)
 
 
-def _optimize(value_grad, initial, bounds, verbose):
+def _optimize(value_grad, initial, bounds, verbose, session=None):
     """The reference's driver loop (fitnoise.py:143-158): L-BFGS-B with analytic gradient and
-    ftol = gtol = 1e-12, restarted from the optimum until it moves by less than 1e-6."""
+    ftol = gtol = 1e-12, restarted from the optimum until it moves by less than 1e-6.  For the
+    duration of the loop the session keeps its evaluation kernel resident on the GPU."""
     initial = np.asarray(initial, dtype="float64")
-    while True:
-        result = scipy.optimize.minimize(
-            value_grad, initial, method="L-BFGS-B", jac=True, bounds=bounds,
-            options=dict(ftol=1e-12, gtol=1e-12))
-        if verbose:
-            print(result)
-        if np.all(np.abs(result.x - initial) < 1e-6):
-            return result
-        initial = result.x
+    with (session.resident() if session is not None else contextlib.nullcontext()):
+        while True:
+            result = scipy.optimize.minimize(
+                value_grad, initial, method="L-BFGS-B", jac=True, bounds=bounds,
+                options=dict(ftol=1e-12, gtol=1e-12))
+            if verbose:
+                print(result)
+            if np.all(np.abs(result.x - initial) < 1e-6):
+                return result
+            initial = result.x
 
 
 class Model(Withable):
@@ -235,7 +238,7 @@ class Model(Withable):
             fit = Withable()._with(x=np.zeros(0), fun=0.0)
         else:
             assert np.all(np.isfinite(initial)), "initial hyper-parameters are not finite"
-            fit = _optimize(value_grad, initial, result._bounds, verbose)
+            fit = _optimize(value_grad, initial, result._bounds, verbose, session)
         param = result._unpack(as_vector(fit.x))
         if verbose:
             print("Model cost:", result._model_cost(param))

@@ -16,6 +16,26 @@ def _give_back(engine, pooled):
         engine.close()
 
 
+class _Resident(object):
+    def __init__(self, session):
+        self.session, self.on = session, False
+
+    def __enter__(self):
+        s = self.session
+        usable = (hasattr(s.local, "resident_begin") and s.family.nf == 0 and s.P > 0
+                  and (s.world == 1 or s._fused) and not os.environ.get("FN_NO_RESIDENT"))
+        if usable:
+            s.local.resident_begin()
+            self.on = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.on and self.session.local is not None:
+            self.session.local.resident_end()
+        self.on = False
+        return False
+
+
 class Session(object):
     """``local`` is this rank's evaluator.  By default a ``_native.Engine`` (CUDA; raises without
     a GPU).  Tests of the sharding logic on a CPU-only box pass their own stand-in through
@@ -114,6 +134,14 @@ class Session(object):
         self._finalizer()
 
     # ---- likelihood -----------------------------------------------------------------------
+    def resident(self):
+        """Context manager for a run of nll_grad calls (the optimiser loop): keeps ONE evaluation
+        kernel resident on the GPU so that an evaluation costs no kernel launch (fn_resident_begin).
+        Used when this rank's kernel produces the global totals by itself (one GPU, or the fused
+        exchange); a no-op for factor models and for the kernel + ncclAllReduce path -- a collective
+        could not run beside a kernel that occupies every SM."""
+        return _Resident(self)
+
     def nll_grad(self, theta, factors=None):
         """Global (all ranks) value and gradient of the REML objective at theta:
         (value, grad, grad_factors | None, n_used, n_bad).  ``factors``: m x nf matrix of the factor

@@ -13,8 +13,10 @@
  *     fails.
  *   - a handle owns one GPU's shard of the genes (device memory, stream, pinned result buffer).
  *     One host thread per handle.  Multi-GPU: one handle per process/GPU, genes sharded by the
- *     caller; the per-evaluation sums of all shards are added by the caller (NCCL allreduce of
- *     1+P doubles over fn_nll_grad_dev output, see fitnoise_b200/parallel.py).
+ *     caller.  After fn_comm_mailbox / fn_comm_connect the per-evaluation sums of all shards are
+ *     added inside the evaluation kernel itself (peer stores over NVLink) and fn_nll_grad returns
+ *     the totals over all ranks; without them the caller adds the shards' sums (e.g. an NCCL
+ *     all-reduce of the P+3 doubles fn_nll_grad_dev leaves in device memory).
  */
 #ifndef FITNOISE_B200_H
 #define FITNOISE_B200_H
@@ -57,6 +59,8 @@ typedef struct fn_prep_info {
 const char* fn_last_error(void);
 int fn_device_count(void);
 const char* fn_version(void);
+/* hash of the sources the library was built from (the binding refuses a stale binary) */
+const char* fn_source_hash(void);
 
 /* One handle per GPU.  `stream` is a cudaStream_t to launch on (e.g. torch's current stream) or
  * NULL for a stream owned by the handle. */
@@ -86,6 +90,18 @@ int fn_upload_dev(fn_handle* h, int64_t n, int32_t m, const double* y_dev, const
  * n_used / n_bad (may be NULL): genes that contributed / that produced a non-finite term. */
 int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double* value, double* grad,
                 int64_t* n_used, int64_t* n_bad);
+/* Resident evaluation: between fn_resident_begin and fn_resident_end ONE kernel stays on the GPU and
+ * fn_nll_grad hands it each theta through a command block in mapped pinned memory -- no kernel
+ * launch and no launch latency per evaluation (what the optimiser loop of fitnoise.py:143-158 needs:
+ * tens of evaluations of a few microseconds each).  Results are identical to the one-launch form.
+ * Any other entry point ends the resident phase by itself; the kernel also leaves on its own after
+ * FN_RESIDENT_IDLE_MS (default 20) without a command and is relaunched transparently by the next
+ * fn_nll_grad.  Not for factor models.  While resident the handle's GPU runs nothing else. */
+int fn_resident_begin(fn_handle* h);
+int fn_resident_end(fn_handle* h);
+/* returns 1 while resident; launches = resident kernels started, evaluations = commands executed */
+int64_t fn_resident_stats(fn_handle* h, int64_t* launches, int64_t* evaluations);
+
 /* Asynchronous form for multi-GPU: leaves [value, grad[0..P-1], n_used, n_bad] (P+3 doubles) in
  * device memory at out_dev on the handle's stream, for the caller to allreduce.  No host sync. */
 int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, double* out_dev);

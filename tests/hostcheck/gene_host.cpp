@@ -38,7 +38,7 @@ void prepare_all(const Family& fam, long n, int m, const double* y, const double
         if (po.nfinite > 0) { vsum += po.yss / po.nfinite; ++vcount; }
         if (fam.kind == KIND_PATSEQ) {
             pr.gs[g] = po.avg_tail * po.avg_tail;
-            for (int j = 0; j < m; ++j) pr.aux[g * m + j] = 1.0 / fmax(aux_raw[g * m + j], 1.0);
+            for (int j = 0; j < m; ++j) { const double cnt = aux_raw[g * m + j]; pr.aux[g * m + j] = (cnt == cnt) ? 1.0 / fmax(cnt, 1.0) : NAN; }
         } else if (aux_raw) {
             for (int j = 0; j < m; ++j) pr.aux[g * m + j] = aux_raw[g * m + j];
         }
