@@ -5,22 +5,36 @@
 
 Metric (BASELINE.json): gene-likelihood-evals/sec.  A *step* is ONE evaluation of the REML
 objective and its gradient over every gene of the workload (what the optimiser calls per proposed
-theta; reference fitnoise.py:125-136).  Workload at N = 1: BASELINE.json configs[4], 1,000,000
-genes x 96 samples, two-group design, on one GPU; the likelihood-and-gradient evaluation is timed
-with Model_t (P = 2) because the literal Model_independent has no hyper-parameters and never
-evaluates a likelihood; the literal Model_independent fit + test wall time is reported
-beside it under "fit_test".  With N > 1 (torchrun, one rank per GPU) every rank holds its own
-1M x 96 shard (weak scaling) and each step ends with the sum of the P+3 partial results over the
-ranks: fused into the kernel epilogue over NVLink peer memory (default), or kernel + ncclAllReduce
-(FN_REDUCE=nccl, also the fallback when peer mapping is unavailable).
+theta; reference fitnoise.py:125-136).  Workload: BASELINE.json configs[4], 1,000,000 genes x 96
+samples IN TOTAL, two-group design; under torchrun the genes are sharded over the N ranks (STRONG
+scaling: 1M / N genes per GPU) and each step ends with the sum of the P+4 partial results over
+the ranks, fused into the kernel epilogue over NVLink peer memory (FN_REDUCE=nccl: kernel +
+ncclAllReduce, also the fallback when peer mapping is unavailable).  The likelihood-and-gradient
+evaluation is timed with Model_t (P = 2) because the literal Model_independent has no
+hyper-parameters and never evaluates a likelihood; the literal Model_independent (and
+Model_t) fit + test wall times are reported beside it under "fit_test" for 1M x 96 and 20k x 6.
 
-`value`   : genes of all ranks / device time per step, inputs resident in HBM (y is 768 MB per GPU,
-            six times the L2, so every step streams from DRAM; no extra L2 flush needed).
-`e2e`     : the same through the C-ABI with HOST buffers: every step copies the step's y from pinned
-            host memory (fn_upload: H2D + preparation kernel), evaluates, and reads the result back.
+`value`   : 1M genes / device time per step, inputs resident in HBM.  The K steps run the way the
+            optimiser runs them: through fn_nll_grad while the evaluation kernel is RESIDENT on the
+            GPU (fn_resident_begin .. fn_resident_end inside the timed region: one kernel launch for
+            the K evaluations, each evaluation a command in mapped pinned memory).
+`l2`      : at N = 1 the 768 MB of y are six times the L2, every step streams from DRAM.  At N >= 8
+            a shard (96 MB) fits the 126 MB L2: `value` is then L2-assisted (the real steady state
+            of the optimiser loop) and says so; `flushed` repeats the steps with an L2 flush (sweep
+            of a 2 x L2 buffer) before every step, timed per step on the host clock.
+`weak`    : (N > 1) the same step with 1M genes PER GPU (weak scaling), secondary.
+`e2e`     : the same metric through the C-ABI with HOST buffers: every step copies the rank's shard
+            of y from pinned host memory (fn_upload: H2D + preparation kernel), evaluates, and
+            reads the result back.
 `roofline`: algorithmic bytes of the nll+grad kernel (8 m + 1 per gene: the y row and the status
-            byte) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
-`cpu_baseline`: the oracle port (the reference's per-gene numpy algorithm) on a bounded gene sample.
+            byte) / its CUDA-event duration (one launch per evaluation, this rank's
+            shard), against MEASURED_PEAKS.json hbm_gbs; `per_step`: the same bytes over all ranks
+            / ms_per_step / (N x peak) -- the north-star fraction "per evaluation".
+`exchange_check`: (N > 1) the fused totals against an NCCL all-reduce of the per-rank sums, and the
+            objective value itself (the data is the same for every N: 8 seeded blocks).
+`cpu_baseline` / --impl reference: the reference's OWN numpy scorer (oracle/_ref: the py3-patched
+            copy of fitnoise/{env,distributions,fitnoise,p_adjust}.py written by
+            __graft_entry__.build()) on a bounded gene sample of the same workload.
 """
 import argparse
 import json
@@ -35,22 +49,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_GENES = int(os.environ.get("FN_BENCH_GENES", 1000000))
+N_TOTAL = int(os.environ.get("FN_BENCH_GENES", 1000000))
 M = 96
+BLOCKS = 8                      # the data set is 8 seeded blocks: identical for N = 1, 2, 4, 8
 THETA = np.array([8.0, 1.1])
-WORKLOAD = "cfg5: %d genes x %d samples per GPU, 2-group design, Model_t likelihood+gradient evaluation" % (N_GENES, M)
+WORKLOAD = ("cfg5: %d genes x %d samples in total, 2-group design, Model_t likelihood+gradient "
+            "evaluation, genes sharded over the ranks" % (N_TOTAL, M))
+L2_BYTES = 126 * (1 << 20)
 
 
-def design_matrix():
-    return np.array([[1.0, 0.0]] * (M // 2) + [[1.0, 1.0]] * (M // 2))
+def design_matrix(m=M):
+    return np.array([[1.0, 0.0]] * (m // 2) + [[1.0, 1.0]] * (m - m // 2))
 
 
-def measured_traffic():
+def measured_traffic(n_local):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        if t.get("genes") == N_GENES and t.get("samples") == M:
+        if t.get("genes") == n_local and t.get("samples") == M:
             return float(t["dram_bytes_per_launch"])
     except Exception:
         pass
@@ -120,38 +137,84 @@ class ClockSampler(object):
         return out
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank's host threads (and therefore allocate its pinned buffers, first touch) on the
+    NUMA node its GPU hangs off: eight ranks pulling their shards from one node's memory is what
+    capped the round-1 e2e figure.  Best effort; returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:             # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's per-gene algorithm
+# CPU arm: the reference's own numpy scorer (oracle/_ref); the oracle port if _ref is missing
 # --------------------------------------------------------------------------------------------
 def _cpu_chunk(args):
-    seed, genes = args
+    seed, genes, calls = args
     os.environ["OMP_NUM_THREADS"] = "1"
-    from oracle import fitnoise_oracle as oracle
     rng = np.random.default_rng(seed)
     y = rng.normal(size=(genes, M)) * np.sqrt(10.0 / rng.chisquare(10.0, size=(genes, 1)))
     design = design_matrix()
+    from oracle import make_ref
+    if make_ref.load() is not None:
+        from oracle import ref_timing
+        seconds, value = ref_timing.score_seconds(y, design, THETA, calls=calls)
+        return seconds, value, "reference"
+    from oracle import fitnoise_oracle as oracle
     cfg = oracle.Configured("Model_t", y)
     prepared = oracle.prepare_rows(cfg, [design] * genes)       # fitnoise.py:23-35 (not timed: done once per fit)
     t0 = time.perf_counter()
-    value, grad = oracle.total_score_grad(cfg, prepared, THETA)  # one objective + gradient evaluation
-    return time.perf_counter() - t0, value
+    for _ in range(calls):
+        value, grad = oracle.total_score_grad(cfg, prepared, THETA)
+    return (time.perf_counter() - t0) / calls, value, "port"
 
 
-def cpu_evals_per_sec(cores, genes_per_core, pool=None):
-    """Gene-likelihood evaluations per second of the oracle port on `cores` processes."""
+def cpu_evals_per_sec(cores, genes_per_core, pool=None, calls=1):
+    """Gene-likelihood evaluations per second on `cores` processes, and which implementation ran."""
     if cores == 1:
-        dt, _ = _cpu_chunk((1, genes_per_core))
-        return genes_per_core / dt
-    res = pool.map(_cpu_chunk, [(100 + i, genes_per_core) for i in range(cores)])
+        dt, _, kind = _cpu_chunk((1, genes_per_core, calls))
+        return genes_per_core / dt, kind
+    res = pool.map(_cpu_chunk, [(100 + i, genes_per_core, calls) for i in range(cores)])
     # per-process evaluation time excludes data generation and the one-off QR prep
     slowest = max(r[0] for r in res)
-    return cores * genes_per_core / slowest
+    return cores * genes_per_core / slowest, res[0][2]
+
+
+def cpu_sample_text(kind, cores, genes_per_core):
+    what = ("the reference's own numpy scorer `score` (fitnoise.py:63-71, value only; its gradient costs the "
+            "reference 1+P such calls)" if kind == "reference" else
+            "the oracle port's objective+gradient (per-gene numpy loop: inv/det of the 94x94 covariance)")
+    return "%d genes x %d samples per step (%d process(es) x %d genes) of the cfg5 workload, one call of %s" % (
+        cores * genes_per_core, M, cores, genes_per_core, what)
 
 
 def run_reference(args):
-    """The reference arm: the oracle port of the reference's CPU algorithm (the reference itself is
-    Python-2 source and cannot travel to the GPU box) on all host cores, each
-    step one objective+gradient evaluation over a bounded sample of the workload's genes."""
+    """The reference arm: the reference's own CPU implementation of the path on all host cores, each
+    step one objective evaluation over a bounded sample of the workload's genes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -161,12 +224,14 @@ def run_reference(args):
     genes_per_core = int(os.environ.get("FN_REF_GENES_PER_CORE", 1500))
     import multiprocessing as mp
     pool = mp.get_context("spawn").Pool(cores) if cores > 1 else None
+    kind = "port"
     try:
         for _ in range(min(args.warmup, 1)):
             cpu_evals_per_sec(cores, max(50, genes_per_core // 10), pool)
         rates, t0 = [], time.perf_counter()
         for _ in range(max(args.steps, 1)):
-            rates.append(cpu_evals_per_sec(cores, genes_per_core, pool))
+            rate, kind = cpu_evals_per_sec(cores, genes_per_core, pool)
+            rates.append(rate)
             if time.perf_counter() - t0 > 120:
                 break
     finally:
@@ -174,15 +239,14 @@ def run_reference(args):
             pool.close()
             pool.join()
     value = float(np.median(rates))
-    sample = "%d genes x %d samples per step (%d processes x %d genes), one objective+gradient evaluation each" % (
-        cores * genes_per_core, M, cores, genes_per_core)
+    sample = cpu_sample_text(kind, cores, genes_per_core)
     line = {
         "impl": "reference", "metric": "gene_likelihood_evals_per_sec", "value": value, "unit": "gene-evals/s",
         "n_gpus": args.gpus, "steps": len(rates), "warmup": args.warmup,
-        "ms_per_step": 1000.0 * cores * genes_per_core / value, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1000.0 * cores * genes_per_core / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "gene-evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "gene-evals/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "gene-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,15 +256,57 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def make_block(torch, dev, block, genes, m):
+    """Block `block` of the synthetic data set (recipe of backyard/synthetic.R: t-distributed noise,
+    10 % of the genes shifted in group 2), generated on the device from the block's own seed."""
+    torch.cuda.manual_seed(2019 + block)
+    y = torch.randn((genes, m), dtype=torch.float64, device=dev)
+    chi = torch.distributions.Chi2(torch.tensor(10.0, dtype=torch.float64, device=dev)).sample((genes, 1))
+    y = y * torch.sqrt(10.0 / chi)
+    y[: genes // 10, m // 2:] += 1.0
+    return y
+
+
+def connect_fused(engine, dist, torch, dev, rank, world, max_values):
+    """All ranks end up in the same mode: fused exchange if every rank could map every mailbox."""
+    ok, why, mine = 1, "", None
+    try:
+        mine = engine.comm_mailbox(world, max_values)
+    except Exception as exc:            # e.g. CUDA IPC not permitted on this box
+        ok, why = 0, str(exc)
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)       # every rank takes part, whatever happened
+    if ok and all(h is not None for h in handles):
+        try:
+            engine.comm_connect(rank, world, b"".join(handles))
+        except Exception as exc:        # peer access not available
+            ok, why = 0, str(exc)
+    else:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        try:
+            engine.comm_disconnect()
+        except Exception:
+            pass
+        if rank == 0:
+            sys.stderr.write("fused exchange unavailable (%s); using ncclAllReduce\n" % why)
+        return False
+    dist.barrier()
+    return True
+
+
 def run_gpu(args):
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_node = bind_to_gpu_numa_node(local_rank)       # before any pinned allocation
     import torch
     import torch.distributed as dist
-    from fitnoise_b200 import _native
+    from fitnoise_b200 import _native, parallel
     import fitnoise_b200 as fitnoise
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; fitnoise_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -208,19 +314,22 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    n, m = N_GENES, M
+    m = M
     design = design_matrix()
     fam = fitnoise.Model_t()._family(m)
     P = fam.theta_length()
+    if BLOCKS % world == 0 and N_TOTAL % BLOCKS == 0:
+        my_blocks = list(range(rank * BLOCKS // world, (rank + 1) * BLOCKS // world))
+        block_genes = N_TOTAL // BLOCKS
+    else:                                            # odd world size: one block per rank
+        bounds = parallel.shard_bounds(N_TOTAL, world)
+        my_blocks, block_genes = [1000 + rank], int(bounds[rank + 1] - bounds[rank])
+    n = block_genes * len(my_blocks)
+    shard_bytes = n * m * 8
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(2019 + rank)
-        y_dev = torch.randn((n, m), dtype=torch.float64, device=dev, generator=gen)
-        chi = torch.distributions.Chi2(torch.tensor(10.0, dtype=torch.float64, device=dev)).sample((n, 1))
-        y_dev = y_dev * torch.sqrt(10.0 / chi)
-        y_dev[: n // 10, m // 2:] += 1.0
+        y_dev = torch.cat([make_block(torch, dev, b, block_genes, m) for b in my_blocks])
         y_host = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
         y_host.copy_(y_dev)
         stream.synchronize()
@@ -228,51 +337,54 @@ def run_gpu(args):
 
         engine = _native.Engine(local_rank, stream.cuda_stream)
         engine.upload_dev(n, m, y_dev.data_ptr(), 0, fam, 0, design)
-        del y_dev
         reduce_buf = torch.zeros(P + 3, dtype=torch.float64, device=dev)
 
-        # N > 1: the all-reduce of the P+3 sums is fused into the kernel epilogue (peer stores over
+        # N > 1: the all-reduce of the sums is fused into the kernel epilogue (peer stores over
         # NVLink into IPC-mapped mailboxes); FN_REDUCE=nccl times kernel + ncclAllReduce instead.
         reduce_mode = os.environ.get("FN_REDUCE", "fused") if world > 1 else "none"
-        if reduce_mode == "fused":
-            # every rank must end up in the same mode: agree on whether the IPC mapping worked
-            ok, why, mine = 1, "", None
-            try:
-                mine = engine.comm_mailbox(world, 8 + 2 * m)
-            except Exception as exc:            # e.g. CUDA IPC not permitted on this box
-                ok, why = 0, str(exc)
-            handles = [None] * world
-            dist.all_gather_object(handles, mine)       # every rank takes part, whatever happened
-            if ok and all(h is not None for h in handles):
-                try:
-                    engine.comm_connect(rank, world, b"".join(handles))
-                except Exception as exc:        # peer access not available
-                    ok, why = 0, str(exc)
-            else:
-                ok = 0
-            flag = torch.tensor([ok], dtype=torch.int64, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
-                try:
-                    engine.comm_disconnect()
-                except Exception:
-                    pass
-                reduce_mode = "nccl"
-                if rank == 0:
-                    sys.stderr.write("fused exchange unavailable (%s); using ncclAllReduce\n" % why)
-            dist.barrier()
+        if reduce_mode == "fused" and not connect_fused(engine, dist, torch, dev, rank, world, 8 + 2 * m):
+            reduce_mode = "nccl"
+        resident = reduce_mode != "nccl" and not os.environ.get("FN_NO_RESIDENT")
+
+        def step_nccl():
+            engine.nll_grad_dev(THETA, reduce_buf.data_ptr())
+            dist.all_reduce(reduce_buf)
+            out = reduce_buf.cpu().numpy()
+            return float(out[0]), out[1:P + 1].copy(), int(out[P + 1]), int(out[P + 2])
 
         def step():
             if reduce_mode == "nccl":
-                engine.nll_grad_dev(THETA, reduce_buf.data_ptr())
-                dist.all_reduce(reduce_buf)
-                return reduce_buf.cpu().numpy()
+                return step_nccl()
             return engine.nll_grad(THETA)          # (value, grad, n_used, n_bad): totals over all ranks, on the host
 
         def barrier():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
+
+        def agree_max(x):
+            if world == 1:
+                return x
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def timed_steps(k):
+            """K steps between two events on the launching stream, bracketed by barrier + synchronize;
+            the resident phase (one kernel launch for the K evaluations) lies INSIDE the timed region."""
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            launches0 = engine.launch_count()
+            barrier()
+            ev0.record(stream)
+            if resident:
+                engine.resident_begin()
+            for _ in range(k):
+                out = step()
+            if resident:
+                engine.resident_end()
+            ev1.record(stream)
+            barrier()
+            return agree_max(ev0.elapsed_time(ev1)) / k, engine.launch_count() - launches0, out
 
         # clocks are sampled from the start of the warm-up to the end of the timed region; the
         # warm-up runs for at least ~0.7 s so that the 100 ms sampler sees the GPU under this load
@@ -282,135 +394,254 @@ def run_gpu(args):
         warm = max(args.warmup, 3)
         for _ in range(warm):
             first = step()
-        # keep the GPU under this load for ~0.7 s more (same step count on every rank) so that the
-        # 100 ms clock sampler sees it; still warm-up, not timed
         t_one = time.perf_counter()
         step()
         t_one = max(time.perf_counter() - t_one, 1e-5)
-        extra = int(min(0.7 / t_one, 20000))
-        if world > 1:
-            t = torch.tensor([extra], dtype=torch.int64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            extra = int(t.item())
-        for _ in range(extra):
-            step()
-        if reduce_mode == "nccl":
-            first = (first[0], first[1:P + 1], first[P + 1], first[P + 2])
-        assert int(first[2]) == n * world and int(first[3]) == 0, first
-        launches0 = engine.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kernel_ms = []
-        barrier()
-        ev0.record(stream)
-        for _ in range(args.steps):
-            out = step()
-        ev1.record(stream)
-        barrier()
-        elapsed_ms = ev0.elapsed_time(ev1)
-        launches = engine.launch_count() - launches0
-        clocks = sampler.stop() if rank == 0 else None
-        if world > 1:
-            t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            elapsed_ms = float(t.item())
-        ms_per_step = elapsed_ms / args.steps
-        value = n * world / (ms_per_step / 1000.0)
+        extra = int(agree_max(min(0.7 / t_one, 20000)))
+        timed_steps(max(extra, 3))                  # still warm-up (in the timed form), not reported
+        assert int(first[2]) == N_TOTAL and int(first[3]) == 0, first
 
-        # kernel-only duration for the roofline: a second pass over the same launches with the
-        # library's CUDA events around each kernel (on the stream it is launched on).  Kept out of the
-        # timed region above because the extra event records and synchronisation slow the step down.
+        ms_per_step, launches, out = timed_steps(args.steps)
+        clocks = sampler.stop() if rank == 0 else None
+        value = N_TOTAL / (ms_per_step / 1000.0)
+        _, res_launches, res_evals = engine.resident_stats()
+
+        # the same steps with the L2 flushed before each one (only relevant when the shard fits the L2)
+        flushed = None
+        if shard_bytes < 2 * L2_BYTES and not os.environ.get("FN_BENCH_SKIP_FLUSH"):
+            k = max(20, min(args.steps, 300))
+            barrier()
+            if resident:
+                engine.resident_begin()
+            total = 0.0
+            for i in range(k + 5):
+                engine.l2_flush()
+                if world > 1 and reduce_mode == "nccl":
+                    dist.barrier()
+                t0 = time.perf_counter()
+                step()
+                if i >= 5:
+                    total += time.perf_counter() - t0
+            if resident:
+                engine.resident_end()
+            barrier()
+            fl_ms = agree_max(total / k * 1000.0)
+            flushed = {"ms_per_step": fl_ms, "value": N_TOTAL / (fl_ms / 1000.0), "steps": k,
+                       "timing": "host clock around each fn_nll_grad call, max over ranks; fn_l2_flush (sweep of a "
+                                 "2 x L2 buffer) before every step, not timed; ranks are NOT re-aligned after the "
+                                 "flush, so the figure includes their skew"}
+
+        # multi-GPU correctness under the driver's clock: fused totals vs an NCCL all-reduce of the
+        # per-rank sums (fn_nll_grad_dev), on the same theta
+        exchange_check = None
+        if world > 1:
+            fused = step()
+            if reduce_mode == "fused":
+                ref = step_nccl()
+            else:
+                ref = fused
+            scale = abs(ref[0])
+            diff = max(abs(fused[0] - ref[0]) / scale,
+                       float(np.max(np.abs(np.asarray(fused[1]) - np.asarray(ref[1])))) / scale)
+            exchange_check = {"max_rel_diff": diff, "ok": bool(diff < 1e-12 and fused[2] == ref[2] == N_TOTAL),
+                              "genes_used": int(fused[2]), "mode": reduce_mode}
+        objective = {"value": float(out[0]), "grad": [float(x) for x in out[1]],
+                     "note": "same 8 seeded blocks for every N: equal across N up to summation order"}
+
+        # kernel-only duration for the roofline: one launch per evaluation with the library's CUDA
+        # events around each kernel (on the stream it is launched on), this rank's shard, no exchange
+        # partner waiting.  Kept out of the timed region above.
+        kernel_ms = []
         engine.set_timing(True)
         for _ in range(max(10, min(args.steps, 200))):
-            step()
+            if shard_bytes < 2 * L2_BYTES:
+                engine.l2_flush()
+            if world > 1:
+                engine.nll_grad_dev(THETA, reduce_buf.data_ptr())     # this rank's kernel alone: no peer to wait for
+            else:
+                step()
             kernel_ms.append(engine.last_kernel_ms())
         engine.set_timing(False)
         kms_queued = engine.time_nll_grad(THETA, 100)      # back to back: no launch-latency gap in the events
-        kms = float(np.mean(kernel_ms))
+        kms = agree_max(float(np.mean(kernel_ms)))
         alg_bytes = n * (8 * m + 1)
         peak, peak_src = measured_peak()
         achieved = alg_bytes / (kms * 1e-3) / 1e9
+        per_step_gbs = N_TOTAL * (8 * m + 1) / (ms_per_step * 1e-3) / 1e9
 
         # e2e through the C-ABI with host buffers (pinned): H2D + prepare + evaluate + read back
         e2e_steps = max(2, min(args.steps, 5))
         engine.upload(y_np, None, fam, None, design)
-        engine.nll_grad(THETA)
+        step()
         barrier()
         t0 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(e2e_steps):
             engine.upload(y_np, None, fam, None, design)
-            res = step()
+            step()
         ev1.record(stream)
         barrier()
         e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
         e2e_wall_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms, e2e_wall_ms = float(t[0].item()), float(t[1].item())
-        e2e_ms = max(e2e_ms, e2e_wall_ms)      # the host-side staging of pageable->device is wall time
-        e2e_value = n * world / (e2e_ms / 1000.0)
+        e2e_ms = agree_max(max(e2e_ms, e2e_wall_ms))      # the host-side staging is wall time
+        e2e_value = N_TOTAL / (e2e_ms / 1000.0)
 
-        # the literal configs[4]: Model_independent fit + coef test through the public API (rank 0 only, N = 1)
-        fit_test = None
-        if world == 1 and not os.environ.get("FN_BENCH_SKIP_FIT"):
-            engine.close()
-            t_ind = []
-            for _ in range(2):          # first call allocates the pooled engine's buffers; second is warm
-                t0 = time.perf_counter()
-                fitted = fitnoise.Model_independent().fit(y_np, design)
-                tested = fitted.test(coef=[1])
-                t_ind.append(time.perf_counter() - t0)
-                n_sig = int((tested.q_values < 0.01).sum())
-                fitted._session.close()
-            t0 = time.perf_counter()
-            fitted_t = fitnoise.Model_t().fit(y_np, design)
-            tested_t = fitted_t.test(coef=[1])
-            t_t = time.perf_counter() - t0
-            fit_test = {
-                "Model_independent_fit_test_wall_s": t_ind[1], "Model_independent_first_call_wall_s": t_ind[0],
-                "q_lt_0.01": n_sig,
-                "Model_t_fit_test_wall_s": t_t, "Model_t_evaluations": int(fitted_t._evaluations),
-                "Model_t_df": float(fitted_t.param.df), "Model_t_sd": float(np.sqrt(fitted_t.param.variance)),
-                "includes": "H2D of y (768 MB) from pinned host memory, preparation, optimiser, noise "
-                            "p-values, coefficients, test, BH, D2H of all per-gene results",
-            }
-            fitted_t._session.close()
+        # weak scaling (secondary): 1M genes on EVERY GPU
+        weak = None
+        if world > 1 and not os.environ.get("FN_BENCH_SKIP_WEAK"):
+            del y_dev
+            reps = BLOCKS
+            big = torch.cat([make_block(torch, dev, 100 * (rank + 1) + b, N_TOTAL // reps, m) for b in range(reps)])
+            engine.upload_dev(N_TOTAL, m, big.data_ptr(), 0, fam, 0, design)
+            del big
+            for _ in range(5):
+                step()
+            k = max(50, min(args.steps, 500))
+            wms, _, wout = timed_steps(k)
+            weak = {"ms_per_step": wms, "value": N_TOTAL * world / (wms / 1000.0), "genes_per_gpu": N_TOTAL,
+                    "genes_total": N_TOTAL * world, "steps": k, "genes_used": int(wout[2])}
+        engine.comm_disconnect() if reduce_mode == "fused" else None
+        engine.close()
+
+    # fit + test wall time through the public API (BASELINE metric, second half): cfg5 and cfg1 shapes,
+    # every rank calls the same fit under torchrun (genes sharded by the session)
+    fit_test = None
+    if not os.environ.get("FN_BENCH_SKIP_FIT"):
+        fit_test = run_fit_test(fitnoise, torch, dist, world, rank, dev)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not os.environ.get("FN_BENCH_SKIP_CPU"):
         genes = int(os.environ.get("FN_CPU_GENES", 6000))
         os.environ["OMP_NUM_THREADS"] = "1"
-        rate = cpu_evals_per_sec(1, genes)
-        cpu_baseline = {"value": rate, "unit": "gene-evals/s", "cores": 1, "kind": "port",
-                        "sample": "%d genes x %d samples, one objective+gradient evaluation of the oracle port "
-                                  "(per-gene numpy loop: inv/det of the 94x94 covariance)" % (genes, m)}
+        rate, kind = cpu_evals_per_sec(1, genes, calls=2)
+        cpu_baseline = {"value": rate, "unit": "gene-evals/s", "cores": 1, "kind": kind,
+                        "sample": cpu_sample_text(kind, 1, genes)}
 
     if rank == 0:
+        if shard_bytes > L2_BYTES:
+            l2 = "inputs (%d MB per GPU) larger than the 126 MB L2: every step streams from DRAM, no flush needed" % (shard_bytes >> 20)
+        else:
+            l2 = ("shard of %d MB per GPU FITS the 126 MB L2: `value` is L2-assisted (steady state of the optimiser "
+                  "loop, no flush); `flushed` repeats the step with an L2 flush before every step" % (shard_bytes >> 20))
         line = {
             "metric": "gene_likelihood_evals_per_sec", "value": value, "unit": "gene-evals/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "genes_total": n * world, "samples": m, "design_columns": 2,
-                       "theta_len": P, "l2": "inputs (768 MB per GPU) larger than L2; no flush needed",
-                       "parallelism": "genes sharded, %d rank(s), all-reduce of %d doubles per step (%s)" % (world, P + 3, reduce_mode)},
+            "config": {"workload": WORKLOAD, "genes_total": N_TOTAL, "genes_per_gpu": n, "samples": m,
+                       "design_columns": 2, "theta_len": P, "l2": l2,
+                       "evaluation": ("resident kernel: %d launch(es), %d evaluations as commands" % (launches, args.steps))
+                       if resident else "one kernel launch per evaluation",
+                       "parallelism": "genes sharded, %d rank(s), all-reduce of %d doubles per step (%s)" % (world, P + 4, reduce_mode),
+                       "numa_node": numa_node},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "gene-evals/s", "h2d_bytes_per_step": int(n * m * 8),
-                    "d2h_bytes_per_step": int((P + 3) * 8), "ms_per_step": e2e_ms},
+            "e2e": {"value": e2e_value, "unit": "gene-evals/s", "h2d_bytes_per_step": int(shard_bytes),
+                    "d2h_bytes_per_step": int((P + 4) * 16), "ms_per_step": e2e_ms,
+                    "note": "per rank: its shard of y from pinned host memory every step"},
             "gpu_launches": int(launches),
+            "resident": {"kernel_launches_total": int(res_launches), "evaluations_total": int(res_evals)} if resident else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(), "kernel": "fn::eval_kernel<2, SCALE1>", "kernel_ms": kms,
+                         "traffic": measured_traffic(n), "kernel": "fn::eval_kernel<2, SCALE1>", "kernel_ms": kms,
                          "kernel_ms_queued": kms_queued, "achieved_queued": alg_bytes / (kms_queued * 1e-3) / 1e9,
+                         "per_step": {"achieved": per_step_gbs, "peak": peak * world, "frac": per_step_gbs / (peak * world),
+                                      "note": "bytes of ALL ranks / ms_per_step (whole step incl. command, exchange, "
+                                              "hand-over) against N x peak: the north-star fraction per evaluation"},
                          "note": "achieved/frac use kernel_ms: CUDA events around each launch on an idle stream "
-                                 "(includes the launch latency); *_queued: 100 launches back to back between two events",
+                                 "(one launch per evaluation, includes the launch latency; L2 flushed before each launch "
+                                 "when the shard would fit it); *_queued: 100 launches back to back between two events",
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+            "flushed": flushed,
+            "exchange_check": exchange_check,
+            "objective": objective,
+            "weak": weak,
             "cpu_baseline": cpu_baseline,
             "fit_test": fit_test,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_fit_test(fitnoise, torch, dist, world, rank, dev):
+    """Model.fit(...) + .test(...) wall time through the public API, inputs in pinned host memory,
+    max over ranks.  cfg5 shape (1M x 96: Model_independent as BASELINE names it, and Model_t whose
+    fit runs the optimiser) and cfg1 shape (20k x 6, Model_t)."""
+    def wall(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fn()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, res
+
+    out = {"includes": "H2D of this rank's genes from pinned host memory, preparation, optimiser, noise p-values, "
+                       "coefficients, test, BH over all genes, per-gene results back on the host of every rank",
+           "ranks": world}
+    rng = np.random.default_rng(2019)
+    # ---- cfg5: 1M x 96 -------------------------------------------------------------------
+    n, m = N_TOTAL, M
+    y_host = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
+    y = y_host.numpy()
+    chunk = 125000
+    for lo in range(0, n, chunk):                      # same data on every rank (same seed)
+        hi = min(n, lo + chunk)
+        block = rng.standard_normal((hi - lo, m))
+        block *= np.sqrt(10.0 / rng.chisquare(10.0, size=(hi - lo, 1)))
+        y[lo:hi] = block
+    y[: n // 10, m // 2:] += 1.0
+    design = design_matrix(m)
+
+    def fit_ind():
+        fitted = fitnoise.Model_independent().fit(y, design)
+        tested = fitted.test(coef=[1])
+        return fitted, tested
+
+    def fit_t():
+        fitted = fitnoise.Model_t().fit(y, design)
+        tested = fitted.test(coef=[1])
+        return fitted, tested
+
+    t_first, (f, t) = wall(fit_ind)                    # first call allocates the engine's buffers
+    f._session.close()
+    t_ind, (f, t) = wall(fit_ind)
+    n_sig = int((t.q_values < 0.01).sum())
+    f._session.close()
+    t_t, (f, t) = wall(fit_t)
+    out["1Mx96"] = {"Model_independent_fit_test_wall_s": t_ind, "Model_independent_first_call_wall_s": t_first,
+                    "q_lt_0.01": n_sig, "Model_t_fit_test_wall_s": t_t, "Model_t_evaluations": int(f._evaluations),
+                    "Model_t_df": float(f.param.df), "Model_t_sd": float(np.sqrt(f.param.variance))}
+    f._session.close()
+    del y, y_host
+    # ---- cfg1: 20k x 6 -------------------------------------------------------------------
+    n, m = 20000, 6
+    rng = np.random.default_rng(2015)
+    y = rng.standard_normal((n, m)) * np.sqrt(10.0 / rng.chisquare(10.0, size=(n, 1)))
+    y[: n // 10, m // 2:] += 5.0
+    design = design_matrix(m)
+
+    def fit_small():
+        fitted = fitnoise.Model_t().fit(y, design)
+        tested = fitted.test(coef=[1])
+        return fitted, tested
+
+    _, (f, t) = wall(fit_small)
+    f._session.close()
+    times = []
+    for _ in range(5):
+        dt, (f, t) = wall(fit_small)
+        times.append(dt)
+        evals = int(f._evaluations)
+        df, sd = float(f.param.df), float(np.sqrt(f.param.variance))
+        f._session.close()
+    out["20kx6"] = {"Model_t_fit_test_wall_s": float(np.median(times)), "Model_t_evaluations": evals,
+                    "Model_t_df": df, "Model_t_sd": sd, "q_lt_0.01": int((t.q_values < 0.01).sum())}
+    return out
 
 
 def main():

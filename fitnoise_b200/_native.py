@@ -27,7 +27,7 @@ EXPORTS = [
     "fn_set_timing", "fn_last_kernel_ms", "fn_comm_mailbox", "fn_comm_connect", "fn_comm_disconnect",
     "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked", "fn_nll_grad_factors", "fn_set_factors", "fn_time_nll_grad",
     "fn_transform_upload", "fn_transform_sums", "fn_transform_apply",
-    "fn_resident_begin", "fn_resident_end", "fn_resident_stats", "fn_source_hash",
+    "fn_resident_begin", "fn_resident_end", "fn_resident_stats", "fn_source_hash", "fn_l2_flush",
 ]
 
 
@@ -83,6 +83,7 @@ def load_library():
                           "(ABI may not match the Python declarations); rebuild it")
     lib.fn_resident_begin.argtypes = [ctypes.c_void_p]
     lib.fn_resident_end.argtypes = [ctypes.c_void_p]
+    lib.fn_l2_flush.argtypes = [ctypes.c_void_p]
     lib.fn_resident_stats.restype = ctypes.c_int64
     lib.fn_resident_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.fn_launch_count.restype = ctypes.c_int64
@@ -236,6 +237,10 @@ class Engine(object):
     def resident_end(self):
         if getattr(self, "_h", None):
             self._check(self._lib.fn_resident_end(self._h))
+
+    def l2_flush(self):
+        """Evict the inputs from the L2 (benchmarking aid); works in the resident phase too."""
+        self._check(self._lib.fn_l2_flush(self._h))
 
     def resident_stats(self):
         """(resident now?, resident kernels launched, evaluations they executed)"""

@@ -193,9 +193,11 @@ struct fn_handle {
     unsigned long long* cmd_host_devptr = nullptr;
     unsigned long long* exit_host = nullptr;       // pinned, mapped (one word)
     unsigned long long* exit_host_devptr = nullptr;
-    unsigned long long* cmd_dev = nullptr;
+    Slot* cmd_dev = nullptr;                       // device copy of the command: one authenticated slot per word
     size_t cmd_cap = 0;                            // words the three buffers hold
     int64_t resident_launches = 0, resident_evals = 0;
+    double* flush_buf = nullptr;                   // fn_l2_flush: 2 x L2 size
+    size_t flush_words = 0;
     // fused multi-GPU exchange (fn_comm_*): mailboxes mapped with CUDA IPC
     int comm_world = 0, comm_rank = 0, comm_slot = 0;
     unsigned long long comm_seq = 0;
@@ -316,6 +318,7 @@ extern "C" int fn_destroy(fn_handle* h) {
     if (h->cmd_host) cudaFreeHost(h->cmd_host);
     if (h->exit_host) cudaFreeHost(h->exit_host);
     dfree(h->cmd_dev);
+    dfree(h->flush_buf);
     if (h->bh_exec) { cudaGraphExecDestroy(h->bh_exec); h->bh_exec = nullptr; }
     free_buffers(h);
     dfree(h->partials); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
@@ -475,6 +478,16 @@ static int ensure_scratch(fn_handle* h, size_t bytes) {
     }
     return 0;
 }
+
+#ifdef FN_TRACE
+#include <chrono>
+static double g_host_trace[4];
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+extern "C" void fn_host_trace(double* out) { for (int i = 0; i < 4; ++i) out[i] = g_host_trace[i]; }
+#define FN_HOST_STAMP(i) g_host_trace[i] = now_us()
+#else
+#define FN_HOST_STAMP(i) do { } while (0)
+#endif
 
 static int resident_relaunch(fn_handle* h, unsigned long long next_seq);
 
@@ -852,6 +865,10 @@ static int stage_theta(fn_handle* h, const double* theta, int32_t P, ThetaState&
 
 static bool per_sample_a(const fn_handle* h) { return h->fam.na == h->m && h->fam.kind != KIND_SCALE1; }
 static bool per_sample_b(const fn_handle* h) { return h->fam.nb == h->m && h->fam.kind != KIND_SCALE1; }
+// which of the two per-sample tables (fn_host.hpp unpack_theta) the evaluation kernel needs in full:
+// SCALE_PS uses both (1/theta_j and ln theta_j), PATSEQ one per per-sample block
+static bool table_a(const fn_handle* h) { return per_sample_a(h); }
+static bool table_b(const fn_handle* h) { return per_sample_b(h) || h->fam.kind == KIND_SCALE_PS; }
 
 static int eval_nacc(const fn_handle* h) {
     return ACC_FIXED + ((per_sample_a(h) || per_sample_b(h)) ? 2 * h->m : 0);
@@ -915,14 +932,15 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     ep.v = ts.v; ep.theta0 = ts.theta0;
     ep.ta0 = ts.ta.empty() ? 0.0 : ts.ta[0];
     ep.tb0 = ts.tb.empty() ? 0.0 : ts.tb[0];
-    ep.ta = ia ? h->tab_dev : nullptr;
-    ep.tb = ib ? h->tab_dev + m : nullptr;
+    ep.ta = table_a(h) ? h->tab_dev : nullptr;
+    ep.tb = table_b(h) ? h->tab_dev + m : nullptr;
     ep.inplace_a = ia; ep.inplace_b = ib;
     ep.pg_score = per_gene ? h->pg_score : nullptr;
     ep.pg_d2 = per_gene ? h->pg_d2 : nullptr;
     ep.pg_p = per_gene ? h->pg_p : nullptr;
     ep.rc.cmd_host = nullptr; ep.rc.cmd_dev = nullptr; ep.rc.exit_host = nullptr;
     ep.rc.next_seq = 0; ep.rc.idle_timeout_ns = 0; ep.rc.words = 0;
+    ep.rc.flush_buf = nullptr; ep.rc.flush_words = 0;
     if (resident) {
         // host_seq / comm_seq advance per command, not per launch
         const unsigned long long hs = h->host_seq, cs = h->comm_seq;
@@ -934,6 +952,7 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
         const double idle_ms = env ? atof(env) : 20.0;
         ep.rc.idle_timeout_ns = (unsigned long long)((idle_ms > 0.01 ? idle_ms : 0.01) * 1e6);
         ep.rc.words = h->res_words;
+        ep.rc.flush_buf = h->flush_buf; ep.rc.flush_words = h->flush_words;
     } else {
         fill_reduce(h, ep.gr, ep.sv, nacc, exchange);
         if (!per_gene) table_terms(h, ts, ep.sv);
@@ -951,16 +970,16 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
 // resident evaluation kernel
 // ------------------------------------------------------------------------------------------
 static int resident_words(const fn_handle* h) {
-    return CW_TAB + (per_sample_a(h) ? h->m : 0) + (per_sample_b(h) ? h->m : 0) + 1;
+    return CW_TAB + (table_a(h) ? h->m : 0) + (table_b(h) ? h->m : 0) + 1;
 }
 
 static int resident_launch(fn_handle* h) {
     ThetaState ts;                       // theta arrives with each command
     ts.is_t = h->fam.dist != DIST_NORMAL;
     *(volatile unsigned long long*)h->exit_host = 0;
-    // a flag left behind by an earlier resident kernel (its QUIT, or the seq it gave up on) must not be
-    // taken for this kernel's first command
-    CUDA_TRY(cudaMemsetAsync(h->cmd_dev, 0, FN_CMD_DEV_PAYLOAD * sizeof(unsigned long long), h->stream));
+    // slots left behind by an earlier resident kernel (its QUIT, or the command it fabricated when it
+    // gave up waiting) must not be taken for this kernel's first command
+    CUDA_TRY(cudaMemsetAsync(h->cmd_dev, 0, h->cmd_cap * sizeof(Slot), h->stream));
     int rc = launch_eval(h, ts, false, true, true);
     if (rc) return rc;
     ++h->resident_launches;
@@ -990,7 +1009,7 @@ extern "C" int fn_resident_begin(fn_handle* h) {
         CUDA_TRY(cudaHostAlloc(&h->cmd_host, cap * sizeof(unsigned long long), cudaHostAllocMapped));
         memset(h->cmd_host, 0, cap * sizeof(unsigned long long));
         CUDA_TRY(cudaHostGetDevicePointer(&h->cmd_host_devptr, h->cmd_host, 0));
-        CUDA_TRY(cudaMalloc(&h->cmd_dev, (FN_CMD_DEV_PAYLOAD + cap) * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&h->cmd_dev, cap * sizeof(Slot)));
         h->cmd_cap = cap;
     }
     if (!h->exit_host) {
@@ -1021,8 +1040,8 @@ static void resident_command(fn_handle* h, int op, unsigned long long seq, unsig
     w[CW_TA0] = bits(ts && !ts->ta.empty() ? ts->ta[0] : 0.0);
     w[CW_TB0] = bits(ts && !ts->tb.empty() ? ts->tb[0] : 0.0);
     int at = CW_TAB;
-    if (per_sample_a(h)) for (int j = 0; j < h->m; ++j) w[at++] = bits(ts ? ts->ta[j] : 0.0);
-    if (per_sample_b(h)) for (int j = 0; j < h->m; ++j) w[at++] = bits(ts ? ts->tb[j] : 0.0);
+    if (table_a(h)) for (int j = 0; j < h->m; ++j) w[at++] = bits(ts ? ts->ta[j] : 0.0);
+    if (table_b(h)) for (int j = 0; j < h->m; ++j) w[at++] = bits(ts ? ts->tb[j] : 0.0);
     unsigned long long sum = cmd_mix(seq, CW_SEQ);
     for (int i = 1; i < words - 1; ++i) sum += cmd_mix(w[i], i);
     w[words - 1] = sum;
@@ -1051,6 +1070,38 @@ extern "C" int64_t fn_resident_stats(fn_handle* h, int64_t* launches, int64_t* e
     return h->resident ? 1 : 0;
 }
 
+// Benchmarking aid: evict the data from the L2 (sweep a buffer twice its size) so that the next
+// evaluation streams from DRAM.  Works in both forms; returns when the sweep is done.
+extern "C" int fn_l2_flush(fn_handle* h) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->flush_buf) {
+        const bool was = h->resident;
+        LEAVE_RESIDENT(h);
+        int l2 = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+        h->flush_words = (size_t)(l2 > 0 ? l2 : (128 << 20)) * 2 / sizeof(double);
+        CUDA_TRY(cudaMalloc(&h->flush_buf, h->flush_words * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(h->flush_buf, 0, h->flush_words * sizeof(double), h->stream));
+        if (was) { int rc = fn_resident_begin(h); if (rc) return rc; }
+    }
+    if (h->resident) {
+        const unsigned long long seq = ++h->host_seq;
+        if (*(volatile unsigned long long*)h->exit_host == seq) {
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            int rc = resident_relaunch(h, seq);
+            if (rc) return rc;
+        }
+        resident_command(h, OP_FLUSH, seq, 0, nullptr, nullptr);
+        return wait_result(h, seq, 1);
+    }
+    l2_flush_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->flush_buf, (unsigned long long)h->flush_words);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // one evaluation by the resident kernel: the totals are in h->out_vals afterwards
 static int resident_eval(fn_handle* h, const ThetaState& ts) {
     StepVars sv;
@@ -1064,6 +1115,7 @@ static int resident_eval(fn_handle* h, const ThetaState& ts) {
         if (rc) return rc;
     }
     resident_command(h, OP_EVAL, seq, comm_seq, &ts, &sv);
+    FN_HOST_STAMP(2);
     ++h->resident_evals;
     return wait_result(h, seq, eval_nacc(h));
 }
@@ -1196,21 +1248,12 @@ static void assemble(const fn_handle* h, const double* acc, const double* ta, do
     out[at++] = acc[ACC_BAD] + (acc[ACC_PSUM] != 0.0 ? 1.0 : 0.0);
 }
 
-#ifdef FN_TRACE
-#include <chrono>
-static double g_host_trace[4];
-static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-extern "C" void fn_host_trace(double* out) { for (int i = 0; i < 4; ++i) out[i] = g_host_trace[i]; }
-#define FN_HOST_STAMP(i) g_host_trace[i] = now_us()
-#else
-#define FN_HOST_STAMP(i) do { } while (0)
-#endif
 
 extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double* value, double* grad,
                            int64_t* n_used, int64_t* n_bad) {
     FN_HOST_STAMP(0);
     ThetaState ts;
-    int rc = stage_theta(h, theta, P, ts, !h->resident && (per_sample_a(h) || per_sample_b(h)));
+    int rc = stage_theta(h, theta, P, ts, !h->resident && (table_a(h) || table_b(h)));
     if (rc) return rc;
     if (h->fam.nf > 0) return fail(FN_ERR_STATE, "factor models are evaluated with fn_nll_grad_factors");
     FN_HOST_STAMP(1);
@@ -1678,6 +1721,7 @@ extern "C" int fn_comm_disconnect(fn_handle* h) {
 
 #ifdef FN_TRACE
 extern "C" int fn_trace_dump(fn_handle* h, unsigned long long* out64) {
+    LEAVE_RESIDENT(h);
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpyFromSymbol(out64, fn::g_trace, 64 * sizeof(unsigned long long)));

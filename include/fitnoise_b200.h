@@ -102,6 +102,10 @@ int fn_resident_end(fn_handle* h);
 /* returns 1 while resident; launches = resident kernels started, evaluations = commands executed */
 int64_t fn_resident_stats(fn_handle* h, int64_t* launches, int64_t* evaluations);
 
+/* Benchmarking aid: sweeps a buffer twice the size of the L2 so that the next evaluation reads its
+ * input from DRAM (bench.py uses it between timed steps when a shard would stay L2-resident). */
+int fn_l2_flush(fn_handle* h);
+
 /* Asynchronous form for multi-GPU: leaves [value, grad[0..P-1], n_used, n_bad] (P+3 doubles) in
  * device memory at out_dev on the handle's stream, for the caller to allreduce.  No host sync. */
 int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, double* out_dev);

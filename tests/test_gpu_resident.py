@@ -158,9 +158,12 @@ def test_handover_litmus():
 
 def test_fit_uses_the_resident_kernel():
     g = load_golden("t_twogroup")
+    warm = fitnoise.Model_t().fit(g["y"], g["design"], force_param=g["theta"])     # the pooled engine
+    _, launches0, evals0 = warm._session.local.resident_stats()
+    warm._session.close()
     fitted = fitnoise.Model_t().fit(g["y"], g["design"])
     _, launches, evals = fitted._session.local.resident_stats()
-    assert launches >= 1 and evals == fitted._evaluations
+    assert launches - launches0 >= 1 and evals - evals0 == fitted._evaluations
     os.environ["FN_NO_RESIDENT"] = "1"
     try:
         plain = fitnoise.Model_t().fit(g["y"], g["design"])
@@ -189,4 +192,5 @@ def test_staged_upload_of_two_large_pageable_arrays():
         small = e.per_gene(theta)[0]
     finally:
         e.close()
-    assert np.array_equal(big[rows], small)
+    # (the two uploads use different tile geometries, so the sums associate differently)
+    assert_close(big[rows], small, 1e-12, what="per-gene score after two staged uploads")
