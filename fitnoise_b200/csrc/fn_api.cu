@@ -143,6 +143,8 @@ struct fn_handle {
 
     double* partials = nullptr;
     size_t partials_cap = 0;
+    Slot* pslots = nullptr;            // per-CTA partial sums as authenticated slots (fn_kernels.cuh grid_reduce)
+    size_t pslots_cap = 0;
     unsigned int* ticket = nullptr;
     double* out_dev = nullptr;
     Slot* out_host = nullptr;          // pinned, mapped: {value, seq} per accumulator
@@ -321,7 +323,7 @@ extern "C" int fn_destroy(fn_handle* h) {
     dfree(h->flush_buf);
     if (h->bh_exec) { cudaGraphExecDestroy(h->bh_exec); h->bh_exec = nullptr; }
     free_buffers(h);
-    dfree(h->partials); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
+    dfree(h->partials); dfree(h->pslots); dfree(h->ticket); dfree(h->out_dev); dfree(h->scratch_dev);
     if (h->out_host) cudaFreeHost(h->out_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -456,6 +458,13 @@ static int ensure_reduce(fn_handle* h, int grid, int nacc) {
         CUDA_TRY(cudaMalloc(&h->partials, need * sizeof(double)));
         h->partials_cap = need;
     }
+    if ((size_t)grid * FN_SLOT_ACC > h->pslots_cap) {
+        dfree(h->pslots);
+        const size_t cap = (size_t)grid * FN_SLOT_ACC + 1024;
+        CUDA_TRY(cudaMalloc(&h->pslots, cap * sizeof(Slot)));
+        CUDA_TRY(cudaMemset(h->pslots, 0, cap * sizeof(Slot)));
+        h->pslots_cap = cap;
+    }
     if ((size_t)nacc > h->out_cap) {
         dfree(h->out_dev);
         if (h->out_host) { cudaFreeHost(h->out_host); h->out_host = nullptr; }
@@ -544,7 +553,7 @@ static void collect_result(fn_handle* h, int nacc) {
 }
 
 static void fill_reduce(fn_handle* h, GridReduce& gr, StepVars& sv, int nacc, bool exchange) {
-    gr.partials = h->partials; gr.ticket = h->ticket; gr.out_dev = h->out_dev;
+    gr.pslots = h->pslots; gr.partials = h->partials; gr.ticket = h->ticket; gr.out_dev = h->out_dev;
     gr.out_host = h->out_host_devptr; gr.nacc = nacc;
     sv.host_seq = ++h->host_seq;
     sv.comm_seq = 0; sv.add_on = 0; sv.add_value = 0.0; sv.add_dv = 0.0; sv.add_psum = 0.0;

@@ -81,6 +81,7 @@ struct PeerComm {
 };
 
 struct GridReduce {
+    Slot* pslots;            // gridDim.x * FN_SLOT_ACC authenticated partials (nacc <= FN_SLOT_ACC)
     double* partials;        // gridDim.x * nacc
     unsigned int* ticket;
     double* out_dev;         // nacc doubles
@@ -106,34 +107,79 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-// Sum `nacc` per-CTA values over the grid in a fixed order; the last CTA to arrive does it, then
-// (multi-GPU) exchanges the sums with the peer GPUs, and finally hands the totals to the host.
-// `vals` is this CTA's shared array of nacc doubles (already complete, visible after a barrier).
-// Safe to call once per evaluation from a resident kernel: the ticket is back at zero before any
-// total leaves the GPU, and the next evaluation only starts after the host has seen every total.
+// CTA-wide sum of NV thread-local doubles into shared `out[NV]` (deterministic order).
+template <int NV>
+__device__ __forceinline__ void block_sum(double* v, double* out, double* scratch /* 32*NV */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if (lane == 0) scratch[warp * NV + i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < nwarp; ++w) s += scratch[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+#define FN_SLOT_ACC 8      // grids of up to this many accumulators reduce through authenticated slots
+
+// Reducer side of the slot form of grid_reduce (cold code, kept out of line so that its registers do
+// not weigh on the streaming loop): thread t adds the partials of CTAs t, t + T, ... into s[].
+__device__ __forceinline__ void gather_slots(const Slot* pslots, int nacc, unsigned long long seq, double* s) {
+    const unsigned int G = gridDim.x, T = blockDim.x;
+#pragma unroll
+    for (int i = 0; i < FN_SLOT_ACC; ++i) s[i] = 0.0;
+    const unsigned long long t0 = global_ns();
+    bool failed = false;
+    for (unsigned int b = threadIdx.x; b < G; b += T) {
+        const Slot* line = &pslots[(size_t)b * FN_SLOT_ACC];
+        double v[FN_SLOT_ACC];
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < FN_SLOT_ACC; ++i) {
+                v[i] = 0.0;
+                if (i < nacc) ok = slot_try_load(line + i, seq, v[i]) && ok;
+            }
+            if (ok) break;
+            if (global_ns() - t0 > 10000000000ull) { failed = true; break; }     // a CTA died: NaN totals
+        }
+#pragma unroll
+        for (int i = 0; i < FN_SLOT_ACC; ++i) s[i] += failed ? NAN : v[i];
+    }
+}
+
+
+// Sum `nacc` per-CTA values over the grid in a fixed order, (multi-GPU) exchange the sums with the
+// peer GPUs, and hand the totals to the host.  `vals` is this CTA's shared array of nacc doubles
+// (complete and visible after a barrier).
+//
+// nacc <= FN_SLOT_ACC (every model without per-sample parameters): each CTA stores its partials as
+// authenticated slots -- one 128-byte line per CTA, no fence, no atomic -- and is done.  CTA 0 is the
+// reducer: thread t polls the lines of CTAs t, t + T, ... (all loads of a line in flight together,
+// re-read until every slot carries this evaluation's seq), the thread sums are added by the fixed
+// tree of block_sum: deterministic for a given grid, and the last partial to arrive is seen one L2
+// round trip after it was stored.  (The slower alternative below -- partials, fence, ticket, and the
+// last CTA to arrive re-reads everything -- costs the slowest CTA about 2.5 us more.)
+// Larger nacc keeps the ticket form.  Either way the function is safe to call once per evaluation
+// from a resident kernel: nothing of evaluation k can be mistaken for evaluation k+1.
 __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const StepVars& sv, const double* vals) {
     __shared__ int is_last;
     __shared__ double gsum[256];
+    __shared__ double tot[FN_SLOT_ACC];
+    static_assert(32 * FN_SLOT_ACC <= 256, "gsum doubles as block_sum scratch");
     const int T = blockDim.x, nacc = gr.nacc;
-    for (int i = threadIdx.x; i < nacc; i += T)
-        gr.partials[(size_t)blockIdx.x * nacc + i] = vals[i];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(gr.ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    FN_STAMP_ANY(8);
-    if (threadIdx.x == 0) *gr.ticket = 0;
-    __threadfence();
-    __syncthreads();
     const unsigned int G = gridDim.x;
     const PeerComm& pc = gr.comm;
     const bool exchange = pc.world > 1;
     const int parity = (int)(sv.comm_seq & 1ull);
-    // total of component i over the grid, by thread i (nacc <= T) or by a strided loop
+    // total of component i over the grid -> peers' mailboxes, or device + host
     auto publish = [&](int i, double s) {
         if (sv.add_on) {
             if (i == ACC_VALUE) s += sv.add_value;
@@ -148,39 +194,55 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const StepVars
             if (gr.out_host) slot_store(&gr.out_host[i], s, sv.host_seq);
         }
     };
-    if (nacc * 32 <= T) {
-        // one warp per component: lane l adds blocks l, l+32, ... (independent loads), then a shuffle
-        // tree; no shared memory, no barrier.  The usual case (7 accumulators, 256 threads).
-        const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (i < nacc) {
-            double s = 0.0;
-            for (unsigned int b = lane; b < G; b += 32) s += __ldcg(&gr.partials[(size_t)b * nacc + i]);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) publish(i, s);
-        }
-    } else if (nacc <= T) {
-        // thread (slice, i) adds blocks slice, slice+S, ... of component i; then the slices are added
-        const int S = T / nacc, i = threadIdx.x % nacc, slice = threadIdx.x / nacc;
-        if (slice < S) {
-            double s = 0.0;
-            for (unsigned int b = slice; b < G; b += S) s += __ldcg(&gr.partials[(size_t)b * nacc + i]);
-            gsum[slice * nacc + i] = s;
+
+    if (nacc <= FN_SLOT_ACC) {
+        if (threadIdx.x < nacc)
+            slot_store(&gr.pslots[(size_t)blockIdx.x * FN_SLOT_ACC + threadIdx.x], vals[threadIdx.x], sv.host_seq);
+        if (blockIdx.x != 0) return;
+        FN_STAMP_ANY(8);
+        double s[FN_SLOT_ACC];
+        gather_slots(gr.pslots, nacc, sv.host_seq, s);
+        block_sum<FN_SLOT_ACC>(s, tot, gsum);
+        if (threadIdx.x < nacc) publish(threadIdx.x, tot[threadIdx.x]);
+        FN_STAMP_ANY(9);
+    } else {
+        for (int i = threadIdx.x; i < nacc; i += T)
+            gr.partials[(size_t)blockIdx.x * nacc + i] = vals[i];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(gr.ticket, 1u);
+            is_last = (t == gridDim.x - 1);
         }
         __syncthreads();
-        if (threadIdx.x < nacc) {
-            double s = 0.0;
-            for (int q = 0; q < S; ++q) s += gsum[q * nacc + threadIdx.x];
-            publish(threadIdx.x, s);
+        if (!is_last) return;
+        FN_STAMP_ANY(8);
+        if (threadIdx.x == 0) *gr.ticket = 0;
+        __threadfence();
+        __syncthreads();
+        if (nacc <= T) {
+            // thread (slice, i) adds blocks slice, slice+S, ... of component i; then the slices are added
+            const int S = T / nacc, i = threadIdx.x % nacc, slice = threadIdx.x / nacc;
+            if (slice < S) {
+                double a = 0.0;
+                for (unsigned int b = slice; b < G; b += S) a += __ldcg(&gr.partials[(size_t)b * nacc + i]);
+                gsum[slice * nacc + i] = a;
+            }
+            __syncthreads();
+            if (threadIdx.x < nacc) {
+                double a = 0.0;
+                for (int q = 0; q < S; ++q) a += gsum[q * nacc + threadIdx.x];
+                publish(threadIdx.x, a);
+            }
+        } else {
+            for (int i = threadIdx.x; i < nacc; i += T) {
+                double a = 0.0;
+                for (unsigned int b = 0; b < G; ++b) a += __ldcg(&gr.partials[(size_t)b * nacc + i]);
+                publish(i, a);
+            }
         }
-    } else {
-        for (int i = threadIdx.x; i < nacc; i += T) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < G; ++b) s += __ldcg(&gr.partials[(size_t)b * nacc + i]);
-            publish(i, s);
-        }
+        FN_STAMP_ANY(9);
     }
-    FN_STAMP_ANY(9);
     if (!exchange) return;
 
     // every component: wait for all senders' slots of this evaluation in my own mailbox, add in rank
@@ -203,26 +265,6 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const StepVars
         gr.out_dev[i] = s;
         if (gr.out_host) slot_store(&gr.out_host[i], s, sv.host_seq);
     }
-}
-
-// CTA-wide sum of NV thread-local doubles into shared `out[NV]` (deterministic order).
-template <int NV>
-__device__ __forceinline__ void block_sum(double* v, double* out, double* scratch /* 32*NV */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double x = v[i];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-        if (lane == 0) scratch[warp * NV + i] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double s = 0.0;
-        for (int w = 0; w < nwarp; ++w) s += scratch[w * NV + threadIdx.x];
-        out[threadIdx.x] = s;
-    }
-    __syncthreads();
 }
 
 // Per-evaluation tables t0[p], t1[p] (p = 0..m) of density_tables(), filled by the whole CTA: thread p
@@ -437,7 +479,9 @@ __device__ __forceinline__ void resident_fetch(const ResidentCtl& rc, unsigned l
                 chk += __shfl_xor_sync(0xffffffffu, chk, off);
             }
             if (sum == chk) {
-                FN_STAMP(10);
+#ifdef FN_TRACE
+                if (__shfl_sync(0xffffffffu, w, CW_OP) == (unsigned long long)OP_EVAL) FN_STAMP(10);
+#endif
                 // forward: the first 32 words from the registers, the rest re-read (only per-sample models)
                 if (lane < nw - 1) slot_store_bits(rc.cmd_dev + lane, w, expect);
                 for (int i = 32 + lane; i < nw - 1; i += 32) slot_store_bits(rc.cmd_dev + i, ld_sys_u64(rc.cmd_host + i), expect);
@@ -492,7 +536,7 @@ struct EvalParams {
 };
 
 template <int C, int KIND>
-__global__ void __launch_bounds__(256, (C <= 8 ? 2 : 1)) eval_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[FN_MAX_STAGES];
     __shared__ double red_scratch[32 * ACC_FIXED];

@@ -18,7 +18,8 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not p.endswith("fdr.npz") and not p.endswith("transform_poly.npz"))
+                  if not p.endswith("fdr.npz") and not p.endswith("transform_poly.npz")
+                  and not os.path.basename(p).startswith("full_"))
 
 
 def load_golden(name):
