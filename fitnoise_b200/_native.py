@@ -28,7 +28,13 @@ EXPORTS = [
     "fn_test_bh", "fn_coef_fetch", "fn_bh_ranked", "fn_nll_grad_factors", "fn_set_factors", "fn_time_nll_grad",
     "fn_transform_upload", "fn_transform_sums", "fn_transform_apply",
     "fn_resident_begin", "fn_resident_end", "fn_resident_stats", "fn_source_hash", "fn_l2_flush",
+    "fn_result_dev", "fn_fetch", "fn_bh_ranked_dev", "fn_pinned_alloc", "fn_pinned_free",
 ]
+
+# fn_result_dev selectors (include/fitnoise_b200.h)
+(RES_SCORE, RES_D2, RES_PDF, RES_NOISE_P, RES_AVERAGES, RES_COEF, RES_COVAR, RES_DFPOST, RES_CONTRASTED,
+ RES_P, RES_Q, RES_ORDER) = range(12)
+RES_DTYPE = {RES_PDF: np.int32, RES_ORDER: np.uint32}
 
 
 class Family(ctypes.Structure):
@@ -78,12 +84,19 @@ def load_library():
     lib.fn_last_error.restype = ctypes.c_char_p
     lib.fn_version.restype = ctypes.c_char_p
     lib.fn_source_hash.restype = ctypes.c_char_p
-    if lib.fn_source_hash().decode() != _build.source_hash():
+    if lib.fn_source_hash().decode() != _build.source_hash() and not os.environ.get("FN_SKIP_SOURCE_HASH"):
         raise NativeError("libfitnoise_b200.so was built from different sources than fitnoise_b200/csrc "
                           "(ABI may not match the Python declarations); rebuild it")
     lib.fn_resident_begin.argtypes = [ctypes.c_void_p]
     lib.fn_resident_end.argtypes = [ctypes.c_void_p]
     lib.fn_l2_flush.argtypes = [ctypes.c_void_p]
+    lib.fn_result_dev.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
+                                  ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)]
+    lib.fn_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    lib.fn_bh_ranked_dev.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.POINTER(ctypes.c_void_p)]
+    lib.fn_pinned_alloc.argtypes = [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]
+    lib.fn_pinned_free.argtypes = [ctypes.c_void_p]
     lib.fn_resident_stats.restype = ctypes.c_int64
     lib.fn_resident_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.fn_launch_count.restype = ctypes.c_int64
@@ -144,6 +157,39 @@ def _f64(a, shape=None):
     if shape is not None:
         assert a.shape == tuple(shape), "expected shape %s, got %s" % (tuple(shape), a.shape)
     return a
+
+
+class _PinnedBlock(object):
+    """Owner of one block of pooled pinned host memory; numpy arrays made from it keep it alive and
+    the block goes back to the library's pool when the last of them dies."""
+
+    def __init__(self, lib, nbytes):
+        ptr = ctypes.c_void_p()
+        if lib.fn_pinned_alloc(int(nbytes), ctypes.byref(ptr)) != 0:
+            raise NativeError(lib.fn_last_error().decode())
+        self._lib, self.ptr, self.nbytes = lib, ptr.value, int(nbytes)
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._lib.fn_pinned_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy.empty in pinned host memory (a DMA target: device-to-host copies run at PCIe rate and
+    touch no fresh pages).  Falls back to plain memory for empty arrays."""
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype)
+    block = _PinnedBlock(load_library(), nbytes)
+    return np.asarray(block).view(dtype).reshape(shape)
 
 
 class Engine(object):
@@ -270,16 +316,21 @@ class Engine(object):
 
     def per_gene(self, theta):
         theta = _f64(theta).reshape(-1)
-        score, d2, p = np.empty(self.n), np.empty(self.n), np.empty(self.n, dtype=np.int32)
+        score, d2, p = pinned_empty(self.n), pinned_empty(self.n), pinned_empty(self.n, np.int32)
         self._check(self._lib.fn_per_gene(self._h, _dp(theta), len(theta), _dp(score), _dp(d2),
                                           p.ctypes.data_as(c_int32_p)))
         return score, d2, p
 
     def noise_stats(self, theta):
         theta = _f64(theta).reshape(-1)
-        noise_p, averages = np.empty(self.n), np.empty(self.n)
+        noise_p, averages = pinned_empty(self.n), pinned_empty(self.n)
         self._check(self._lib.fn_noise_stats(self._h, _dp(theta), len(theta), _dp(noise_p), _dp(averages)))
         return noise_p, averages
+
+    def noise_stats_dev(self, theta):
+        """noise_stats with the results left on the device (result_dev(RES_NOISE_P / RES_AVERAGES))."""
+        theta = _f64(theta).reshape(-1)
+        self._check(self._lib.fn_noise_stats(self._h, _dp(theta), len(theta), None, None))
 
     # ---- coefficients and tests -----------------------------------------------------------
     def coef(self, theta, design, want_covar=True):
@@ -288,18 +339,49 @@ class Engine(object):
         theta = _f64(theta).reshape(-1)
         design = _f64(design)
         c = design.shape[1]
-        coef = np.empty((self.n, c))
-        covar = np.empty((self.n, c, c)) if want_covar else None
-        dfpost = np.empty(self.n) if want_covar else None
+        coef = pinned_empty((self.n, c))
+        covar = pinned_empty((self.n, c, c)) if want_covar else None
+        dfpost = pinned_empty(self.n) if want_covar else None
         self._check(self._lib.fn_coef(self._h, _dp(theta), len(theta), c, _dp(design), _dp(coef),
                                       _dp(covar), _dp(dfpost)))
         self._coef_c = c
         return coef, covar, dfpost
 
+    def coef_dev(self, theta, design):
+        """coef() with every result left on the device (result_dev(RES_COEF / RES_COVAR / RES_DFPOST))."""
+        theta = _f64(theta).reshape(-1)
+        design = _f64(design)
+        self._check(self._lib.fn_coef(self._h, _dp(theta), len(theta), design.shape[1], _dp(design), None, None, None))
+        self._coef_c = design.shape[1]
+
+    def test_dev(self, contrasts):
+        """test() with the results left on the device (result_dev(RES_CONTRASTED / RES_P))."""
+        contrasts = _f64(contrasts)
+        self._check(self._lib.fn_test(self._h, contrasts.shape[1], _dp(contrasts), None, None, None))
+
+    def result_dev(self, which):
+        """(device pointer, rows, columns, dtype) of a result of the last call that computed it."""
+        ptr, rows, cols = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int32()
+        self._check(self._lib.fn_result_dev(self._h, which, ctypes.byref(ptr), ctypes.byref(rows), ctypes.byref(cols)))
+        return ptr.value, rows.value, cols.value, np.dtype(RES_DTYPE.get(which, np.float64))
+
+    def fetch(self, out, dev_ptr):
+        """Copy out.nbytes from device memory at dev_ptr into the (contiguous) host array `out`."""
+        assert out.flags["C_CONTIGUOUS"]
+        if out.nbytes:
+            self._check(self._lib.fn_fetch(self._h, out.ctypes.data, dev_ptr, out.nbytes))
+        return out
+
+    def bh_ranked_dev(self, n, p_ptr, q_ptr):
+        """BH over n device-resident p-values; returns the device pointer of the order (uint32 x n)."""
+        order = ctypes.c_void_p()
+        self._check(self._lib.fn_bh_ranked_dev(self._h, n, p_ptr, q_ptr, ctypes.byref(order)))
+        return order.value
+
     def coef_fetch(self):
         """Covariances (n x c x c) and posterior df (n) of the last coef()."""
         c = self._coef_c
-        covar, dfpost = np.empty((self.n, c, c)), np.empty(self.n)
+        covar, dfpost = pinned_empty((self.n, c, c)), pinned_empty(self.n)
         self._check(self._lib.fn_coef_fetch(self._h, None, _dp(covar), _dp(dfpost)))
         return covar, dfpost
 
@@ -307,8 +389,8 @@ class Engine(object):
         """test() and the BH adjustment of its p-values in one call (p stays on the device)."""
         contrasts = _f64(contrasts)
         kc = contrasts.shape[1]
-        contrasted, p, q = np.empty((self.n, kc)), np.empty(self.n), np.empty(self.n)
-        order = np.empty(self.n, dtype=np.uint32)
+        contrasted, p, q = pinned_empty((self.n, kc)), pinned_empty(self.n), pinned_empty(self.n)
+        order = pinned_empty(self.n, np.uint32)
         self._check(self._lib.fn_test_bh(self._h, kc, _dp(contrasts), _dp(contrasted), _dp(p), _dp(q),
                                          order.ctypes.data))
         self.last_order = order
@@ -317,22 +399,22 @@ class Engine(object):
     def test(self, contrasts, want_covar=False):
         contrasts = _f64(contrasts)
         kc = contrasts.shape[1]
-        contrasted = np.empty((self.n, kc))
-        ccov = np.empty((self.n, kc, kc)) if want_covar else None
-        p = np.empty(self.n)
+        contrasted = pinned_empty((self.n, kc))
+        ccov = pinned_empty((self.n, kc, kc)) if want_covar else None
+        p = pinned_empty(self.n)
         self._check(self._lib.fn_test(self._h, kc, _dp(contrasts), _dp(contrasted), _dp(ccov), _dp(p)))
         return contrasted, ccov, p
 
     def bh(self, p):
         p = _f64(p).reshape(-1)
-        q = np.empty(len(p))
+        q = pinned_empty(len(p))
         self._check(self._lib.fn_bh(self._h, len(p), _dp(p), _dp(q)))
         return q
 
     def bh_ranked(self, p):
         """(q, order): BH q-values and the genes by ascending p (stable, NaN last)."""
         p = _f64(p).reshape(-1)
-        q, order = np.empty(len(p)), np.empty(len(p), dtype=np.uint32)
+        q, order = pinned_empty(len(p)), pinned_empty(len(p), np.uint32)
         if len(p):
             self._check(self._lib.fn_bh_ranked(self._h, len(p), _dp(p), _dp(q), order.ctypes.data))
         return q, order
@@ -342,7 +424,7 @@ class Engine(object):
 
     def weights(self, theta):
         theta = _f64(theta).reshape(-1)
-        out = np.empty((self.n, self.m))
+        out = pinned_empty((self.n, self.m))
         self._check(self._lib.fn_weights(self._h, _dp(theta), len(theta), _dp(out)))
         return out
 

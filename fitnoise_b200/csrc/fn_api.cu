@@ -159,6 +159,10 @@ struct fn_handle {
 
     int coef_c = 0;
     bool coef_is_t = false;
+    // device-resident results of the last fn_test / fn_test_bh (inside scratch_dev)
+    double *test_out = nullptr, *test_p = nullptr, *test_q = nullptr;
+    uint32_t* test_order = nullptr;
+    int test_kc = 0;
     double *coef = nullptr, *covar = nullptr, *dfpost = nullptr, *x_coef = nullptr, *rinv_dev = nullptr;
     double* scratch_dev = nullptr;     // misc device scratch
     size_t scratch_cap = 0;
@@ -185,7 +189,7 @@ struct fn_handle {
     unsigned long long host_seq = 0;   // completion-flag sequence of the pinned result buffer
     // histogram of residual df over the genes in the REML sum (prepare kernel): the (v, p)-only terms of
     // the objective are added on the host from it (table_terms)
-    DevBuf b_phist;
+    DevBuf b_phist, b_bhwork;
     std::vector<long long> p_hist;
     double psum_expected = 0.0;
     // resident evaluation kernel (fn_resident_begin / _end): command block and state
@@ -239,6 +243,7 @@ static void release_data(fn_handle* h) {
     h->pg_score = h->pg_d2 = h->noise_p = nullptr;
     h->pg_p = nullptr;
     h->coef = h->covar = h->dfpost = h->x_coef = h->rinv_dev = nullptr;
+    h->test_out = h->test_p = h->test_q = nullptr; h->test_order = nullptr; h->test_kc = 0;
     h->zn = h->zc = h->fsq = nullptr;
     h->factors.clear();
     h->loaded = false;
@@ -247,7 +252,7 @@ static void release_data(fn_handle* h) {
 
 static void free_buffers(fn_handle* h) {
     release_data(h);
-    DevBuf* all[] = {&h->b_phist, &h->b_y, &h->b_aux, &h->b_gs, &h->b_cst, &h->b_avg, &h->b_status, &h->b_xn, &h->b_xc, &h->b_tab,
+    DevBuf* all[] = {&h->b_phist, &h->b_bhwork, &h->b_y, &h->b_aux, &h->b_gs, &h->b_cst, &h->b_avg, &h->b_status, &h->b_xn, &h->b_xc, &h->b_tab,
                      &h->b_pg_score, &h->b_pg_d2, &h->b_pg_p, &h->b_noise_p, &h->b_coef, &h->b_covar, &h->b_dfpost,
                      &h->b_xcoef, &h->b_rinv, &h->b_zn, &h->b_zc, &h->b_fsq, &h->b_tx, &h->b_tq, &h->b_ta, &h->b_tmean};
     for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
@@ -1479,6 +1484,7 @@ static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* 
     tp.n = h->n; tp.c = c; tp.kc = kc; tp.is_t = h->coef_is_t;
     tp.coef = h->coef; tp.covar = h->covar; tp.dfpost = h->dfpost; tp.contrasts = d_con;
     tp.contrasted = d_out; tp.ccov = d_cc; tp.pval = d_p;
+    h->test_out = d_out; h->test_p = d_p; h->test_q = nullptr; h->test_order = nullptr; h->test_kc = kc;
     const int tb = 128;
     if (h->n > 0) {
         test_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(tp);
@@ -1492,6 +1498,7 @@ static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* 
         uint32_t* d_order = nullptr;
         rc = bh_run(h, h->n, d_p, d_q, base, &d_order);   // p never leaves the device between test and BH
         if (rc) return rc;
+        h->test_q = d_q; h->test_order = d_order;
         D2H_TRY(qval, d_q, nb_p);
         if (order) D2H_TRY(order, d_order, (size_t)h->n * sizeof(uint32_t));
     }
@@ -1667,6 +1674,105 @@ static int bh_host(fn_handle* h, int64_t n, const double* p, double* q, uint32_t
     if (order) D2H_TRY(order, d_order, n * sizeof(uint32_t));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-resident results, pinned host memory
+// ------------------------------------------------------------------------------------------
+// Where the last per-gene results live on the device (for device-to-device gathers across ranks).
+extern "C" int fn_result_dev(fn_handle* h, int32_t which, void** ptr, int64_t* rows, int32_t* cols) {
+    if (!h || !h->loaded || !ptr || !rows || !cols) return fail(FN_ERR_ARG, "fn_result_dev: bad arguments");
+    void* p = nullptr;
+    int c = 1;
+    switch (which) {
+        case FN_RES_SCORE: p = h->pg_score; break;
+        case FN_RES_D2: p = h->pg_d2; break;
+        case FN_RES_PDF: p = h->pg_p; break;
+        case FN_RES_NOISE_P: p = h->noise_p; break;
+        case FN_RES_AVERAGES: p = h->avg; break;
+        case FN_RES_COEF: p = h->coef; c = h->coef_c; break;
+        case FN_RES_COVAR: p = h->covar; c = h->coef_c * h->coef_c; break;
+        case FN_RES_DFPOST: p = h->dfpost; break;
+        case FN_RES_CONTRASTED: p = h->test_out; c = h->test_kc; break;
+        case FN_RES_P: p = h->test_p; break;
+        case FN_RES_Q: p = h->test_q; break;
+        case FN_RES_ORDER: p = h->test_order; break;
+        default: return fail(FN_ERR_ARG, "fn_result_dev: unknown result %d", which);
+    }
+    if (!p) return fail(FN_ERR_STATE, "fn_result_dev: result %d has not been computed", which);
+    *ptr = p; *rows = h->n; *cols = c;
+    return 0;
+}
+
+// Device -> host copy on the handle's stream (pinned destination: one DMA; pageable: staged), then wait.
+extern "C" int fn_fetch(fn_handle* h, void* dst_host, const void* src_dev, int64_t bytes) {
+    if (!h || (bytes > 0 && (!dst_host || !src_dev)) || bytes < 0) return fail(FN_ERR_ARG, "fn_fetch: bad arguments");
+    LEAVE_RESIDENT(h);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (bytes) D2H_TRY(dst_host, src_dev, (size_t)bytes);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// Pinned host memory from a process-wide pool: result arrays are DMA targets (PCIe rate instead of
+// the page-faulting, single-threaded path into fresh pageable memory), and pinning itself is slow
+// (~1 ms per 4 MB), so freed blocks are kept and handed out again.
+static std::mutex g_pin_mutex;
+static std::multimap<size_t, void*> g_pin_free;
+static std::map<void*, size_t> g_pin_size;
+static size_t g_pin_held = 0;
+
+extern "C" int fn_pinned_alloc(int64_t bytes, void** out) {
+    if (!out || bytes < 0) return fail(FN_ERR_ARG, "fn_pinned_alloc: bad arguments");
+    size_t cap = 4096;
+    while (cap < (size_t)bytes) cap *= 2;
+    if (cap > (64u << 20)) cap = ((size_t)bytes + (16u << 20) - 1) / (16u << 20) * (16u << 20);
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        auto it = g_pin_free.lower_bound(cap);
+        if (it != g_pin_free.end() && it->first <= 2 * cap) {
+            *out = it->second;
+            g_pin_held -= it->first;
+            g_pin_free.erase(it);
+            return 0;
+        }
+    }
+    void* p = nullptr;
+    CUDA_TRY(cudaHostAlloc(&p, cap, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    g_pin_size[p] = cap;
+    *out = p;
+    return 0;
+}
+
+extern "C" int fn_pinned_free(void* p) {
+    if (!p) return 0;
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    auto it = g_pin_size.find(p);
+    if (it == g_pin_size.end()) return fail(FN_ERR_ARG, "fn_pinned_free: not a block of fn_pinned_alloc");
+    const size_t cap = it->second;
+    if (g_pin_held + cap > ((size_t)4 << 30)) {          // keep at most 4 GB of idle pinned memory
+        g_pin_size.erase(it);
+        cudaFreeHost(p);
+        return 0;
+    }
+    g_pin_free.insert(std::make_pair(cap, p));
+    g_pin_held += cap;
+    return 0;
+}
+
+// Benjamini-Hochberg on device-resident p (n values, e.g. gathered from all ranks): q_dev receives the
+// q-values, *order_dev points at the genes by ascending p (inside the handle's scratch; valid until
+// the next call that uses it).
+extern "C" int fn_bh_ranked_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, uint32_t** order_dev) {
+    if (!h) return fail(FN_ERR_ARG, "NULL handle");
+    if (n < 0 || n >= (1LL << 32)) return fail(FN_ERR_UNSUPPORTED, "fn_bh: n out of range");
+    if (n == 0) return 0;
+    LEAVE_RESIDENT(h);
+    CUDA_TRY(cudaSetDevice(h->device));
+    // the scratch may hold the last test's results (p_dev may even point into it): use a dedicated buffer
+    CUDA_TRY(ensure_buf(h->b_bhwork, bh_work_bytes(n)));
+    return bh_run(h, n, p_dev, q_dev, (char*)h->b_bhwork.p, order_dev);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -175,27 +175,103 @@ class Session(object):
         """Factor vectors (m x nf) used by the per-gene statistics, coefficients and weights."""
         self.local.set_factors(factors)
 
+    # ---- per-gene results: local at world == 1, gathered device-to-device otherwise ---------
+    def _gather(self, which, keep_device=False):
+        """Result `which` (``_native.RES_*``) of ALL genes on every rank.  The shards are gathered
+        device-to-device (NCCL all-gather on the stream the kernels ran on) and come to the host once,
+        into pinned memory.  ``keep_device``: also return the gathered device tensor."""
+        ptr, rows, cols, dtype = self.local.result_dev(which)
+        full = self._gather_dev(ptr, rows, cols, dtype)
+        shape = (self.n,) if cols == 1 and which not in (_native.RES_COEF, _native.RES_CONTRASTED) else (self.n, cols)
+        out = _native.pinned_empty(shape, dtype)
+        self.local.fetch(out, full.data_ptr())
+        return (out, full) if keep_device else out
+
+    def _gather_dev(self, ptr, rows, cols, dtype):
+        """All ranks' row blocks (device memory at ptr: rows x cols) as one contiguous n x cols device
+        tensor on this rank."""
+        torch = self._torch
+        import torch.distributed as dist
+        tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32,
+                  np.dtype(np.uint32): torch.int32}[np.dtype(dtype)]
+        sizes = np.diff(self.bounds)
+        width = int(sizes.max())
+        with torch.cuda.stream(self._stream):
+            local = _device_tensor(torch, ptr, (rows, cols), tdtype)
+            if rows != width:                                   # ragged shards: pad to the widest
+                padded = torch.zeros((width, cols), dtype=tdtype, device=local.device)
+                padded[:rows] = local
+                local = padded
+            full = torch.empty((self.world * width, cols), dtype=tdtype, device=local.device)
+            dist.all_gather_into_tensor(full, local.contiguous())
+            if int(sizes.min()) != width:                       # drop the padding rows
+                full = torch.cat([full[r * width:r * width + int(sizes[r])] for r in range(self.world)])
+        return full
+
+    @property
+    def _device_gather(self):
+        # several ranks on CUDA engines; a stand-in evaluator (CPU tests, gloo) gathers through the host
+        return self.world > 1 and self._cuda_reduce is not None
+
     def per_gene(self, theta):
         score, d2, p = self.local.per_gene(theta)
-        return (parallel.allgather_rows(score, self.n), parallel.allgather_rows(d2, self.n),
-                parallel.allgather_rows(p, self.n))
+        if self.world == 1:
+            return score, d2, p
+        if not self._device_gather:
+            return (parallel.allgather_rows(score, self.n), parallel.allgather_rows(d2, self.n),
+                    parallel.allgather_rows(p, self.n))
+        return (self._gather(_native.RES_SCORE), self._gather(_native.RES_D2), self._gather(_native.RES_PDF))
 
     def noise_stats(self, theta):
-        noise_p, averages = self.local.noise_stats(theta)
-        return parallel.allgather_rows(noise_p, self.n), parallel.allgather_rows(averages, self.n)
+        if not self._device_gather:
+            noise_p, averages = self.local.noise_stats(theta)
+            return parallel.allgather_rows(noise_p, self.n), parallel.allgather_rows(averages, self.n)
+        self.local.noise_stats_dev(theta)
+        return self._gather(_native.RES_NOISE_P), self._gather(_native.RES_AVERAGES)
 
     # ---- coefficients, tests --------------------------------------------------------------
     def coef(self, theta, design, token):
-        """Coefficients now; their covariances and posterior df stay on the GPU until asked for."""
-        coef, _, _ = self.local.coef(theta, design, want_covar=False)
+        """Coefficients now; their covariances and posterior df stay on the GPU until asked for.
+        With several ranks the covariances of ALL genes are gathered to this rank's GPU right away
+        (NVLink), so that fetching them later is a local copy and not a collective that every
+        rank would have to enter."""
         self.coef_token = token
-        return parallel.allgather_rows(coef, self.n)
+        if self.world == 1:
+            coef, _, _ = self.local.coef(theta, design, want_covar=False)
+            return coef
+        if not self._device_gather:
+            # the covariances are gathered right away as well: a later, lazy gather would be a
+            # collective that only some ranks might enter
+            coef, covar, dfpost = self.local.coef(theta, design, want_covar=True)
+            self._covar_host = (parallel.allgather_rows(covar, self.n), parallel.allgather_rows(dfpost, self.n))
+            return parallel.allgather_rows(coef, self.n)
+        self.local.coef_dev(theta, design)
+        coef = self._gather(_native.RES_COEF)
+        c = coef.shape[1]
+        ptr, rows, cols, dtype = self.local.result_dev(_native.RES_COVAR)
+        self._covar_dev = self._gather_dev(ptr, rows, cols, dtype)
+        ptr, rows, cols, dtype = self.local.result_dev(_native.RES_DFPOST)
+        self._dfpost_dev = self._gather_dev(ptr, rows, cols, dtype)
+        self._coef_c = c
+        return coef
 
     def coef_covar(self, theta, design, token):
-        if self.coef_token is not token:              # another fit_coef ran on this session since
-            self.coef(theta, design, token)
-        covar, dfpost = self.local.coef_fetch()
-        return parallel.allgather_rows(covar, self.n), parallel.allgather_rows(dfpost, self.n)
+        """(covar n x c x c, dfpost n); never a collective."""
+        if self.world == 1:
+            if self.coef_token is not token:          # another fit_coef ran on this session since
+                self.coef(theta, design, token)
+            return self.local.coef_fetch()
+        if self.coef_token is token and not self._device_gather:
+            return self._covar_host
+        if self.coef_token is not token:
+            raise RuntimeError("the coefficient covariances of this fit are no longer on the GPU: another "
+                               "fit_coef ran on the session since (with several ranks they cannot be "
+                               "recomputed lazily: every rank would have to take part)")
+        c = self._coef_c
+        covar, dfpost = _native.pinned_empty((self.n, c, c)), _native.pinned_empty(self.n)
+        self.local.fetch(covar, self._covar_dev.data_ptr())
+        self.local.fetch(dfpost, self._dfpost_dev.data_ptr())
+        return covar, dfpost
 
     def test(self, contrasts):
         """contrasted, p_values, q_values (BH over ALL genes), order (genes by ascending p, stable,
@@ -203,9 +279,22 @@ class Session(object):
         if self.world == 1:
             contrasted, p, q = self.local.test_bh(contrasts)   # p never leaves the device before the adjustment
             return contrasted, p, q, self.local.last_order
-        contrasted, _, p = self.local.test(contrasts)
-        contrasted, p = parallel.allgather_rows(contrasted, self.n), parallel.allgather_rows(p, self.n)
-        q, order = self.local.bh_ranked(p)
+        if not self._device_gather:
+            contrasted, _, p = self.local.test(contrasts)
+            contrasted, p = parallel.allgather_rows(contrasted, self.n), parallel.allgather_rows(p, self.n)
+            q, order = self.local.bh_ranked(p)
+            return contrasted, p, q, order
+        torch = self._torch
+        self.local.test_dev(contrasts)
+        contrasted = self._gather(_native.RES_CONTRASTED)
+        p, p_dev = self._gather(_native.RES_P, keep_device=True)
+        # every rank adjusts the full, device-resident p vector on its own GPU
+        with torch.cuda.stream(self._stream):
+            q_dev = torch.empty(self.n, dtype=torch.float64, device=p_dev.device)
+        order_ptr = self.local.bh_ranked_dev(self.n, p_dev.data_ptr(), q_dev.data_ptr())
+        q, order = _native.pinned_empty(self.n), _native.pinned_empty(self.n, np.uint32)
+        self.local.fetch(q, q_dev.data_ptr())
+        self.local.fetch(order, order_ptr)
         return contrasted, p, q, order
 
     def bh(self, p):
@@ -214,3 +303,18 @@ class Session(object):
 
     def weights(self, theta):
         return parallel.allgather_rows(self.local.weights(theta), self.n)
+
+
+class _DevicePointer(object):
+    """Zero-copy view of raw device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _device_tensor(torch, ptr, shape, tdtype):
+    typestr = {torch.float64: "<f8", torch.int32: "<i4"}[tdtype]
+    if shape[0] == 0:
+        return torch.empty(shape, dtype=tdtype, device="cuda")
+    return torch.as_tensor(_DevicePointer(ptr, shape, typestr), device="cuda")

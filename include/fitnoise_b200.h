@@ -154,6 +154,24 @@ int fn_bh_ranked(fn_handle* h, int64_t n, const double* p, double* q, uint32_t* 
 /* device-resident form: p_dev, q_dev are device pointers of n doubles */
 int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev);
 
+/* Device-resident results.  Every output pointer of fn_noise_stats / fn_coef / fn_test / fn_test_bh
+ * may be NULL: the results then stay in device memory, where fn_result_dev finds them (pointer,
+ * rows = this handle's genes, columns) -- a multi-GPU caller all-gathers them device-to-device
+ * (NCCL on the same stream) instead of bouncing every array through the host.  fn_fetch copies
+ * device memory to the host on the handle's stream and waits. */
+enum { FN_RES_SCORE = 0, FN_RES_D2 = 1, FN_RES_PDF = 2 /* int32 */, FN_RES_NOISE_P = 3, FN_RES_AVERAGES = 4,
+       FN_RES_COEF = 5, FN_RES_COVAR = 6, FN_RES_DFPOST = 7, FN_RES_CONTRASTED = 8, FN_RES_P = 9,
+       FN_RES_Q = 10, FN_RES_ORDER = 11 /* uint32 */ };
+int fn_result_dev(fn_handle* h, int32_t which, void** ptr, int64_t* rows, int32_t* cols);
+int fn_fetch(fn_handle* h, void* dst_host, const void* src_dev, int64_t bytes);
+/* Benjamini-Hochberg over device-resident p (e.g. all ranks' p after a gather); *order_dev: genes by
+ * ascending p, in the handle's memory, valid until the next BH call. */
+int fn_bh_ranked_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, uint32_t** order_dev);
+/* Pinned host memory from a process-wide pool (result arrays are DMA targets; pinning is slow, so
+ * freed blocks are reused). */
+int fn_pinned_alloc(int64_t bytes, void** out);
+int fn_pinned_free(void* p);
+
 /* Model.get_weights (fitnoise.py:399-404): 1/sigma2, n x m. */
 int fn_weights(fn_handle* h, const double* theta, int32_t P, double* weights);
 

@@ -39,7 +39,7 @@ def make_case(config, n):
     return dict(model="Model_t_factors", y=y, design=design, context={}, test=dict(coef=[1])), fitnoise.Model_t_factors(1)
 
 
-single = {}
+single, forced = {}, {}
 for config, n in cases:                 # before the process group exists: plain single-GPU fits
     s, model = make_case(config, n)
     kw = {k: s[k] for k in ("controls", "control_design") if k in s}
@@ -47,7 +47,15 @@ for config, n in cases:                 # before the process group exists: plain
     t = f.test(**s["test"])
     single[config] = (f.optimization_result.x.copy(), f.optimization_result.fun, t.p_values.copy(), t.q_values.copy(),
                       f.noise_p_values.copy())
+    # and everything else at a FORCED theta, so that the sharded run can be compared to the last bit
+    f2 = model.fit(fitnoise.Dataset(s["y"], s["context"]), s["design"], force_param=f.optimization_result.x, **kw)
+    t2 = f2.test(**s["test"])
+    forced[config] = dict(coef=f2.coef.copy(), covar=f2._coef_covar.copy(), dfpost=f2._coef_df.copy(),
+                          contrasts=t2.contrasts.copy(), p=t2.p_values.copy(), q=t2.q_values.copy(),
+                          order=t2._order.copy(), noise_p=f2.noise_p_values.copy(), averages=f2.averages.copy(),
+                          weights=f2.get_weights().copy(), combined=f2.noise_combined_p_value)
     f._session.close()
+    f2._session.close()
 
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 for config, n in cases:
@@ -66,7 +74,18 @@ for config, n in cases:
     print("rank %d config %s world %d shard [%d,%d): dtheta %.2e dfun %.2e dp %.2e dnoise_p %.2e nan-pattern %s -> %s" % (
         rank, config, f._session.world, f._session.lo, f._session.hi, dx, dfun, dp, dnp, same_nan, "OK" if good else "FAIL"),
         flush=True)
+    # forced theta: per-gene results do not depend on how the genes are sharded -> identical arrays
+    f2 = model.fit(fitnoise.Dataset(s["y"], s["context"]), s["design"], force_param=x1, **kw)
+    t2 = f2.test(**s["test"])
+    got = dict(coef=f2.coef, covar=f2._coef_covar, dfpost=f2._coef_df, contrasts=t2.contrasts, p=t2.p_values,
+               q=t2.q_values, order=t2._order, noise_p=f2.noise_p_values, averages=f2.averages,
+               weights=f2.get_weights(), combined=f2.noise_combined_p_value)
+    bad = [k for k in got if not np.array_equal(np.asarray(got[k]), np.asarray(forced[config][k]), equal_nan=True)]
+    ok &= not bad
+    print("rank %d config %s forced theta: %s" % (rank, config, "all per-gene results identical to one GPU" if not bad
+                                                   else "DIFFER: %s" % bad), flush=True)
     f._session.close()
+    f2._session.close()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

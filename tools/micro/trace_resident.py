@@ -14,6 +14,7 @@ sys.path.insert(0, ROOT)
 from fitnoise_b200 import build
 build.LIB_PATH = os.path.join(ROOT, "tools", "micro", "libfn_trace.so")
 build.needs_build = lambda: False
+os.environ["FN_SKIP_SOURCE_HASH"] = "1"       # development build: whatever the sources were
 import fitnoise_b200 as fitnoise
 from fitnoise_b200 import _native
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
