@@ -148,7 +148,11 @@ struct GeneView {
         blocked = (lpg <= bsize) ? 1 : 0;
         steps = blocked ? bsize / lpg : 0;
         nblk = blocked ? m / bsize : 0;
-        skew = blocked ? gene_local : 0;
+        // Rows are m doubles apart: with B < 16 the rows of 16/B consecutive genes start in different
+        // bank pairs already, so the rotation only has to separate genes 16/B apart: gene_local * B / 16.
+        // (Rotating by gene_local itself put genes g and g + 8/lpg of a half-warp into the same bank
+        // pair whenever B = 8: two-way conflicts on every load at m = 24, 40, 56, ...)
+        skew = blocked ? (gene_local * bsize) / 16 : 0;
     }
     // Visit this lane's samples, each exactly once; `on` = false visits nothing.  The order only
     // changes the association of the floating-point sums.  Every thread of a warp makes the same
@@ -352,10 +356,23 @@ struct Normal {
     }
 };
 
+// Row stride of a design table.  In shared memory the rows are padded to an ODD number of doubles:
+// the lanes of a warp visit different samples j at the same step (the bank rotation of GeneView), and
+// with an odd stride 16 different rows start in 16 different bank pairs, so a warp-wide read of one
+// design column costs the two wavefronts an 8-byte access needs and no more (stride 6 put two rows in
+// every bank pair: 14 wavefronts per warp-sample at c = 6).  Host builds keep the dense layout.
+template <int C> struct XStride {
+#ifdef __CUDA_ARCH__
+    enum { V = C | 1 };
+#else
+    enum { V = C };
+#endif
+};
+
 template <int C>
 FN_HD void load_x(const double* X, int j, double* x) {
 #pragma unroll
-    for (int i = 0; i < C; ++i) x[i] = X[j * C + i];
+    for (int i = 0; i < C; ++i) x[i] = X[j * XStride<C>::V + i];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -291,6 +291,16 @@ __device__ __forceinline__ void fill_density_tables(int is_t, double v, int m, d
     __syncthreads();
 }
 
+// Copy an m x C design table from global memory into shared memory with the padded row stride.
+template <int C>
+__device__ __forceinline__ void stage_design(double* dst, const double* src, int m) {
+    constexpr int XS = XStride<C>::V;
+    for (int i = threadIdx.x; i < m * C; i += blockDim.x) {
+        const int j = i / C, k = i - j * C;
+        dst[j * XS + k] = src[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // shared-memory carve-up common to the per-gene kernels
 // ------------------------------------------------------------------------------------------
@@ -338,9 +348,11 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
     const TileLayout L = tile_layout(p.src);
     tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);
     double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
-    double* xc = xn + m * C;
-    unsigned int* hist = (unsigned int*)(xc + m * C);          // m + 1 counters of this CTA
-    for (int i = threadIdx.x; i < m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
+    constexpr int XS = XStride<C>::V;
+    double* xc = xn + m * XS;
+    unsigned int* hist = (unsigned int*)(xc + m * XS);          // m + 1 counters of this CTA
+    stage_design<C>(xn, p.xn, m);
+    stage_design<C>(xc, p.xc, m);
     for (int i = threadIdx.x; i <= m; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
 
@@ -551,15 +563,17 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
     // tables behind the stage area: xn, xc (m*C each), ta, tb (m each), t0, t1 (m+1 each),
     // vals (ACC_FIXED + 2m), colscr (2*blockDim when a theta block is per-sample)
     double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
-    double* xc = xn + m * C;
-    double* ta = xc + m * C;
+    constexpr int XS = XStride<C>::V;
+    double* xc = xn + m * XS;
+    double* ta = xc + m * XS;
     double* tb = ta + m;
     double* t0 = tb + m;
     double* t1 = t0 + (m + 1);
     double* vals = t1 + (m + 1);
     double* colscr = vals + (ACC_FIXED + 2 * m);
     const bool inplace = p.inplace_a || p.inplace_b;
-    for (int i = threadIdx.x; i < m * C; i += blockDim.x) { xn[i] = p.xn[i]; xc[i] = p.xc[i]; }
+    stage_design<C>(xn, p.xn, m);
+    stage_design<C>(xc, p.xc, m);
     __syncthreads();                                   // barrier initialisation + designs visible
     ring.begin(smem_raw, bars, p.src, L);              // the first tiles are in flight
     FN_STAMP(1);
@@ -763,13 +777,15 @@ __global__ void __launch_bounds__(256) eval_factors_kernel(const EvalFactorsPara
     const TileLayout L = tile_layout(p.src);
     tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);
     double* zn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
-    double* zc = zn + m * C;
-    double* t0 = zc + m * C;
+    constexpr int XS = XStride<C>::V;
+    double* zc = zn + m * XS;
+    double* t0 = zc + m * XS;
     double* t1 = t0 + (m + 1);
     double* vals = t1 + (m + 1);
     double* colscr = vals + (ACC_FIXED + ncol);
     double* gscr = colscr + blockDim.x;              // genes x m x nf: d/dF terms of the current tile
-    for (int i = threadIdx.x; i < m * C; i += blockDim.x) { zn[i] = p.zn[i]; zc[i] = p.zc[i]; }
+    stage_design<C>(zn, p.zn, m);
+    stage_design<C>(zc, p.zc, m);
     const bool per_gene = p.pg_score != nullptr;
     if (per_gene) fill_density_tables(p.is_t, p.v, m, t0, t1);
     else __syncthreads();
@@ -870,9 +886,9 @@ __global__ void __launch_bounds__(256) coef_kernel(const CoefParams p) {
     const TileLayout L = tile_layout(p.src);
     tile_prologue(smem_raw, bars, p.g.stages, p.src, L, p.g.n_tiles);
     double* x = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
-    double* ta = x + m * C;
+    double* ta = x + m * XStride<C>::V;
     double* tb = ta + m;
-    for (int i = threadIdx.x; i < m * C; i += blockDim.x) x[i] = p.x[i];
+    stage_design<C>(x, p.x, m);
     for (int i = threadIdx.x; i < m; i += blockDim.x) { ta[i] = p.ta ? p.ta[i] : 0.0; tb[i] = p.tb ? p.tb[i] : 0.0; }
     for (int i = threadIdx.x; i < c * c; i += blockDim.x) rinv[i] = p.rinv[i];
     __syncthreads();

@@ -80,9 +80,16 @@ for config, n in cases:
     got = dict(coef=f2.coef, covar=f2._coef_covar, dfpost=f2._coef_df, contrasts=t2.contrasts, p=t2.p_values,
                q=t2.q_values, order=t2._order, noise_p=f2.noise_p_values, averages=f2.averages,
                weights=f2.get_weights(), combined=f2.noise_combined_p_value)
-    bad = [k for k in got if not np.array_equal(np.asarray(got[k]), np.asarray(forced[config][k]), equal_nan=True)]
+    # (not bit-identical: a gene's position inside its tile sets the order in which its samples are
+    # visited, and the shard boundaries move genes to other positions)
+    def same(key):
+        a, b = np.asarray(got[key]), np.asarray(forced[config][key])
+        if key == "order":
+            return np.array_equal(a, b)
+        return a.shape == b.shape and np.allclose(a, b, rtol=1e-11, atol=0.0, equal_nan=True)
+    bad = [k for k in got if not same(k)]
     ok &= not bad
-    print("rank %d config %s forced theta: %s" % (rank, config, "all per-gene results identical to one GPU" if not bad
+    print("rank %d config %s forced theta: %s" % (rank, config, "all per-gene results equal to one GPU (1e-11), top-table order identical" if not bad
                                                    else "DIFFER: %s" % bad), flush=True)
     f._session.close()
     f2._session.close()
