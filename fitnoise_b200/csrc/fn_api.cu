@@ -785,7 +785,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
 
     // K1
     Geom g;
-    const size_t table_bytes = 2 * (size_t)m * (width | 1) * sizeof(double) + (((size_t)m + 1) * sizeof(unsigned int) + 15) / 16 * 16;
+    const size_t table_bytes = 2 * (size_t)m * width * sizeof(double) + (((size_t)m + 1) * sizeof(unsigned int) + 15) / 16 * 16;
     int rc = choose_geom(h, h->has_aux, false, false, table_bytes, g, 0, 0, h->has_aux && fam.kind != KIND_PATSEQ);
     if (rc) return rc;
     rc = ensure_reduce(h, g.grid, PREP_NACC);
@@ -910,13 +910,20 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     const bool ia = per_sample_a(h), ib = per_sample_b(h);
     const bool inplace = ia || ib;
     Geom g;
-    const size_t table_bytes = (2 * (size_t)m * (h->width | 1) + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
-    const bool one_big_stage = (h->fam.kind == KIND_SCALE1 && h->has_aux) || (h->fam.kind == KIND_SCALE_PS && !h->has_aux);
+    const size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
+    const bool patseq_shared = h->fam.kind == KIND_PATSEQ && h->fam.na == 1 && h->fam.nb == 1 && h->width <= 4 &&
+                               !getenv("FN_NO_PATSEQ_SHARED");
+    const bool one_big_stage = (h->fam.kind == KIND_SCALE1 && h->has_aux) || (h->fam.kind == KIND_SCALE_PS && !h->has_aux) ||
+                               patseq_shared;
     int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0, 0, one_big_stage);
     if (rc) return rc;
     if (inplace && m > g.threads) return fail(FN_ERR_UNSUPPORTED, "per-sample variance models need m <= threads per CTA (%d)", g.threads);
     const KernelSet* ks = kernel_set(h->width);
     const void* kernel = ks ? ks->eval[h->fam.kind] : nullptr;
+    // PAT-Seq with one shared theta_a / theta_b: the single-sweep kernel (narrow designs)
+    if (ks && h->fam.kind == KIND_PATSEQ && h->fam.na == 1 && h->fam.nb == 1 && ks->eval[KIND_PATSEQ_SHARED] &&
+        !getenv("FN_NO_PATSEQ_SHARED"))
+        kernel = ks->eval[KIND_PATSEQ_SHARED];
     if (!kernel) return fail(FN_ERR_UNSUPPORTED, "no kernel for this design width");
     if (resident) {
         // every CTA of a resident kernel must be on the GPU at once (they wait for each other's sums)
@@ -1179,7 +1186,7 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
     const int m = h->m, nf = h->fam.nf, ncol = m * nf;
     if (!h->zn) return fail(FN_ERR_STATE, "factors have not been set (fn_set_factors / fn_nll_grad_factors)");
     Geom g;
-    const size_t table_bytes = (2 * (size_t)m * (h->width | 1) + 2 * (m + 1) + ACC_FIXED + ncol + 256) * sizeof(double);
+    const size_t table_bytes = (2 * (size_t)m * h->width + 2 * (m + 1) + ACC_FIXED + ncol + 256) * sizeof(double);
     int rc = choose_geom(h, h->has_aux, false, per_gene, table_bytes, g, ncol, (size_t)ncol * sizeof(double));
     if (rc) return rc;
     if (ncol > g.threads) return fail(FN_ERR_UNSUPPORTED, "factor models need m * n_factors <= threads per CTA (%d)", g.threads);
@@ -1427,7 +1434,7 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     h->coef_is_t = ts.is_t != 0;
 
     Geom g;
-    const size_t table_bytes = ((size_t)m * (d.width | 1) + 2 * m) * sizeof(double);
+    const size_t table_bytes = ((size_t)m * d.width + 2 * m) * sizeof(double);
     rc = choose_geom(h, h->has_aux, h->gs != nullptr, false, table_bytes, g, 0, 0, h->has_aux && h->fam.kind != KIND_PATSEQ);
     if (rc) return rc;
     CoefParams cp;

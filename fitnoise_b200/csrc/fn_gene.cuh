@@ -22,6 +22,8 @@
 namespace fn {
 
 enum { KIND_SCALE1 = 0, KIND_SCALE_PS = 1, KIND_PATSEQ = 2 };
+// kernel-internal specialisation of KIND_PATSEQ: one shared theta_a and theta_b (eval_patseq_shared)
+enum { KIND_PATSEQ_SHARED = 3 };
 enum { DIST_NORMAL = 0, DIST_T = 1, DIST_T_FIXED = 2 };
 
 // Variance family: sigma2_j = theta_a[j or 0] * U_j + theta_b[j or 0] * T_j   
@@ -356,17 +358,13 @@ struct Normal {
     }
 };
 
-// Row stride of a design table.  In shared memory the rows are padded to an ODD number of doubles:
-// the lanes of a warp visit different samples j at the same step (the bank rotation of GeneView), and
-// with an odd stride 16 different rows start in 16 different bank pairs, so a warp-wide read of one
-// design column costs the two wavefronts an 8-byte access needs and no more (stride 6 put two rows in
-// every bank pair: 14 wavefronts per warp-sample at c = 6).  Host builds keep the dense layout.
+// Row stride of a design table in shared memory: the dense stride C.  Rows of an even width are then
+// 16-byte aligned and a row is read with C/2 LDS.128; with the bank rotation of GeneView the quarter-
+// warps of such a read hit distinct 16-byte units (3 j mod 8 is a permutation for C = 6, j mod 8 for
+// C = 2).  (An odd stride removes the conflicts of LDS.64 reads but doubles the number of load
+// instructions -- measured slower at c = 6 on B200: 67 vs 48 us, 200k x 48.)
 template <int C> struct XStride {
-#ifdef __CUDA_ARCH__
-    enum { V = C | 1 };
-#else
     enum { V = C };
-#endif
 };
 
 template <int C>
@@ -805,6 +803,165 @@ FN_HD void eval_general(const EvalConst& ec, GeneView& gv, const double* X, int 
     if (!inplace_a) out.ga = lane_sum(ga, gv.lpg);
     if (KIND == KIND_PATSEQ && !inplace_b) out.gb = lane_sum(gb, gv.lpg);
     // every lane of the gene now holds the same totals: only lane 0 may add them to the CTA sums
+}
+
+// 1/x for a positive normal double.  Device: hardware seed (>= 20 bits) and two Newton steps, i.e. one
+// MUFU and four FMAs instead of the ~12-instruction correctly rounded division; the result is within
+// an ulp, and it only ever feeds sums over samples and genes.
+FN_HD double rcp_pos(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// KIND_PATSEQ with ONE shared theta_a and ONE shared theta_b (Model_*_patseq_v1 / _v2 / _v3 without
+// per-sample parameters; fitnoise.py:659-678, 757-776, 863-882): value AND gradient from a single sweep.
+//
+// The second sweep of eval_general exists to form  G_b = sum_j T_j e_j,  e_j = d(-ll)/d sigma2_j =
+// 1/2 (w_j - w_j^2 h_j) - kappa (w_j r_j)^2, which needs beta, A^-1 and kappa.  Expanded in moments that
+// the first sweep can accumulate next to the normal equations (t_j = T_j w_j^2):
+//   sum_j T_j w_j^2 h_j   = tr(A^-1 M_T),                M_T = sum_j t_j x_j x_j'
+//   sum_j T_j w_j^2 r_j^2 = S_Tyy - 2 beta'b_T + beta'M_T beta,   b_T = sum_j t_j x_j y_j,  S_Tyy = sum_j t_j y_j^2
+// so  G_b = 1/2 sum_j T_j w_j - 1/2 tr(A^-1 M_T) - kappa (S_Tyy - 2 beta'b_T + beta'M_T beta),  and because
+// theta_a U_j + theta_b T_j = sigma2_j:
+//   theta_a G_a + theta_b G_b = sum_j sigma2_j e_j = 1/2 (k - c) - kappa d2,
+// the theta_a gradient needs no moments of its own.  One sweep, no per-sample leverage, and the staged
+// tile is never written.  The quadratic form cancels like d2 = y'Wy - b'beta does; when that loses more
+// than four digits both are recomputed from residuals (a second sweep for those genes only).
+// Returns out.ga multiplied by theta_a, as eval_general does for this kind.
+template <int C>
+FN_HD void eval_patseq_shared(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
+                              bool eligible, double cst, EvalOut& out) {
+    const double tha = ec.ta[0], thb = ec.tb[0];
+    Normal<C> nm;
+    nm.init();
+    double mt[Tri<C>::N], bt[C];
+#pragma unroll
+    for (int i = 0; i < Tri<C>::N; ++i) mt[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) bt[i] = 0.0;
+    double sums[2] = {0.0, 0.0};       // S_Tyy, sum_j T_j w_j
+    LogProd lp; lp.init();
+    double pend = 1.0;
+    int npend = 0;
+    // sigma2, validity and the weight of sample j
+    auto variance = [&](int j, double y, double& T, bool& valid) -> double {
+        const double rc = gv.aux[j];
+        const bool yok = finite_d(y);
+        const double U = ec.v3 ? rc * gv.gs : rc;
+        T = ec.tail_own ? (yok ? y * y : 0.0) : gv.gs;
+        const double s2 = tha * U + thb * T;
+        valid = yok && finite_d(s2);                      // Mv*.good: distributions.py:31-36
+        return s2;
+    };
+    gv.for_each(eligible, [&](int j) {
+        const double y = gv.y[j];
+        double T;
+        bool valid;
+        const double s2 = variance(j, y, T, valid);
+        const double w = valid ? rcp_pos(s2) : 0.0;
+        const double yv = valid ? y : 0.0;
+        const double t2 = valid ? T * w * w : 0.0;
+        double x[C];
+        load_x<C>(X, j, x);
+        nm.add(w, yv, x);
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const double tx = t2 * x[i];
+#pragma unroll
+            for (int q = 0; q <= i; ++q) mt[FN_TRI(i, q)] += tx * x[q];
+            bt[i] += tx * yv;
+        }
+        sums[0] += (t2 * yv) * yv;
+        if (valid) {
+            sums[1] += T * w;
+            ++nm.k;
+            pend *= s2;
+            if (++npend == 4) { lp.mul(pend); pend = 1.0; npend = 0; }
+        }
+    });
+    lp.mul(pend);
+    if (gv.lpg > 1) {
+        lp.lane_reduce(gv.lpg);
+        nm.reduce(gv.lpg);
+        lane_sum_n<Tri<C>::N>(mt, gv.lpg);
+        lane_sum_n<C>(bt, gv.lpg);
+        lane_sum_n<2>(sums, gv.lpg);
+    }
+    nm.pad(c_real);
+    double det;
+    const bool ok = chol<C, true>(nm.a, det, 0.0);
+    double beta[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
+    chol_solve<C>(nm.a, beta);
+    double d2 = nm.yy;
+#pragma unroll
+    for (int i = 0; i < C; ++i) d2 -= nm.b[i] * beta[i];
+    // sum_j T_j w_j^2 r_j^2
+    double quad = sums[0];
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        double mb = 0.0;
+#pragma unroll
+        for (int q = 0; q < C; ++q) mb += mt[q > i ? FN_TRI(q, i) : FN_TRI(i, q)] * beta[q];
+        quad += beta[i] * (mb - 2.0 * bt[i]);
+    }
+    if (warp_any(eligible && d2 < 1e-4 * nm.yy)) {          // cancellation: both from residuals
+        double r2[2] = {0.0, 0.0};
+        gv.for_each(eligible && d2 < 1e-4 * nm.yy, [&](int j) {
+            const double y = gv.y[j];
+            double T;
+            bool valid;
+            const double s2 = variance(j, y, T, valid);
+            if (valid) {
+                const double w = 1.0 / s2;
+                double x[C];
+                load_x<C>(X, j, x);
+                double r = y;
+#pragma unroll
+                for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
+                r2[0] += w * r * r;
+                r2[1] += T * w * w * r * r;
+            }
+        });
+        lane_sum_n<2>(r2, gv.lpg);
+        if (d2 < 1e-4 * nm.yy) { d2 = r2[0]; quad = r2[1]; }
+    }
+    if (d2 < 0.0) d2 = 0.0;
+
+    eval_zero(out);
+    const int p = nm.k - c_real;
+    const bool good = eligible && ok && p > 0 && d2 == d2;
+    if (!good) {
+        if (eligible) { out.value = NAN; out.used = 1; }
+        return;
+    }
+    const double logdet = lp.log_value() + log(det) + cst;
+    double dv, kappa;
+    out.value = finish_density(ec, p, logdet, d2, dv, kappa);
+    out.d2 = d2; out.p = p; out.used = 1;
+    if (!(out.value == out.value)) return;
+    out.dv = dv;
+    // tr(A^-1 M_T) over the real columns (padded columns have M = 0)
+    double ainv[Tri<C>::N];
+    chol_inverse<C>(nm.a, ainv);
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        tr += ainv[FN_TRI(i, i)] * mt[FN_TRI(i, i)];
+#pragma unroll
+        for (int q = 0; q < i; ++q) tr += 2.0 * ainv[FN_TRI(i, q)] * mt[FN_TRI(i, q)];
+    }
+    out.gb = 0.5 * (sums[1] - tr) - kappa * quad;
+    out.ga = 0.5 * p - kappa * d2 - thb * out.gb;          // theta_a G_a: the caller divides
 }
 
 // ------------------------------------------------------------------------------------------

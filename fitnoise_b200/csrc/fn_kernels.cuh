@@ -26,7 +26,7 @@ static __device__ unsigned long long g_trace[64];
 // parallel; the C-ABI layer launches them through this table (cudaLaunchKernel).
 struct KernelSet {
     const void* prepare;          // prepare_kernel<C>
-    const void* eval[3];          // eval_kernel<C, KIND_SCALE1 | KIND_SCALE_PS | KIND_PATSEQ>
+    const void* eval[4];          // eval_kernel<C, KIND_SCALE1 | KIND_SCALE_PS | KIND_PATSEQ | KIND_PATSEQ_SHARED (C <= 4, else null)>
     const void* eval_factors;     // eval_factors_kernel<C>
     const void* coef;             // coef_kernel<C>
 };
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
         if (per_gene) fill_density_tables(p.is_t, ec.v, m, t0, t1);      // ends with a barrier
         else if (KIND != KIND_SCALE1) __syncthreads();
         FN_STAMP(2);
-        ec.kind = KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t;
+        ec.kind = (KIND == KIND_PATSEQ_SHARED) ? KIND_PATSEQ : KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t;
         ec.ta = ta; ec.tb = tb;
         ec.t0 = per_gene ? t0 : nullptr; ec.t1 = per_gene ? t1 : nullptr;
         ec.finish_setup();
@@ -702,6 +702,20 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
             FN_STAMP(3);
             finalize();
             FN_STAMP(4);
+        } else if constexpr (KIND == KIND_PATSEQ_SHARED) {
+            // one sweep per gene, nothing written to the stage (eval_patseq_shared)
+            ring.pass(smem_raw, bars, p.src, L, false, [&](unsigned char* st, long long tile) {
+                const long long gene = tile * p.g.genes + gl;
+                gv.y = (double*)st + (size_t)gl * m;
+                gv.aux = (double*)(st + L.aux_off) + (size_t)gl * m;
+                gv.gs = p.src.gs ? ((const double*)(st + L.gs_off))[gl] : 0.0;
+                const uint8_t status = st[L.status_off + gl];
+                const bool control = (status & 2) != 0;
+                const double cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
+                EvalOut eo;
+                eval_patseq_shared<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, (status & 1) != 0, cst, eo);
+                if (lane == 0) account(eo, gene);
+            });
         } else {
             // PATSEQ keeps 1/sigma2 in the aux tile between its two sweeps: the stage is always written
             ring.pass(smem_raw, bars, p.src, L, inplace || KIND == KIND_PATSEQ, [&](unsigned char* st, long long tile) {

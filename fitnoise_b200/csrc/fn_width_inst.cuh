@@ -12,7 +12,13 @@ const KernelSet* FN_WCAT(kernel_set_w, FN_W)() {
     static const KernelSet ks = {
         (const void*)prepare_kernel<FN_W>,
         {(const void*)eval_kernel<FN_W, KIND_SCALE1>, (const void*)eval_kernel<FN_W, KIND_SCALE_PS>,
-         (const void*)eval_kernel<FN_W, KIND_PATSEQ>},
+         (const void*)eval_kernel<FN_W, KIND_PATSEQ>,
+#if FN_W <= 4
+         (const void*)eval_kernel<FN_W, KIND_PATSEQ_SHARED>
+#else
+         nullptr
+#endif
+        },
         (const void*)eval_factors_kernel<FN_W>,
         (const void*)coef_kernel<FN_W>,
     };

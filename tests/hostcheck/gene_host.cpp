@@ -4,6 +4,7 @@
 // It is NOT a CPU fallback: the product never loads this library (fitnoise_b200/_native.py only
 // loads libfitnoise_b200.so and raises when it or a CUDA device is missing).
 #include <stdint.h>
+#include <stdlib.h>
 #include <vector>
 #include "../../fitnoise_b200/csrc/fn_host.hpp"
 
@@ -93,6 +94,7 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
     }
     const int P = theta_length(*fam);
     for (int i = 0; i < P; ++i) grad[i] = 0.0;
+    const bool general_only = getenv("FN_NO_PATSEQ_SHARED") != nullptr;      // as the CUDA library: two-sweep path
     const int off_a = fam->dist == DIST_T ? 1 : 0, off_b = off_a + fam->na;
     double total = 0.0;
     std::vector<double> row(m), arow(m);
@@ -107,6 +109,7 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
             if (nf) eval_factors<C>(ec, gv, ((controls && controls[g]) ? zc : zn).data(), d.c, nf, pr.eligible[g], pr.cst[g], gscratch.data(), eo);
             else if (fam->kind == KIND_SCALE1) eval_scale1<C>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], eo);
             else if (fam->kind == KIND_SCALE_PS) eval_general<C, KIND_SCALE_PS>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], inpl_a, inpl_b, eo);
+            else if (fam->na == 1 && fam->nb == 1 && width <= 4 && !general_only) eval_patseq_shared<C>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], eo);
             else eval_general<C, KIND_PATSEQ>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], inpl_a, inpl_b, eo));
         score[g] = eo.used ? eo.value : NAN;
         d2[g] = eo.d2; pdf[g] = eo.p;
