@@ -12,6 +12,7 @@
 #include <utility>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "../../include/fitnoise_b200.h"
@@ -446,6 +447,34 @@ static int set_smem(fn_handle* h, K kernel, size_t bytes) {
     return 0;
 }
 
+// Every per-gene kernel is persistent (CTA b takes tiles b, b + grid, ...), and the ones that reduce
+// over the grid let CTA 0 wait for the partial sums of all the others (fn_kernels.cuh grid_reduce):
+// the grid must never exceed what the GPU holds at once, or the waiting CTA blocks the slot a queued
+// CTA needs (measured: 40 % slower at c = 6, where registers allow one CTA per SM, not the two
+// choose_geom plans for).  Occupancy per (device, kernel, threads, shared memory) is asked once.
+static std::map<std::tuple<int, const void*, int, size_t>, int> g_occupancy;
+
+static int bound_grid(fn_handle* h, const void* kernel, Geom& g) {
+    if (!kernel) return fail(FN_ERR_UNSUPPORTED, "no kernel for this design width");
+    int rc = set_smem(h, kernel, g.smem);
+    if (rc) return rc;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_smem_mutex);
+        const auto key = std::make_tuple(h->device, kernel, g.threads, g.smem);
+        auto it = g_occupancy.find(key);
+        if (it != g_occupancy.end()) per_sm = it->second;
+        else {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, g.threads, g.smem));
+            g_occupancy[key] = per_sm;
+        }
+    }
+    if (per_sm < 1) return fail(FN_ERR_UNSUPPORTED, "the kernel does not fit on an SM (%d threads, %zu bytes of shared memory)", g.threads, g.smem);
+    const long long cap = (long long)per_sm * h->sm_count;
+    if (g.grid > cap) g.grid = (int)cap;
+    return 0;
+}
+
 // launch one of the per-width kernels (all take their parameter block by value as the only argument)
 static int launch_width_kernel(fn_handle* h, const void* kernel, int grid, int threads, size_t smem, void* params) {
     if (!kernel) return fail(FN_ERR_UNSUPPORTED, "no kernel for this design width");
@@ -788,6 +817,11 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     const size_t table_bytes = 2 * (size_t)m * width * sizeof(double) + (((size_t)m + 1) * sizeof(unsigned int) + 15) / 16 * 16;
     int rc = choose_geom(h, h->has_aux, false, false, table_bytes, g, 0, 0, h->has_aux && fam.kind != KIND_PATSEQ);
     if (rc) return rc;
+    {
+        const KernelSet* ks0 = kernel_set(width);
+        rc = bound_grid(h, ks0 ? ks0->prepare : nullptr, g);
+        if (rc) return rc;
+    }
     rc = ensure_reduce(h, g.grid, PREP_NACC);
     if (rc) return rc;
     CUDA_TRY(ensure_buf(h->b_phist, ((size_t)m + 1) * sizeof(unsigned long long)));
@@ -910,7 +944,9 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     const bool ia = per_sample_a(h), ib = per_sample_b(h);
     const bool inplace = ia || ib;
     Geom g;
-    const size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
+    size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
+    if (h->fam.kind == KIND_SCALE_PS)      // complete-row fast path: two designs' tables, scratch, kappa per gene
+        table_bytes += (2 * (size_t)m * h->width + 2 * m + (size_t)h->width * (h->width + 1) / 2 + 8 + 256) * sizeof(double);
     const bool patseq_shared = h->fam.kind == KIND_PATSEQ && h->fam.na == 1 && h->fam.nb == 1 && h->width <= 4 &&
                                !getenv("FN_NO_PATSEQ_SHARED");
     const bool one_big_stage = (h->fam.kind == KIND_SCALE1 && h->has_aux) || (h->fam.kind == KIND_SCALE_PS && !h->has_aux) ||
@@ -925,16 +961,8 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
         !getenv("FN_NO_PATSEQ_SHARED"))
         kernel = ks->eval[KIND_PATSEQ_SHARED];
     if (!kernel) return fail(FN_ERR_UNSUPPORTED, "no kernel for this design width");
-    if (resident) {
-        // every CTA of a resident kernel must be on the GPU at once (they wait for each other's sums)
-        rc = set_smem(h, kernel, g.smem);
-        if (rc) return rc;
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, g.threads, g.smem));
-        if (per_sm < 1) return fail(FN_ERR_UNSUPPORTED, "the evaluation kernel does not fit on an SM");
-        const long long cap = (long long)per_sm * h->sm_count;
-        if (g.grid > cap) g.grid = (int)cap;
-    }
+    rc = bound_grid(h, kernel, g);       // resident or not: all CTAs on the GPU at once
+    if (rc) return rc;
     const int nacc = eval_nacc(h);
     rc = ensure_reduce(h, g.grid, nacc);
     if (rc) return rc;
@@ -1190,6 +1218,11 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
     int rc = choose_geom(h, h->has_aux, false, per_gene, table_bytes, g, ncol, (size_t)ncol * sizeof(double));
     if (rc) return rc;
     if (ncol > g.threads) return fail(FN_ERR_UNSUPPORTED, "factor models need m * n_factors <= threads per CTA (%d)", g.threads);
+    {
+        const KernelSet* ks0 = kernel_set(h->width);
+        rc = bound_grid(h, ks0 ? ks0->eval_factors : nullptr, g);
+        if (rc) return rc;
+    }
     const int nacc = ACC_FIXED + ncol;
     rc = ensure_reduce(h, g.grid, nacc);
     if (rc) return rc;

@@ -531,6 +531,43 @@ __device__ __forceinline__ int resident_wait(const ResidentCtl& rc, unsigned lon
     return (int)hdr[CW_OP];
 }
 
+// Per-evaluation tables of the complete-row fast path of KIND_SCALE_PS (fn_gene.cuh, PsDesign), built by
+// the whole CTA for one design: A = X'WX (thread per packed entry), its inverse (one thread: c <= 16),
+// then one table row per thread.  `tri`: Tri<C>::N doubles of scratch, `sc`: 3 doubles.
+template <int C>
+__device__ __forceinline__ void build_ps_design(const double* X, int c_real, const double* w, const double* lt, int m,
+                                                double* hx, double* cj, double* tri, double* sc) {
+    constexpr int N = Tri<C>::N;
+    for (int e = threadIdx.x; e < N; e += blockDim.x) {
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        const int k = e - i * (i + 1) / 2;
+        double a = 0.0;
+        for (int j = 0; j < m; ++j) a += w[j] * X[j * C + i] * X[j * C + k];
+        tri[e] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a[N], ainv[N];
+        for (int e = 0; e < N; ++e) a[e] = tri[e];
+        for (int i = c_real; i < C; ++i) a[FN_TRI(i, i)] = 1.0;
+        double det;
+        const bool ok = chol<C>(a, det, 0.0);
+        chol_inverse<C>(a, ainv);
+        for (int e = 0; e < N; ++e) tri[e] = ainv[e];
+        double slt = 0.0;
+        for (int j = 0; j < m; ++j) slt += lt[j];
+        sc[0] = log(det); sc[1] = slt; sc[2] = ok ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        double x[C];
+        load_x<C>(X, j, x);
+        ps_table_row<C>(tri, x, w[j], hx + j * C, cj[j]);
+    }
+    __syncthreads();
+}
+
 struct EvalParams {
     GeomParams g;
     TileSrc src;             // y, aux (precision weights / rc), gs, cst (per-gene mode only), status
@@ -572,6 +609,16 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
     double* vals = t1 + (m + 1);
     double* colscr = vals + (ACC_FIXED + 2 * m);
     const bool inplace = p.inplace_a || p.inplace_b;
+    // KIND_SCALE_PS without weights: tables of the complete-row fast path (two designs), kappa per gene
+    const bool fastps = KIND == KIND_SCALE_PS && p.src.aux == nullptr;
+    double* hxn = colscr + (inplace ? 2 * blockDim.x : 0);
+    double* hxc = hxn + m * C;
+    double* cjn = hxc + m * C;
+    double* cjc = cjn + m;
+    double* pstri = cjc + m;
+    double* pssc = pstri + Tri<C>::N;          // 2 x 3
+    double* kap = pssc + 8;                    // genes per tile
+    __shared__ int ps_count[2];
     stage_design<C>(xn, p.xn, m);
     stage_design<C>(xc, p.xc, m);
     __syncthreads();                                   // barrier initialisation + designs visible
@@ -637,6 +684,15 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
         }
         if (per_gene) fill_density_tables(p.is_t, ec.v, m, t0, t1);      // ends with a barrier
         else if (KIND != KIND_SCALE1) __syncthreads();
+        PsDesign<C> pdn, pdc;
+        if (fastps) {
+            build_ps_design<C>(xn, p.c_noise, ta, tb, m, hxn, cjn, pstri, pssc);
+            build_ps_design<C>(xc, p.c_ctrl, ta, tb, m, hxc, cjc, pstri, pssc + 3);
+            pdn.hx = hxn; pdn.cj = cjn; pdn.logdet_a = pssc[0]; pdn.slt = pssc[1]; pdn.ok = pssc[2] != 0.0;
+            pdc.hx = hxc; pdc.cj = cjc; pdc.logdet_a = pssc[3]; pdc.slt = pssc[4]; pdc.ok = pssc[5] != 0.0;
+            if (threadIdx.x < 2) ps_count[threadIdx.x] = 0;
+            __syncthreads();
+        }
         FN_STAMP(2);
         ec.kind = (KIND == KIND_PATSEQ_SHARED) ? KIND_PATSEQ : KIND; ec.tail_own = p.tail_own; ec.v3 = p.v3; ec.is_t = p.is_t;
         ec.ta = ta; ec.tb = tb;
@@ -729,15 +785,36 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
                 const bool control = (status & 2) != 0;
                 const bool eligible = (status & 1) != 0;
                 const double cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
+                const double* X = control ? xc : xn;
+                const int c_real = control ? p.c_ctrl : p.c_noise;
                 EvalOut eo;
-                eval_general<C, KIND>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, eligible, cst,
-                                      p.inplace_a != 0, p.inplace_b != 0, eo);
+                if (KIND == KIND_SCALE_PS && fastps) {
+                    // complete genes: shared normal matrix (PsDesign); the others: the general two sweeps
+                    const PsDesign<C>& pd = control ? pdc : pdn;
+                    double beta[C];
+                    const bool complete = ps_complete_beta<C>(pd, gv, eligible, beta);
+                    eval_zero(eo);
+                    if (warp_any(eligible && !complete))
+                        eval_general<C, KIND>(ec, gv, X, c_real, eligible && !complete, cst, true, false, eo,
+                                              eligible && !complete);
+                    EvalOut ef;
+                    double kappa;
+                    ps_complete_finish<C>(ec, pd, gv, X, c_real, complete, !eligible, beta, cst, ef, kappa);
+                    if (complete) eo = ef;
+                    if (lane == 0) {
+                        // the column sum multiplies the gene's slots by this: -kappa for s_j = (w_j r_j)^2
+                        kap[gl] = complete ? -kappa : 1.0;
+                        if (complete && kappa > 0.0 && gene < p.g.n) atomicAdd(&ps_count[control ? 1 : 0], 1);
+                    }
+                } else {
+                    eval_general<C, KIND>(ec, gv, X, c_real, eligible, cst, p.inplace_a != 0, p.inplace_b != 0, eo);
+                }
                 if (lane == 0) account(eo, gene);
                 if (inplace) {
                     __syncthreads();
                     if (sub < nsub) {
                         for (int g = sub; g < p.g.genes; g += nsub) {
-                            if (p.inplace_a) col_a += ys[(size_t)g * m + col];
+                            if (p.inplace_a) col_a += (KIND == KIND_SCALE_PS && fastps) ? kap[g] * ys[(size_t)g * m + col] : ys[(size_t)g * m + col];
                             if (p.inplace_b) col_b += auxs[(size_t)g * m + col];
                         }
                     }
@@ -754,6 +831,8 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
             if (threadIdx.x < m) {
                 double sa = 0.0, sb = 0.0;
                 for (int q = 0; q < nsub; ++q) { sa += colscr[q * m + threadIdx.x]; sb += colscr[blockDim.x + q * m + threadIdx.x]; }
+                // the gene-independent part of the complete genes' gradient, once per gene of this CTA
+                if (fastps) sa += ps_count[0] * cjn[threadIdx.x] + ps_count[1] * cjc[threadIdx.x];
                 vals[ACC_FIXED + threadIdx.x] = sa;
                 vals[ACC_FIXED + m + threadIdx.x] = sb;
             }

@@ -47,6 +47,43 @@ void prepare_all(const Family& fam, long n, int m, const double* y, const double
     pr.rowvar_mean = vcount ? vsum / vcount : NAN;
 }
 
+// host build of the complete-row tables of KIND_SCALE_PS (the CUDA kernel builds them per CTA:
+// fn_kernels.cuh build_ps_design)
+template <int C>
+struct PsHost {
+    std::vector<double> hx, cj;
+    PsDesign<C> pd;
+    void build(const Design& d, int m, const double* w, const double* lt) {
+        constexpr int N = Tri<C>::N;
+        double a[N], ainv[N];
+        for (int e = 0; e < N; ++e) a[e] = 0.0;
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < C; ++i)
+                for (int k = 0; k <= i; ++k) a[FN_TRI(i, k)] += w[j] * d.q[(size_t)j * C + i] * d.q[(size_t)j * C + k];
+        for (int i = d.c; i < C; ++i) a[FN_TRI(i, i)] = 1.0;
+        double det;
+        pd.ok = chol<C>(a, det, 0.0);
+        chol_inverse<C>(a, ainv);
+        hx.assign((size_t)m * C, 0.0); cj.assign(m, 0.0);
+        double slt = 0.0;
+        for (int j = 0; j < m; ++j) {
+            ps_table_row<C>(ainv, &d.q[(size_t)j * C], w[j], &hx[(size_t)j * C], cj[j]);
+            slt += lt[j];
+        }
+        pd.hx = hx.data(); pd.cj = cj.data(); pd.logdet_a = log(det); pd.slt = slt;
+    }
+};
+
+// one gene through the complete-row fast path; returns false when the row is not complete
+template <int C>
+bool ps_gene(const EvalConst& ec, const PsHost<C>& ps, GeneView& gv, const Design& d, bool eligible, double cst,
+             EvalOut& eo, double& kappa) {
+    double beta[C];
+    if (!ps_complete_beta<C>(ps.pd, gv, eligible, beta)) return false;
+    ps_complete_finish<C>(ec, ps.pd, gv, d.q.data(), d.c, true, false, beta, cst, eo, kappa);
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -105,6 +142,27 @@ int hc_eval(const Family* fam, long n, int m, const double* y, const double* aux
         const Design& d = (controls && controls[g]) ? dc : dn;
         EvalOut eo;
         const bool inpl_a = fam->na == m && fam->kind != KIND_SCALE1, inpl_b = fam->nb == m;
+        if (fam->kind == KIND_SCALE_PS && !aux_raw && !nf && !getenv("FN_NO_PS_FAST")) {
+            // complete genes: the shared-normal-matrix fast path, as the CUDA kernel does
+            bool done = false;
+            double kappa = 0.0;
+            const bool ctl = controls && controls[g];
+            FN_DISPATCH_WIDTH(width, {
+                static thread_local PsHost<C> psn, psc;
+                static thread_local const double* built_for = nullptr;
+                if (built_for != theta || g == 0) { psn.build(dn, m, ta.data(), tb.data()); psc.build(dc, m, ta.data(), tb.data()); built_for = theta; }
+                done = ps_gene<C>(ec, ctl ? psc : psn, gv, d, pr.eligible[g], pr.cst[g], eo, kappa);
+                if (done) {
+                    score[g] = eo.value; d2[g] = eo.d2; pdf[g] = eo.p; averages[g] = pr.average[g]; eligible[g] = pr.eligible[g];
+                    total += eo.value;
+                    if (fam->dist == DIST_T) grad[0] += eo.dv;
+                    const std::vector<double>& cj = ctl ? psc.cj : psn.cj;
+                    for (int j = 0; j < m; ++j) grad[off_a + j] += (kappa > 0.0 ? cj[j] : 0.0) - kappa * row[j];
+                }
+            });
+            if (done) continue;
+            for (int j = 0; j < m; ++j) row[j] = y[g * m + j];      // (untouched: the first sweep only reads)
+        }
         FN_DISPATCH_WIDTH(width,
             if (nf) eval_factors<C>(ec, gv, ((controls && controls[g]) ? zc : zn).data(), d.c, nf, pr.eligible[g], pr.cst[g], gscratch.data(), eo);
             else if (fam->kind == KIND_SCALE1) eval_scale1<C>(ec, gv, d.q.data(), d.c, pr.eligible[g], pr.cst[g], eo);
