@@ -193,6 +193,7 @@ struct fn_handle {
     DevBuf b_phist, b_bhwork;
     std::vector<long long> p_hist;
     double psum_expected = 0.0;
+    bool all_complete = false;         // no weights and every gene of the REML sum has all m samples: lean kernels
     // resident evaluation kernel (fn_resident_begin / _end): command block and state
     bool resident = false;
     int res_words = 0;
@@ -855,6 +856,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     h->psum_expected = 0.0;
     for (int pdf = 0; pdf <= m; ++pdf) h->psum_expected += (double)pdf * (double)h->p_hist[pdf];
     h->cst_sum = h->out_vals[PREP_CSTSUM];
+    h->all_complete = !h->has_aux && h->out_vals[PREP_PARTIAL] == 0.0;
     if (info) {
         const double cnt = h->out_vals[PREP_VARCNT];
         info->row_variance_mean = cnt > 0 ? h->out_vals[PREP_VARSUM] / cnt : NAN;
@@ -960,6 +962,9 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     if (ks && h->fam.kind == KIND_PATSEQ && h->fam.na == 1 && h->fam.nb == 1 && ks->eval[KIND_PATSEQ_SHARED] &&
         !getenv("FN_NO_PATSEQ_SHARED"))
         kernel = ks->eval[KIND_PATSEQ_SHARED];
+    // nothing missing, nothing weighted: the variants without the masked paths (fewer registers, two CTAs per SM)
+    if (ks && h->all_complete && !per_gene && h->fam.kind <= KIND_SCALE_PS && ks->eval_lean[h->fam.kind] && !getenv("FN_NO_LEAN"))
+        kernel = ks->eval_lean[h->fam.kind];
     if (!kernel) return fail(FN_ERR_UNSUPPORTED, "no kernel for this design width");
     rc = bound_grid(h, kernel, g);       // resident or not: all CTAs on the GPU at once
     if (rc) return rc;
@@ -1527,7 +1532,14 @@ static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* 
     h->test_out = d_out; h->test_p = d_p; h->test_q = nullptr; h->test_order = nullptr; h->test_kc = kc;
     const int tb = 128;
     if (h->n > 0) {
-        test_kernel<<<(unsigned)((h->n + tb - 1) / tb), tb, 0, h->stream>>>(tp);
+        const unsigned blocks = (unsigned)((h->n + tb - 1) / tb);
+        switch (kc) {
+            case 1: test_kernel<1><<<blocks, tb, 0, h->stream>>>(tp); break;
+            case 2: test_kernel<2><<<blocks, tb, 0, h->stream>>>(tp); break;
+            case 3: test_kernel<3><<<blocks, tb, 0, h->stream>>>(tp); break;
+            case 4: test_kernel<4><<<blocks, tb, 0, h->stream>>>(tp); break;
+            default: test_kernel<0><<<blocks, tb, 0, h->stream>>>(tp); break;
+        }
         ++h->launches;
     }
     CUDA_TRY(cudaGetLastError());

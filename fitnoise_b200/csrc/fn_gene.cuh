@@ -571,7 +571,11 @@ struct Scale1Mid {
 };
 
 // First half: everything that needs the gene's row (sums, solve, d2).  Cheap in the common case.
-template <int C>
+// LEAN: the caller guarantees that every eligible gene is complete and unweighted (the preparation
+// kernel counted none that is not), so the masked sweep is not even compiled into the kernel -- its
+// registers are what limits the streaming kernel to one CTA per SM at c >= 6.  A gene that turns out
+// incomplete all the same is reported as failed (state 2), never silently mis-evaluated.
+template <int C, bool LEAN = false>
 FN_HD void scale1_sweep(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
                         bool eligible, Scale1Mid& mid) {
     const bool has_aux = gv.aux != nullptr;
@@ -599,7 +603,9 @@ FN_HD void scale1_sweep(const EvalConst& ec, const GeneView& gv, const double* X
 #pragma unroll
         for (int i = 0; i < C; ++i) beta[i] = b[i];
     }
-    if (has_aux || warp_any(eligible && !complete)) {
+    if (LEAN) {
+        ok = complete;
+    } else if (has_aux || warp_any(eligible && !complete)) {
         Normal<C> nm;
         nm.init();
         // sigma2 = theta / w_prec at theta = 1: a sample counts when y is finite and its precision
@@ -884,8 +890,8 @@ FN_HD void ps_complete_finish(const EvalConst& ec, const PsDesign<C>& pd, GeneVi
         gv.y[j] = s;
     });
     kappa_out = 0.0;
+    d2 = lane_sum(d2, gv.lpg);          // every lane of the warp takes part (full-mask shuffles), whatever its gene does
     if (!mine) return;
-    d2 = lane_sum(d2, gv.lpg);
     eval_zero(out);
     out.used = 1;
     const int p = gv.m - c_real;
@@ -1294,6 +1300,66 @@ FN_HDN void test_gene(int c, int kc, const double* coef, const double* V, double
     }
     if (!ok) { pval = NAN; return; }
     pval = is_t ? f_sf(q / kc, (double)kc, df) : chi2_sf(q, (double)kc);
+}
+
+// The same for a compile-time number of contrasts KC (1..4): C'VC is accumulated straight from V, so
+// nothing is indexed at run time and everything stays in registers (test_gene keeps FN_MAXC^2 local
+// arrays: a 4 KB stack frame per thread for what is usually c = 2, kc = 1).
+template <int KC>
+FN_HD void test_gene_k(int c, const double* coef, const double* V, double df, int is_t,
+                       const double* contrasts, double* contrasted, double* ccov, double& pval) {
+    double mean[KC], s[KC * KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a) mean[a] = 0.0;
+#pragma unroll
+    for (int a = 0; a < KC * KC; ++a) s[a] = 0.0;
+    for (int i = 0; i < c; ++i) {
+        const double ci = coef[i];
+        double vc[KC];                       // row i of V C, summed in the order test_gene uses
+#pragma unroll
+        for (int b = 0; b < KC; ++b) vc[b] = 0.0;
+        for (int t = 0; t < c; ++t) {
+            const double v = V[i * c + t];
+#pragma unroll
+            for (int b = 0; b < KC; ++b) vc[b] += v * contrasts[t * KC + b];
+        }
+#pragma unroll
+        for (int a = 0; a < KC; ++a) {
+            const double cia = contrasts[i * KC + a];
+            mean[a] += cia * ci;
+#pragma unroll
+            for (int b = 0; b < KC; ++b) s[a * KC + b] += cia * vc[b];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < KC; ++a) contrasted[a] = mean[a];
+    if (ccov) {
+#pragma unroll
+        for (int a = 0; a < KC * KC; ++a) ccov[a] = s[a];
+    }
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < KC; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+            double acc = s[a * KC + b];
+#pragma unroll
+            for (int t = 0; t < b; ++t) acc -= s[a * KC + t] * s[b * KC + t];
+            if (b < a) s[a * KC + b] = acc / s[b * KC + b];
+            else { if (!(acc > 0.0)) { ok = false; acc = 1.0; } s[a * KC + a] = sqrt(acc); }
+        }
+    }
+    double q = 0.0, z[KC];
+#pragma unroll
+    for (int a = 0; a < KC; ++a) {
+        double acc = mean[a];
+#pragma unroll
+        for (int t = 0; t < a; ++t) acc -= s[a * KC + t] * z[t];
+        z[a] = acc / s[a * KC + a];
+        q += z[a] * z[a];
+    }
+    if (!ok) { pval = NAN; return; }
+    pval = is_t ? f_sf(q / KC, (double)KC, df) : chi2_sf(q, (double)KC);
 }
 
 }  // namespace fn

@@ -27,6 +27,7 @@ static __device__ unsigned long long g_trace[64];
 struct KernelSet {
     const void* prepare;          // prepare_kernel<C>
     const void* eval[4];          // eval_kernel<C, KIND_SCALE1 | KIND_SCALE_PS | KIND_PATSEQ | KIND_PATSEQ_SHARED (C <= 4, else null)>
+    const void* eval_lean[2];     // eval_kernel<C, KIND_SCALE1 | KIND_SCALE_PS, true>: all genes complete, no weights (C <= 8, else null)
     const void* eval_factors;     // eval_factors_kernel<C>
     const void* coef;             // coef_kernel<C>
 };
@@ -321,7 +322,8 @@ struct GeomParams {
 // ------------------------------------------------------------------------------------------
 // K1 prepare
 // ------------------------------------------------------------------------------------------
-enum { PREP_VARSUM = 0, PREP_VARCNT = 1, PREP_BAD = 2, PREP_CSTSUM = 3, PREP_ELIG = 4, PREP_NACC = 5 };
+enum { PREP_VARSUM = 0, PREP_VARCNT = 1, PREP_BAD = 2, PREP_CSTSUM = 3, PREP_ELIG = 4, PREP_PARTIAL = 5, PREP_NACC = 6 };
+// PREP_PARTIAL: eligible genes with fewer than m retained samples (0 => the lean evaluation kernels apply)
 
 struct PrepParams {
     GeomParams g;
@@ -381,6 +383,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepParams p) {
             acc[PREP_BAD] += po.bad_counts;
             if (po.eligible) {
                 acc[PREP_CSTSUM] += po.cst; acc[PREP_ELIG] += 1.0;
+                if (po.k < m) acc[PREP_PARTIAL] += 1.0;
                 atomicAdd(&hist[po.k - c_real], 1u);            // 0 < k - c <= m
             }
         }
@@ -584,8 +587,8 @@ struct EvalParams {
     ResidentCtl rc;
 };
 
-template <int C, int KIND>
-__global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalParams p) {
+template <int C, int KIND, bool LEAN = false>
+__global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) eval_kernel(const EvalParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[FN_MAX_STAGES];
     __shared__ double red_scratch[32 * ACC_FIXED];
@@ -747,7 +750,7 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
                 const uint8_t status = st[L.status_off + gl];
                 const bool control = (status & 2) != 0;
                 Scale1Mid mid;
-                scale1_sweep<C>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, (status & 1) != 0, mid);
+                scale1_sweep<C, LEAN>(ec, gv, control ? xc : xn, control ? p.c_ctrl : p.c_noise, (status & 1) != 0, mid);
                 if (lane == sel) {
                     pend = mid;
                     pend_cst = p.src.cst ? ((const double*)(st + L.cst_off))[gl] : 0.0;
@@ -794,19 +797,23 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 2 : 1)) eval_kernel(const EvalP
                     double beta[C];
                     const bool complete = ps_complete_beta<C>(pd, gv, eligible, beta);
                     eval_zero(eo);
-                    if (warp_any(eligible && !complete))
-                        eval_general<C, KIND>(ec, gv, X, c_real, eligible && !complete, cst, true, false, eo,
-                                              eligible && !complete);
+                    if constexpr (!LEAN) {
+                        if (warp_any(eligible && !complete))
+                            eval_general<C, KIND>(ec, gv, X, c_real, eligible && !complete, cst, true, false, eo,
+                                                  eligible && !complete);
+                    } else if (eligible && !complete) {
+                        eo.value = NAN; eo.used = 1;             // cannot happen (PREP_PARTIAL == 0): reported as bad
+                    }
                     EvalOut ef;
                     double kappa;
-                    ps_complete_finish<C>(ec, pd, gv, X, c_real, complete, !eligible, beta, cst, ef, kappa);
+                    ps_complete_finish<C>(ec, pd, gv, X, c_real, complete, LEAN ? !complete : !eligible, beta, cst, ef, kappa);
                     if (complete) eo = ef;
                     if (lane == 0) {
                         // the column sum multiplies the gene's slots by this: -kappa for s_j = (w_j r_j)^2
                         kap[gl] = complete ? -kappa : 1.0;
                         if (complete && kappa > 0.0 && gene < p.g.n) atomicAdd(&ps_count[control ? 1 : 0], 1);
                     }
-                } else {
+                } else if constexpr (!LEAN) {
                     eval_general<C, KIND>(ec, gv, X, c_real, eligible, cst, p.inplace_a != 0, p.inplace_b != 0, eo);
                 }
                 if (lane == 0) account(eo, gene);
@@ -1061,6 +1068,8 @@ struct TestParams {
 };
 
 #ifndef FN_WIDTH_ONLY
+// KC = compile-time number of contrasts (1..4: everything in registers), 0 = any (local arrays)
+template <int KC>
 __global__ void test_kernel(const TestParams p) {
     __shared__ double cm[FN_MAXC * FN_MAXC];
     for (int i = threadIdx.x; i < p.c * p.kc; i += blockDim.x) cm[i] = p.contrasts[i];
@@ -1076,8 +1085,10 @@ __global__ void test_kernel(const TestParams p) {
         return;
     }
     double pv;
-    test_gene(p.c, p.kc, p.coef + g * p.c, V, p.dfpost[g], p.is_t, cm, out,
-              p.ccov ? p.ccov + g * p.kc * p.kc : nullptr, pv);
+    const double* cf = p.coef + g * p.c;
+    double* cc = p.ccov ? p.ccov + g * p.kc * p.kc : nullptr;
+    if constexpr (KC > 0) test_gene_k<KC>(p.c, cf, V, p.dfpost[g], p.is_t, cm, out, cc, pv);
+    else test_gene(p.c, p.kc, cf, V, p.dfpost[g], p.is_t, cm, out, cc, pv);
     p.pval[g] = pv;
 }
 #endif

@@ -19,6 +19,11 @@ const KernelSet* FN_WCAT(kernel_set_w, FN_W)() {
          nullptr
 #endif
         },
+#if FN_W <= 8
+        {(const void*)eval_kernel<FN_W, KIND_SCALE1, true>, (const void*)eval_kernel<FN_W, KIND_SCALE_PS, true>},
+#else
+        {nullptr, nullptr},
+#endif
         (const void*)eval_factors_kernel<FN_W>,
         (const void*)coef_kernel<FN_W>,
     };

@@ -259,8 +259,16 @@ void hc_test(long n, int c, int kc, const double* coef, const double* covar, con
             p[g] = NAN;
             continue;
         }
-        test_gene(c, kc, coef + g * c, covar + g * c * c, df[g], is_t, contrasts,
-                  contrasted + g * kc, ccov + g * kc * kc, p[g]);
+        // the same dispatch as the CUDA test_kernel: compile-time kc up to 4
+        const double* cf = coef + g * c; const double* V = covar + g * c * c;
+        double* out = contrasted + g * kc; double* cc = ccov + g * kc * kc;
+        switch (kc) {
+            case 1: test_gene_k<1>(c, cf, V, df[g], is_t, contrasts, out, cc, p[g]); break;
+            case 2: test_gene_k<2>(c, cf, V, df[g], is_t, contrasts, out, cc, p[g]); break;
+            case 3: test_gene_k<3>(c, cf, V, df[g], is_t, contrasts, out, cc, p[g]); break;
+            case 4: test_gene_k<4>(c, cf, V, df[g], is_t, contrasts, out, cc, p[g]); break;
+            default: test_gene(c, kc, cf, V, df[g], is_t, contrasts, out, cc, p[g]); break;
+        }
     }
 }
 
