@@ -190,6 +190,53 @@ struct GeneView {
             for (int t = 0; t < NB; ++t) f(jr + 16 * t);
         }
     }
+    // The same visit with a hook after every rotation step, i.e. after at most 8 samples: the caller
+    // can keep a running PRODUCT of per-sample values and renormalise it there instead of testing a
+    // counter per sample.  The block loop is unrolled for the common block counts.
+    template <int BS, int NB, class F, class G>
+    FN_HD void steps_unrolled(F f, G step_end) const {
+        for (int r = 0; r < steps; ++r) {
+            const int jr = (lane + lpg * (skew + r)) & (BS - 1);
+#pragma unroll
+            for (int t = 0; t < NB; ++t) f(jr + BS * t);
+            step_end();
+        }
+    }
+    template <class F, class G>
+    FN_HD void for_each_steps(bool on, F f, G step_end) const {
+        if (!on) return;
+        if (blocked) {
+            if (bsize == 16) {
+                switch (nblk) {
+                    case 1: steps_unrolled<16, 1>(f, step_end); return;
+                    case 2: steps_unrolled<16, 2>(f, step_end); return;
+                    case 3: steps_unrolled<16, 3>(f, step_end); return;
+                    case 4: steps_unrolled<16, 4>(f, step_end); return;
+                    case 6: steps_unrolled<16, 6>(f, step_end); return;
+                    default: break;
+                }
+            } else if (bsize == 8) {
+                switch (nblk) {
+                    case 1: steps_unrolled<8, 1>(f, step_end); return;
+                    case 3: steps_unrolled<8, 3>(f, step_end); return;
+                    case 5: steps_unrolled<8, 5>(f, step_end); return;
+                    default: break;
+                }
+            }
+            const int mask = bsize - 1;
+            for (int r = 0; r < steps; ++r) {
+                const int jr = (lane + lpg * (skew + r)) & mask;
+                for (int t = 0; t < nblk; ++t) {
+                    f(jr + bsize * t);
+                    if ((t & 7) == 7) step_end();
+                }
+                step_end();
+            }
+            return;
+        }
+        int j = lane;
+        for (int i = 0; i < cnt; ++i, j += lpg) { f(j); step_end(); }
+    }
     template <class F>
     FN_HD void for_each_hot(bool on, F f) const {
         if (!on) return;
@@ -456,42 +503,59 @@ struct PrepOut {
 // `counts_raw`: for PATSEQ the aux row still holds RAW counts at prepare time.
 template <int C>
 FN_HD void prepare_gene(const Family& fam, const GeneView& gv, const double* X, int c_real, PrepOut& out) {
-    Normal<C> g;
-    g.init();
     LogProd lw; lw.init();
     double ysum = 0.0, csum = 0.0, ycsum = 0.0, ysel = 0.0;
-    int nfin = 0, bad = 0;
+    int nfin = 0, bad = 0, k = 0;
     const bool patseq = fam.kind == KIND_PATSEQ;
+    // whether sample j is retained (theta-independent part of Mv*.good)
+    auto retained = [&](double y, double aux) -> bool {
+        if (patseq) return finite_d(y) && finite_d(aux);
+        return finite_d(y) && aux != 0.0 && aux == aux;
+    };
     gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
         const bool yok = finite_d(y);
-        double aux = gv.aux ? gv.aux[j] : 1.0;
-        bool valid;
+        const double aux = gv.aux ? gv.aux[j] : 1.0;
+        const bool valid = retained(y, aux);
         if (patseq) {
             if (aux == 0.0 && yok) ++bad;
             csum += aux;
             ycsum += (yok ? y : 0.0) * aux;
-            valid = yok && finite_d(aux);
-        } else {
-            valid = yok && aux != 0.0 && aux == aux;
-            if (valid && gv.aux) lw.mul(fabs(aux));
+        } else if (valid && gv.aux) {
+            lw.mul(fabs(aux));
         }
         if (yok) { ysum += y; ++nfin; }
-        if (valid) {
-            double x[C];
-            load_x<C>(X, j, x);
-            g.add(1.0, 0.0, x);
-            ysel += y;
-            ++g.k;
-        }
+        if (valid) { ysel += y; ++k; }
     });
-    g.reduce(gv.lpg);
     lw.lane_reduce(gv.lpg);
     ysum = lane_sum(ysum, gv.lpg);
     ysel = lane_sum(ysel, gv.lpg);
     nfin = lane_sum_i(nfin, gv.lpg);
     bad = lane_sum_i(bad, gv.lpg);
+    k = lane_sum_i(k, gv.lpg);
     if (patseq) { csum = lane_sum(csum, gv.lpg); ycsum = lane_sum(ycsum, gv.lpg); }
+    // The design columns are orthonormal over all m samples (Design::build), so a gene that keeps every
+    // sample has X_ret'X_ret = I: determinant 1, full rank.  Only genes that lost a sample need the masked
+    // Gram matrix and its factorisation (none at all in a data set without missing values).
+    double det = 1.0;
+    bool full_rank = true;
+    const bool partial = k < gv.m;
+    if (warp_any(partial)) {
+        Normal<C> g;
+        g.init();
+        gv.for_each(partial, [&](int j) {
+            if (retained(gv.y[j], gv.aux ? gv.aux[j] : 1.0)) {
+                double x[C];
+                load_x<C>(X, j, x);
+                g.add(1.0, 0.0, x);
+            }
+        });
+        g.reduce(gv.lpg);
+        g.pad(c_real);
+        double det2;
+        const bool rank2 = chol<C>(g.a, det2, FN_RANK_TOL);
+        if (partial) { det = det2; full_rank = rank2; }
+    }
     // second sweep: squared deviations of the finite y about their mean (numpy.var, fitnoise.py:546)
     const double mean = nfin > 0 ? ysum / nfin : 0.0;
     double ss = 0.0;
@@ -501,14 +565,11 @@ FN_HD void prepare_gene(const Family& fam, const GeneView& gv, const double* X, 
     });
     ss = lane_sum(ss, gv.lpg);
 
-    g.pad(c_real);
-    double det;
-    const bool full_rank = chol<C>(g.a, det, FN_RANK_TOL);
-    out.k = g.k;
-    out.eligible = (g.k > c_real) && full_rank;
-    out.cst = -log(det);
+    out.k = k;
+    out.eligible = (k > c_real) && full_rank;
+    out.cst = (det == 1.0) ? 0.0 : -log(det);
     if (!patseq && gv.aux) out.cst -= lw.log_value();
-    out.average = (g.k > c_real) ? ysel / g.k : NAN;
+    out.average = (k > c_real) ? ysel / k : NAN;
     out.ysum = ysum; out.yss = ss; out.nfinite = nfin;
     out.bad_counts = bad;
     out.avg_tail = 0.0;
@@ -933,6 +994,56 @@ FN_HD double rcp_pos(double x) {
 // tile is never written.  The quadratic form cancels like d2 = y'Wy - b'beta does; when that loses more
 // than four digits both are recomputed from residuals (a second sweep for those genes only).
 // Returns out.ga multiplied by theta_a, as eval_general does for this kind.
+// The sweep: normal equations in nm, the T-weighted moments in mt / bt / sums, prod sigma2 in lp.
+// TAIL_OWN (v1): T_j = y_j^2.  Otherwise T = gs for every sample of the gene, so it is factored out of
+// the moments (they are accumulated with w_j^2 and multiplied by T once per gene) and
+// sigma2_j = ua rc_j + tb0 with two per-gene scalars (v3 folds its avgtail^2 into ua).
+// Written without a branch per sample: a dropped sample gets w = 0, y = 0, sigma2 = 1.
+template <int C, bool TAIL_OWN>
+FN_HD void patseq_shared_sweep(const EvalConst& ec, const GeneView& gv, const double* X, bool eligible,
+                               double tha, double thb, Normal<C>& nm, double* mt, double* bt, double* sums, LogProd& lp) {
+    const double ua = ec.v3 ? tha * gv.gs : tha;           // sigma2 = ua rc + thb T
+    const double tb0 = TAIL_OWN ? 0.0 : thb * gv.gs;
+    double pend = 1.0, sw = 0.0;
+    gv.for_each_steps(eligible, [&](int j) {
+        const double y = gv.y[j];
+        const double rc = gv.aux[j];
+        // rc is in (0, 1] or NaN and theta is finite: sigma2 is finite exactly when rc is, unless y^2 overflows
+        const double T = TAIL_OWN ? y * y : 0.0;
+        const double s2 = TAIL_OWN ? fma(ua, rc, thb * T) : fma(ua, rc, tb0);
+        const bool valid = finite_d(TAIL_OWN ? s2 : y * rc);       // Mv*.good: distributions.py:31-36
+        const double s2v = valid ? s2 : 1.0;
+        const double w = valid ? rcp_pos(s2v) : 0.0;
+        const double yv = valid ? y : 0.0;
+        pend *= s2v;
+        nm.k += valid ? 1 : 0;
+        double x[C];
+        load_x<C>(X, j, x);
+        nm.add(w, yv, x);
+        const double t2 = TAIL_OWN ? (valid ? T : 0.0) * (w * w) : w * w;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const double tx = t2 * x[i];
+#pragma unroll
+            for (int q = 0; q <= i; ++q) mt[FN_TRI(i, q)] += tx * x[q];
+            bt[i] += tx * yv;
+        }
+        sums[0] += (t2 * yv) * yv;
+        sw += TAIL_OWN ? t2 * s2v : w;                    // T_j w_j (T factored out below)
+    }, [&]() { lp.mul(pend); pend = 1.0; });
+    if (TAIL_OWN) {
+        sums[1] = sw;
+    } else {                                               // T = gs: put it back
+        const double T = gv.gs;
+#pragma unroll
+        for (int i = 0; i < Tri<C>::N; ++i) mt[i] *= T;
+#pragma unroll
+        for (int i = 0; i < C; ++i) bt[i] *= T;
+        sums[0] *= T;
+        sums[1] = T * sw;
+    }
+}
+
 template <int C>
 FN_HD void eval_patseq_shared(const EvalConst& ec, const GeneView& gv, const double* X, int c_real,
                               bool eligible, double cst, EvalOut& out) {
@@ -946,45 +1057,18 @@ FN_HD void eval_patseq_shared(const EvalConst& ec, const GeneView& gv, const dou
     for (int i = 0; i < C; ++i) bt[i] = 0.0;
     double sums[2] = {0.0, 0.0};       // S_Tyy, sum_j T_j w_j
     LogProd lp; lp.init();
-    double pend = 1.0;
-    int npend = 0;
-    // sigma2, validity and the weight of sample j
+    if (ec.tail_own) patseq_shared_sweep<C, true>(ec, gv, X, eligible, tha, thb, nm, mt, bt, sums, lp);
+    else patseq_shared_sweep<C, false>(ec, gv, X, eligible, tha, thb, nm, mt, bt, sums, lp);
+    // sigma2, validity and the weight of sample j (the cancellation fallback below)
     auto variance = [&](int j, double y, double& T, bool& valid) -> double {
         const double rc = gv.aux[j];
         const bool yok = finite_d(y);
         const double U = ec.v3 ? rc * gv.gs : rc;
         T = ec.tail_own ? (yok ? y * y : 0.0) : gv.gs;
         const double s2 = tha * U + thb * T;
-        valid = yok && finite_d(s2);                      // Mv*.good: distributions.py:31-36
+        valid = yok && finite_d(s2);
         return s2;
     };
-    gv.for_each(eligible, [&](int j) {
-        const double y = gv.y[j];
-        double T;
-        bool valid;
-        const double s2 = variance(j, y, T, valid);
-        const double w = valid ? rcp_pos(s2) : 0.0;
-        const double yv = valid ? y : 0.0;
-        const double t2 = valid ? T * w * w : 0.0;
-        double x[C];
-        load_x<C>(X, j, x);
-        nm.add(w, yv, x);
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            const double tx = t2 * x[i];
-#pragma unroll
-            for (int q = 0; q <= i; ++q) mt[FN_TRI(i, q)] += tx * x[q];
-            bt[i] += tx * yv;
-        }
-        sums[0] += (t2 * yv) * yv;
-        if (valid) {
-            sums[1] += T * w;
-            ++nm.k;
-            pend *= s2;
-            if (++npend == 4) { lp.mul(pend); pend = 1.0; npend = 0; }
-        }
-    });
-    lp.mul(pend);
     if (gv.lpg > 1) {
         lp.lane_reduce(gv.lpg);
         nm.reduce(gv.lpg);
@@ -1202,32 +1286,86 @@ struct CoefOut {
 template <int C>
 FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, int c_real, int nf,
                      double* beta, double* ainv, CoefOut& out) {
-    Normal<C> nm, gm;
-    nm.init(); gm.init();
     const double wscale = nf > 0 ? ec.itheta0 : 1.0;       // the ridge does not scale with theta
-    gv.for_each(true, [&](int j) {
-        const double y = gv.y[j];
-        const SampleVar sv = sample_var(ec, gv, j, y);
-        double x[C];
-        load_x<C>(X, j, x);
-        nm.add(sv.w * wscale, sv.valid ? y : 0.0, x);
-        if (sv.valid) {
+    // SCALE1 without weights and factors works at theta = 1 with w_j = 1: for a gene that keeps every
+    // sample the normal matrix is X'X = I (orthonormal columns), so beta = X'y and A^-1 = I -- no
+    // accumulation of A, no factorisation, no inverse.  A missing value makes y'y non-finite, which is
+    // how the other genes are found (as in scale1_sweep); they take the general route below.
+    const bool unit = ec.kind == KIND_SCALE1 && gv.aux == nullptr && nf == 0;
+    bool done = false;
+    int k = 0;
+    if (unit) {
+        double b[C], yy = 0.0;
 #pragma unroll
-            for (int i = 0; i < C; ++i) if (i >= c_real) x[i] = 0.0;     // rank of the design only
-            gm.add(1.0, 0.0, x);
-            ++nm.k;
+        for (int i = 0; i < C; ++i) b[i] = 0.0;
+        gv.for_each_hot(true, [&](int j) {
+            const double y = gv.y[j];
+            double x[C];
+            load_x<C>(X, j, x);
+#pragma unroll
+            for (int i = 0; i < C; ++i) b[i] += x[i] * y;
+            yy += y * y;
+        });
+        lane_sum_n<C>(b, gv.lpg);
+        yy = lane_sum(yy, gv.lpg);
+        done = finite_d(yy);
+        if (done) {
+            k = gv.m;
+#pragma unroll
+            for (int i = 0; i < C; ++i) beta[i] = (i < c_real) ? b[i] : 0.0;
+#pragma unroll
+            for (int i = 0; i < C; ++i)
+#pragma unroll
+                for (int q = 0; q <= i; ++q) ainv[FN_TRI(i, q)] = (i == q) ? 1.0 : 0.0;
         }
-    });
-    nm.reduce(gv.lpg);
-    gm.reduce(gv.lpg);
-    ridge_and_pad<C>(nm.a, c_real, nf); gm.pad(c_real);
-    double det;
-    const bool full_rank = chol<C>(gm.a, det, FN_RANK_TOL);
-    const bool okA = chol<C>(nm.a, det, 0.0);
+    }
+    bool full_rank = true, okA = true;
+    if (!unit || warp_any(!done)) {
+        Normal<C> nm;
+        nm.init();
+        gv.for_each(!done, [&](int j) {
+            const double y = gv.y[j];
+            const SampleVar sv = sample_var(ec, gv, j, y);
+            double x[C];
+            load_x<C>(X, j, x);
+            nm.add(sv.w * wscale, sv.valid ? y : 0.0, x);
+            nm.k += sv.valid ? 1 : 0;
+        });
+        nm.reduce(gv.lpg);
+        // rank of the retained sub-design: the unweighted masked Gram matrix -- the identity when nothing is
+        // dropped, so only genes that lost a sample factorise it
+        const bool partial = !done && nm.k < gv.m;
+        if (warp_any(partial)) {
+            Normal<C> gm;
+            gm.init();
+            gv.for_each(partial, [&](int j) {
+                const SampleVar sv = sample_var(ec, gv, j, gv.y[j]);
+                if (sv.valid) {
+                    double x[C];
+                    load_x<C>(X, j, x);
 #pragma unroll
-    for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
-    chol_solve<C>(nm.a, beta);
-    chol_inverse<C>(nm.a, ainv);
+                    for (int i = 0; i < C; ++i) if (i >= c_real) x[i] = 0.0;     // rank of the design only
+                    gm.add(1.0, 0.0, x);
+                }
+            });
+            gm.reduce(gv.lpg);
+            gm.pad(c_real);
+            double detg;
+            const bool rank2 = chol<C>(gm.a, detg, FN_RANK_TOL);
+            if (partial) full_rank = rank2;
+        }
+        ridge_and_pad<C>(nm.a, c_real, nf);
+        double det;
+        const bool ok2 = chol<C>(nm.a, det, 0.0);
+        if (!done) {
+            okA = ok2;
+            k = nm.k;
+#pragma unroll
+            for (int i = 0; i < C; ++i) beta[i] = nm.b[i];
+            chol_solve<C>(nm.a, beta);
+            chol_inverse<C>(nm.a, ainv);
+        }
+    }
     double d2 = 0.0;
     gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
@@ -1247,8 +1385,8 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
 #pragma unroll
         for (int i = 0; i < Tri<C>::N; ++i) ainv[i] *= ec.theta0;
     }
-    out.p2 = nm.k - c_real;
-    out.ok = (nm.k >= c_real) && full_rank && okA;
+    out.p2 = k - c_real;
+    out.ok = (k >= c_real) && full_rank && okA;
     out.d2 = (out.p2 > 0) ? d2 : 0.0;        // k == c: the fit is exact (conditional on nothing)
 }
 

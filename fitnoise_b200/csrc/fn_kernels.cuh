@@ -600,12 +600,16 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
     const TileLayout L = tile_layout(p.src);
     TileRing ring;
     ring_setup(ring, bars, p.g.stages, p.g.n_tiles, resident);
-    // tables behind the stage area: xn, xc (m*C each), ta, tb (m each), t0, t1 (m+1 each),
-    // vals (ACC_FIXED + 2m), colscr (2*blockDim when a theta block is per-sample)
+    // tables behind the stage area: xn, xc (m*C each), [hxn, hxc (m*C each): KIND_SCALE_PS], ta, tb (m each),
+    // t0, t1 (m+1 each), vals (ACC_FIXED + 2m), colscr (2*blockDim when a theta block is per-sample).
+    // The design-shaped tables come first: their rows must stay 16-byte aligned for LDS.128 (the stage
+    // area is a multiple of 128 bytes, rows of an even width are multiples of 16).
     double* xn = (double*)(smem_raw + (size_t)p.g.stages * L.stage_bytes);
     constexpr int XS = XStride<C>::V;
     double* xc = xn + m * XS;
-    double* ta = xc + m * XS;
+    double* hxn = xc + m * XS;
+    double* hxc = hxn + (KIND == KIND_SCALE_PS ? m * XS : 0);
+    double* ta = hxc + (KIND == KIND_SCALE_PS ? m * XS : 0);
     double* tb = ta + m;
     double* t0 = tb + m;
     double* t1 = t0 + (m + 1);
@@ -614,9 +618,7 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
     const bool inplace = p.inplace_a || p.inplace_b;
     // KIND_SCALE_PS without weights: tables of the complete-row fast path (two designs), kappa per gene
     const bool fastps = KIND == KIND_SCALE_PS && p.src.aux == nullptr;
-    double* hxn = colscr + (inplace ? 2 * blockDim.x : 0);
-    double* hxc = hxn + m * C;
-    double* cjn = hxc + m * C;
+    double* cjn = colscr + (inplace ? 2 * blockDim.x : 0);
     double* cjc = cjn + m;
     double* pstri = cjc + m;
     double* pssc = pstri + Tri<C>::N;          // 2 x 3
