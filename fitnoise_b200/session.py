@@ -10,10 +10,20 @@ from . import _native, parallel
 
 
 def _give_back(engine, pooled):
-    if pooled:
+    if pooled == "rank":
+        _RANK_STATE["busy"] = False           # the rank's engine stays alive, connected, with its buffers
+    elif pooled:
         _native.release_engine(engine)
     elif hasattr(engine, "close"):
         engine.close()
+
+
+# Multi-GPU: what a rank sets up ONCE per process and every later fit reuses -- its engine (device
+# buffers, pinned result pool), the torch stream that carries kernels and collectives, and the fused
+# exchange (mailboxes mapped into every rank with CUDA IPC: milliseconds of handle exchange and
+# cudaIpcOpenMemHandle that a 20,000-gene fit cannot afford to repeat).
+_RANK_STATE = {}
+_MAILBOX_VALUES = 8 + 2 * 256      # room for every model the kernels accept (per-sample blocks: m <= 256)
 
 
 class _Resident(object):
@@ -75,7 +85,13 @@ class Session(object):
         self.coef_token = None
         self._fused = False
         if self._cuda_reduce is not None and os.environ.get("FN_REDUCE", "fused") == "fused":
-            self._connect_fused()
+            state = _RANK_STATE
+            if state.get("engine") is self.local and "fused" in state:
+                self._fused = state["fused"]              # connected by an earlier fit of this process
+            else:
+                self._connect_fused()
+                if state.get("engine") is self.local:
+                    state["fused"] = self._fused
 
     def _connect_fused(self):
         """Exchange the ranks' mailbox handles (CUDA IPC) so that the nll+grad kernel itself adds the
@@ -84,7 +100,7 @@ class Session(object):
         import torch.distributed as dist
         ok, handle = 1, None
         try:
-            handle = self.local.comm_mailbox(self.world, 8 + max(2, self.family.nf) * self.m)
+            handle = self.local.comm_mailbox(self.world, max(_MAILBOX_VALUES, 8 + max(2, self.family.nf) * self.m))
         except _native.NativeError:               # CUDA IPC not available on this box
             ok = 0
         handles = [None] * self.world
@@ -118,13 +134,25 @@ class Session(object):
             # ordered after the kernel that produced its input (the handle would otherwise launch on
             # a private non-blocking stream that the NCCL stream knows nothing about).
             import torch
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank)))
             self._torch = torch
-            self._stream = torch.cuda.Stream()
+            state = _RANK_STATE
+            if state.get("engine") is not None and not state.get("busy") and state.get("world") == self.world:
+                self._stream = state["stream"]
+                engine = state["engine"]
+            else:
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank)))
+                self._stream = torch.cuda.Stream()
+                engine = _native.Engine(torch.cuda.current_device(), self._stream.cuda_stream)
+                if state.get("engine") is None or state.get("world") != self.world:
+                    state.clear()
+                    state.update(engine=engine, stream=self._stream, world=self.world)
+            if state.get("engine") is engine:
+                state["busy"] = True
+                self._pooled = "rank"
             with torch.cuda.stream(self._stream):
                 self._cuda_reduce = torch.zeros(self.P + 3, dtype=torch.float64, device="cuda")
             self._stream.synchronize()
-            return _native.Engine(torch.cuda.current_device(), self._stream.cuda_stream)
+            return engine
         self._pooled = True
         return _native.acquire_engine(int(os.environ.get("LOCAL_RANK", "0")))
 
