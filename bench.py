@@ -250,7 +250,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "gene-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -558,7 +558,7 @@ def run_gpu(args):
             "cpu_baseline": cpu_baseline,
             "fit_test": fit_test,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -566,7 +566,8 @@ def run_gpu(args):
 def run_fit_test(fitnoise, torch, dist, world, rank, dev):
     """Model.fit(...) + .test(...) wall time through the public API, inputs in pinned host memory,
     max over ranks.  cfg5 shape (1M x 96: Model_independent as BASELINE names it, and Model_t whose
-    fit runs the optimiser) and cfg1 shape (20k x 6, Model_t)."""
+    fit runs the optimiser) and cfg1 shape (20k x 6, Model_t).  "Warm" = device buffers and pinned
+    result blocks of an earlier fit are reused (the first call of a process is reported beside it)."""
     def wall(fn):
         if world > 1:
             dist.barrier()
@@ -579,6 +580,16 @@ def run_fit_test(fitnoise, torch, dist, world, rank, dev):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         return dt, res
+
+    def summary(res):
+        """Small numbers only: the result arrays are released before the next call (their pinned blocks go
+        back to the pool, which is what a warm call reuses)."""
+        f, t = res
+        info = {"q_lt_0.01": int((t.q_values < 0.01).sum()), "evaluations": int(f._evaluations)}
+        if hasattr(f.param, "df"):
+            info.update(df=float(f.param.df), sd=float(np.sqrt(f.param.variance)))
+        f._session.close()
+        return info
 
     out = {"includes": "H2D of this rank's genes from pinned host memory, preparation, optimiser, noise p-values, "
                        "coefficients, test, BH over all genes, per-gene results back on the host of every rank",
@@ -599,24 +610,27 @@ def run_fit_test(fitnoise, torch, dist, world, rank, dev):
 
     def fit_ind():
         fitted = fitnoise.Model_independent().fit(y, design)
-        tested = fitted.test(coef=[1])
-        return fitted, tested
+        return fitted, fitted.test(coef=[1])
 
     def fit_t():
         fitted = fitnoise.Model_t().fit(y, design)
-        tested = fitted.test(coef=[1])
-        return fitted, tested
+        return fitted, fitted.test(coef=[1])
 
-    t_first, (f, t) = wall(fit_ind)                    # first call allocates the engine's buffers
-    f._session.close()
-    t_ind, (f, t) = wall(fit_ind)
-    n_sig = int((t.q_values < 0.01).sum())
-    f._session.close()
-    t_t, (f, t) = wall(fit_t)
+    t_first, res = wall(fit_ind)                       # first call: device buffers allocated, result memory pinned
+    summary(res)
+    del res
+    t_ind, res = wall(fit_ind)
+    ind = summary(res)
+    del res
+    _, res = wall(fit_t)
+    summary(res)
+    del res
+    t_t, res = wall(fit_t)
+    tt = summary(res)
+    del res
     out["1Mx96"] = {"Model_independent_fit_test_wall_s": t_ind, "Model_independent_first_call_wall_s": t_first,
-                    "q_lt_0.01": n_sig, "Model_t_fit_test_wall_s": t_t, "Model_t_evaluations": int(f._evaluations),
-                    "Model_t_df": float(f.param.df), "Model_t_sd": float(np.sqrt(f.param.variance))}
-    f._session.close()
+                    "q_lt_0.01": ind["q_lt_0.01"], "Model_t_fit_test_wall_s": t_t, "Model_t_evaluations": tt["evaluations"],
+                    "Model_t_df": tt["df"], "Model_t_sd": tt["sd"]}
     del y, y_host
     # ---- cfg1: 20k x 6 -------------------------------------------------------------------
     n, m = 20000, 6
@@ -627,24 +641,38 @@ def run_fit_test(fitnoise, torch, dist, world, rank, dev):
 
     def fit_small():
         fitted = fitnoise.Model_t().fit(y, design)
-        tested = fitted.test(coef=[1])
-        return fitted, tested
+        return fitted, fitted.test(coef=[1])
 
-    _, (f, t) = wall(fit_small)
-    f._session.close()
+    _, res = wall(fit_small)
+    summary(res)
+    del res
     times = []
     for _ in range(5):
-        dt, (f, t) = wall(fit_small)
+        dt, res = wall(fit_small)
+        small = summary(res)
+        del res
         times.append(dt)
-        evals = int(f._evaluations)
-        df, sd = float(f.param.df), float(np.sqrt(f.param.variance))
-        f._session.close()
-    out["20kx6"] = {"Model_t_fit_test_wall_s": float(np.median(times)), "Model_t_evaluations": evals,
-                    "Model_t_df": df, "Model_t_sd": sd, "q_lt_0.01": int((t.q_values < 0.01).sum())}
+    out["20kx6"] = {"Model_t_fit_test_wall_s": float(np.median(times)), "Model_t_evaluations": small["evaluations"],
+                    "Model_t_df": small["df"], "Model_t_sd": small["sd"], "q_lt_0.01": small["q_lt_0.01"]}
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else that writes to fd 1
+    (NCCL's version banner, library chatter) has been redirected to stderr by main()."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                          # fd 1 -> stderr for NCCL / CUDA libraries and stray prints
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
