@@ -619,6 +619,16 @@ def run_fit_test(fitnoise, torch, dist, world, rank, dev):
     t_first, res = wall(fit_ind)                       # first call: device buffers allocated, result memory pinned
     summary(res)
     del res
+    if os.environ.get("FN_BENCH_PROFILE") and rank == 0:      # where does a warm call spend its time? (stderr)
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        res = fit_ind()
+        pr.disable()
+        summary(res)
+        del res
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(12)
     t_ind, res = wall(fit_ind)
     ind = summary(res)
     del res

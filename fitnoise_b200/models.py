@@ -351,23 +351,34 @@ class Model(Withable):
     # ---- top table (legacy R test.fit, backyard/old_fitnoise.R:783-826) ---------------------
     def top_table(self, sort=True, genes=None):
         """Table of the tested contrasts in the layout of the legacy R ``test.fit`` (intended there
-        to match limma's topTableF): one column per contrast, ``AveExpr``, ``P.Value``,
+        to match limma's topTableF; on a fit that has not been tested it is the table of the NOISE
+        fit, ``P.Value`` = ``noise.P.Value``, as ``test.fit(fit)`` without coefs or contrasts):
+        one column per contrast, ``AveExpr``, ``P.Value``,
         ``adj.P.Val``, ``noise.P.Value`` and, when control genes were given, ``control``; rows
         ordered by p (ascending, ties in input order, missing p last -- R's ``order()``).  The order
         comes from the device radix sort that also produced the q-values.
 
         Returns a pandas DataFrame when pandas is importable, else a dict of columns plus "row".
         ``genes``: optional dict of per-gene annotation columns appended to the table."""
-        assert hasattr(self, "p_values"), "top_table() needs a tested fit: call .test(...) first"
-        n = len(self.p_values)
-        rows = self._order if sort else np.arange(n)
+        if hasattr(self, "p_values"):
+            p_values, q_values, order = self.p_values, self.q_values, self._order
+            names, contrasts = self._contrast_names, self.contrasts
+        else:
+            # neither coefficients nor contrasts were tested: "this tests the fit of the noise"
+            # (old_fitnoise.R:776-795): the table of the noise p-values, adjusted and ordered on the GPU
+            assert hasattr(self, "noise_p_values"), "top_table() needs a fitted model"
+            p_values = self.noise_p_values
+            q_values, order = self._session.bh_ranked(p_values)
+            names, contrasts = [], None
+        n = len(p_values)
+        rows = np.asarray(order, dtype=np.int64) if sort else np.arange(n)
         columns = {}
-        for i, name in enumerate(self._contrast_names):
-            columns[name] = self.contrasts[rows, i]
+        for i, name in enumerate(names):
+            columns[name] = contrasts[rows, i]
         with np.errstate(invalid="ignore"):
             columns["AveExpr"] = _row_means(self.data.y)[rows]          # rowMeans(fit$data, na.rm=TRUE)
-        columns["P.Value"] = self.p_values[rows]
-        columns["adj.P.Val"] = self.q_values[rows]
+        columns["P.Value"] = p_values[rows]
+        columns["adj.P.Val"] = q_values[rows]
         columns["noise.P.Value"] = self.noise_p_values[rows]
         if np.any(self.controls):
             columns["control"] = np.asarray(self.controls)[rows]

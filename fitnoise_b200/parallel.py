@@ -12,12 +12,19 @@ the world_size-2 CPU tests with a stand-in local evaluator).
 import numpy as np
 
 
+# Imported HERE, at module import, and not lazily inside a fit: something in torch's import keeps a
+# reference to the importing frame, and with it the whole chain of calling frames -- a first fit that
+# triggered the import from Session.__init__ had all its result arrays (and their pinned host blocks)
+# kept alive by that chain until the cycle collector ran.
+try:
+    import torch.distributed as _torch_dist
+except Exception:  # torch not importable: single process
+    _torch_dist = None
+
+
 def _dist():
-    try:
-        import torch.distributed as dist
-    except Exception:  # torch not importable: single process
-        return None
-    if dist.is_available() and dist.is_initialized():
+    dist = _torch_dist
+    if dist is not None and dist.is_available() and dist.is_initialized():
         return dist
     return None
 

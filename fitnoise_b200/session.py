@@ -325,6 +325,10 @@ class Session(object):
         self.local.fetch(order, order_ptr)
         return contrasted, p, q, order
 
+    def bh_ranked(self, p):
+        """(q, order) of a full-length p vector every rank holds."""
+        return self.local.bh_ranked(p)
+
     def bh(self, p):
         # every rank holds the full p vector after the gather and adjusts it on its own GPU
         return self.local.bh(p)

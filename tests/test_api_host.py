@@ -146,3 +146,40 @@ def test_top_table():
     nan_rows = np.where(np.isnan(g["ref_p_values"]))[0]
     assert np.array_equal(np.asarray(table.index)[-len(nan_rows):], nan_rows)
     assert "control" not in table.columns
+
+
+def test_top_table_of_the_noise_fit():
+    """Legacy ``test.fit(fit)`` with neither coefs nor contrasts (backyard/old_fitnoise.R:776-795):
+    the table of the noise p-values, BH-adjusted, ordered by them."""
+    g = load_golden("t_per_sample_controls")
+    fitted, _ = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
+    table = fitted.top_table()
+    p = g["ref_noise_p_values"]
+    key = np.where(np.isnan(p), np.inf, p)
+    order = np.argsort(key, kind="stable")
+    assert list(table.columns) == ["AveExpr", "P.Value", "adj.P.Val", "noise.P.Value", "control"]
+    assert np.array_equal(np.asarray(table.index), order)
+    assert_close(table["P.Value"].values, p[order], 1e-8)
+    assert_close(table["adj.P.Val"].values, oracle.fdr(fitted.noise_p_values)[order], 1e-12)
+    assert np.array_equal(table["P.Value"].values, table["noise.P.Value"].values, equal_nan=True)
+
+
+def test_results_are_released_without_the_cycle_collector():
+    """A fit's result arrays must die with the last reference to them (their pinned host blocks go
+    back to the pool that the next fit draws from): no frame chain, closure or finaliser may keep
+    them waiting for the garbage collector (regression: a lazy ``import torch.distributed`` inside
+    Session.__init__ pinned the whole calling stack of a process's first fit)."""
+    import gc
+    import weakref
+    g = load_golden("t_twogroup")
+    gc.collect()
+    gc.disable()
+    try:
+        fitted, tested = fit_golden(g, engine_factory=hostcheck.HostEvaluator, force_param=g["theta"])
+        refs = [weakref.ref(o) for o in (fitted, tested, fitted._session, fitted.coef, tested.p_values,
+                                         tested.q_values, fitted.noise_p_values)]
+        fitted._session.close()
+        del fitted, tested
+        assert [r() is not None for r in refs] == [False] * len(refs)
+    finally:
+        gc.enable()
