@@ -119,7 +119,7 @@ struct fn_handle {
 
     int64_t n = 0, n_pad = 0;
     int m = 0;
-    bool has_aux = false, loaded = false;
+    bool has_aux = false, loaded = false, has_controls = false;
     Family fam{};
     Design dn, dc;
     int width = 0;
@@ -375,10 +375,13 @@ extern "C" double fn_last_kernel_ms(fn_handle* h) {
 // models) run 10-18 % faster with half the lanes per gene and ONE ~100 KB stage per CTA than with two
 // 50 KB stages: fewer lanes repeat the per-gene tail (reduction, factorisation, logarithm), and the
 // second CTA of the SM covers the load (measured: profiles/r01_sweep_weighted.log).
+// `rows_stride` > 0: the thread-per-gene layout on padded rows (fn_tile.cuh TileSrc::row_stride): one lane
+// per gene, `rows_stride` doubles per row in the stage; 256 threads = 256 genes per tile and one CTA per SM
+// measured best (tools/ps_rows_sweep.py).
 static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_bytes, Geom& g, int min_threads = 0,
-                       size_t per_gene_extra = 0, bool one_big_stage = false) {
+                       size_t per_gene_extra = 0, bool one_big_stage = false, int rows_stride = 0) {
     const int m = h->m;
-    int ctas = h->tune_ctas > 0 ? h->tune_ctas : 2;
+    int ctas = h->tune_ctas > 0 ? h->tune_ctas : (rows_stride > 0 ? 1 : 2);
     int threads = h->tune_threads > 0 ? h->tune_threads : 256;
     // small problems: more, smaller CTAs so that every SM gets work
     if (h->tune_threads == 0 && h->n < (int64_t)h->sm_count * 256) threads = 128;
@@ -394,8 +397,8 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
                tile_stage_bytes(threads / l, m, aux, gs, cst) + (size_t)(threads / l) * per_gene_extra > stage_target) l *= 2;
         return l;
     };
-    int lpg = h->tune_lpg > 0 ? h->tune_lpg : lanes_for(50 * 1024);
-    if (h->tune_lpg == 0 && one_big_stage && threads == 256 && budget > table_bytes + 256 + 64 * 1024) {
+    int lpg = rows_stride > 0 ? 1 : h->tune_lpg > 0 ? h->tune_lpg : lanes_for(50 * 1024);
+    if (rows_stride == 0 && h->tune_lpg == 0 && one_big_stage && threads == 256 && budget > table_bytes + 256 + 64 * 1024) {
         // only when every CTA still gets enough tiles to balance the grid (large n)
         const int big = lanes_for(budget - table_bytes - 256);
         const long long tiles = (h->n + threads / big - 1) / (threads / big);
@@ -406,7 +409,7 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
     if (lpg > 32 || threads % lpg || (threads / lpg) < 16 || ((threads / lpg) & (threads / lpg - 1)) || FN_ROW_PAD % (threads / lpg))
         return fail(FN_ERR_ARG, "invalid geometry: threads %d lpg %d (genes per tile must be a power of two, 16..%d)", threads, lpg, FN_ROW_PAD);
     const int genes = threads / lpg;
-    const size_t stage = tile_stage_bytes(genes, m, aux, gs, cst);
+    const size_t stage = tile_stage_bytes(genes, m, aux, gs, cst, rows_stride);
     const size_t fixed = table_bytes + 256 + (size_t)genes * per_gene_extra;
     if (fixed + stage > h->smem_optin - static_reserve)
         return fail(FN_ERR_UNSUPPORTED, "m = %d is too large for one tile stage in shared memory (%zu bytes)", m, fixed + stage);
@@ -427,7 +430,7 @@ static int choose_geom(fn_handle* h, bool aux, bool gs, bool cst, size_t table_b
 static GeomParams geom_params(const fn_handle* h, const Geom& g) {
     GeomParams gp;
     gp.n = h->n; gp.n_tiles = g.n_tiles; gp.m = h->m; gp.genes = g.genes; gp.lpg = g.lpg;
-    gp.stages = g.stages; gp.width = h->width;
+    gp.stages = g.stages; gp.width = h->width; gp.rows = 0;
     return gp;
 }
 
@@ -753,6 +756,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
 
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     release_data(h);
+    h->has_controls = controls != nullptr && n > 0;
     h->n = n; h->m = m; h->fam = fam; h->has_aux = aux != nullptr; h->dn = dn; h->dc = dc; h->width = width;
     h->n_pad = (n + FN_ROW_PAD - 1) / FN_ROW_PAD * FN_ROW_PAD;
     if (h->n_pad == 0) h->n_pad = FN_ROW_PAD;
@@ -830,7 +834,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     PrepParams pp;
     pp.g = geom_params(h, g);
     pp.src.y = h->y; pp.src.aux = h->aux; pp.src.gs = nullptr; pp.src.cst = nullptr; pp.src.status = h->status;
-    pp.src.m = m; pp.src.genes = g.genes;
+    pp.src.m = m; pp.src.genes = g.genes; pp.src.row_stride = m;
     pp.fam = fam;
     pp.xn = h->xn; pp.xc = h->xc; pp.c_noise = c_noise; pp.c_ctrl = c_ctrl;
     pp.status_out = h->status; pp.cst_out = h->cst; pp.avg_out = h->avg; pp.gs_out = h->gs;
@@ -953,7 +957,15 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
                                !getenv("FN_NO_PATSEQ_SHARED");
     const bool one_big_stage = (h->fam.kind == KIND_SCALE1 && h->has_aux) || (h->fam.kind == KIND_SCALE_PS && !h->has_aux) ||
                                patseq_shared;
-    int rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0, 0, one_big_stage);
+    // unweighted per-sample models, m even: thread per gene on padded rows (broadcast table reads); falls
+    // back to the lanes-per-gene layout when a stage of 128 such rows does not fit
+    bool rows = h->fam.kind == KIND_SCALE_PS && !h->has_aux && m % 2 == 0 && h->tune_lpg <= 1 && !getenv("FN_NO_ROWS");
+    const int rows_stride = (m % 4 == 0) ? m + 2 : m;
+    int rc = rows ? choose_geom(h, false, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0, 0, false, rows_stride) : -1;
+    if (rc) {
+        rows = false;
+        rc = choose_geom(h, h->has_aux, h->gs != nullptr, per_gene, table_bytes, g, inplace ? m : 0, 0, one_big_stage);
+    }
     if (rc) return rc;
     if (inplace && m > g.threads) return fail(FN_ERR_UNSUPPORTED, "per-sample variance models need m <= threads per CTA (%d)", g.threads);
     const KernelSet* ks = kernel_set(h->width);
@@ -980,8 +992,10 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     EvalParams ep;
     ep.g = geom_params(h, g);
     ep.src.y = h->y; ep.src.aux = h->aux; ep.src.gs = h->gs; ep.src.cst = per_gene ? h->cst : nullptr;
-    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes;
+    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes; ep.src.row_stride = rows ? rows_stride : m;
+    ep.g.rows = rows ? 1 : 0;
     ep.xn = h->xn; ep.xc = h->xc; ep.c_noise = h->dn.c; ep.c_ctrl = h->dc.c;
+    ep.has_ctrl = h->has_controls ? 1 : 0;
     ep.kind = h->fam.kind; ep.tail_own = h->fam.tail_own; ep.v3 = h->fam.v3; ep.is_t = ts.is_t;
     ep.v = ts.v; ep.theta0 = ts.theta0;
     ep.ta0 = ts.ta.empty() ? 0.0 : ts.ta[0];
@@ -1240,7 +1254,7 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
     EvalFactorsParams ep;
     ep.g = geom_params(h, g);
     ep.src.y = h->y; ep.src.aux = h->aux; ep.src.gs = nullptr; ep.src.cst = per_gene ? h->cst : nullptr;
-    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes;
+    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes; ep.src.row_stride = m;
     ep.zn = h->zn; ep.zc = h->zc; ep.c_noise = h->dn.c; ep.c_ctrl = h->dc.c; ep.nf = nf;
     ep.is_t = ts.is_t; ep.v = ts.v; ep.theta0 = ts.theta0;
     ep.pg_score = per_gene ? h->pg_score : nullptr;
@@ -1479,7 +1493,7 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     cp.g = geom_params(h, g);
     cp.g.width = d.width;
     cp.src.y = h->y; cp.src.aux = h->aux; cp.src.gs = h->gs; cp.src.cst = nullptr; cp.src.status = h->status;
-    cp.src.m = m; cp.src.genes = g.genes;
+    cp.src.m = m; cp.src.genes = g.genes; cp.src.row_stride = m;
     cp.x = h->x_coef; cp.rinv = h->rinv_dev; cp.c = c; cp.nf = nf;
     cp.kind = h->fam.kind; cp.tail_own = h->fam.tail_own; cp.v3 = h->fam.v3; cp.is_t = ts.is_t;
     cp.v = ts.v; cp.theta0 = ts.theta0;

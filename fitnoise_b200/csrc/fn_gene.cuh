@@ -963,6 +963,92 @@ FN_HD void ps_complete_finish(const EvalConst& ec, const PsDesign<C>& pd, GeneVi
     if (out.value == out.value) kappa_out = kappa;
 }
 
+// ------------------------------------------------------------------------------------------
+// The same complete-row fast path for the THREAD-PER-GENE layout with padded rows (fn_tile.cuh,
+// TileSrc::row_stride): every thread of a warp walks its own gene's row through the SAME samples in
+// the same order, two samples per step.  The pair (y_t, y_t+1) is one 16-byte load per thread (rows are
+// 16-byte aligned and start in distinct bank groups), and the table rows hx_t, x_t, w_t are the same
+// address for all 32 threads: broadcast reads.  The lanes-per-gene mapping of ps_complete_* reads a
+// different table row in every thread instead (14 shared-memory wavefronts per warp and sample at
+// c = 6); here a sample costs about 5 + 7.  No shuffles: each thread holds its gene's sums alone.
+// ------------------------------------------------------------------------------------------
+FN_HD void load_pair(const double* p, double& a, double& b) {
+#ifdef __CUDA_ARCH__
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+FN_HD void store_pair(double* p, double a, double b) {
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
+// beta = sum_j hx_j y_j; false when the row holds a non-finite y (m even)
+template <int C>
+FN_HD bool ps_rows_beta(const PsDesign<C>& pd, const double* yrow, int m, bool on, double* beta) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) beta[i] = 0.0;
+    if (!on) return false;
+#pragma unroll 2
+    for (int t = 0; t < m; t += 2) {
+        double y0, y1;
+        load_pair(yrow + t, y0, y1);
+        double h0[C], h1[C];
+        load_x<C>(pd.hx, t, h0);
+        load_x<C>(pd.hx, t + 1, h1);
+#pragma unroll
+        for (int i = 0; i < C; ++i) beta[i] = fma(h0[i], y0, beta[i]);
+#pragma unroll
+        for (int i = 0; i < C; ++i) beta[i] = fma(h1[i], y1, beta[i]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) s += beta[i];
+    return finite_d(s);
+}
+
+// residuals, d2, s_j = (w_j r_j)^2 into the row's slots (zeros when `zero`), then the density
+template <int C>
+FN_HD void ps_rows_finish(const EvalConst& ec, const PsDesign<C>& pd, double* yrow, int m, const double* X, int c_real,
+                          bool mine, bool zero, const double* beta, double cst, EvalOut& out, double& kappa_out) {
+    kappa_out = 0.0;
+    if (!mine) {
+        if (zero)
+            for (int t = 0; t < m; t += 2) store_pair(yrow + t, 0.0, 0.0);
+        return;
+    }
+    double d2 = 0.0;
+#pragma unroll 2
+    for (int t = 0; t < m; t += 2) {
+        double y0, y1, w0, w1;
+        load_pair(yrow + t, y0, y1);
+        load_pair(ec.ta + t, w0, w1);
+        double x0[C], x1[C];
+        load_x<C>(X, t, x0);
+        load_x<C>(X, t + 1, x1);
+        double r0 = y0, r1 = y1;
+#pragma unroll
+        for (int i = 0; i < C; ++i) { r0 = fma(-x0[i], beta[i], r0); r1 = fma(-x1[i], beta[i], r1); }
+        const double wr0 = w0 * r0, wr1 = w1 * r1;
+        d2 = fma(wr0, r0, d2);
+        d2 = fma(wr1, r1, d2);
+        store_pair(yrow + t, wr0 * wr0, wr1 * wr1);
+    }
+    eval_zero(out);
+    out.used = 1;
+    const int p = m - c_real;
+    if (!(pd.ok && p > 0 && d2 == d2)) { out.value = NAN; return; }
+    double dv, kappa;
+    out.value = finish_density(ec, p, pd.slt + pd.logdet_a + cst, d2, dv, kappa);
+    out.dv = dv; out.d2 = d2; out.p = p;
+    if (out.value == out.value) kappa_out = kappa;
+}
+
 // 1/x for a positive normal double.  Device: hardware seed (>= 20 bits) and two Newton steps, i.e. one
 // MUFU and four FMAs instead of the ~12-instruction correctly rounded division; the result is within
 // an ulp, and it only ever feeds sums over samples and genes.

@@ -221,25 +221,37 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const StepVars
         if (threadIdx.x == 0) *gr.ticket = 0;
         __threadfence();
         __syncthreads();
-        if (nacc <= T) {
-            // thread (slice, i) adds blocks slice, slice+S, ... of component i; then the slices are added
-            const int S = T / nacc, i = threadIdx.x % nacc, slice = threadIdx.x / nacc;
-            if (slice < S) {
-                double a = 0.0;
-                for (unsigned int b = slice; b < G; b += S) a += __ldcg(&gr.partials[(size_t)b * nacc + i]);
-                gsum[slice * nacc + i] = a;
-            }
-            __syncthreads();
-            if (threadIdx.x < nacc) {
-                double a = 0.0;
-                for (int q = 0; q < S; ++q) a += gsum[q * nacc + threadIdx.x];
-                publish(threadIdx.x, a);
-            }
-        } else {
-            for (int i = threadIdx.x; i < nacc; i += T) {
-                double a = 0.0;
-                for (unsigned int b = 0; b < G; ++b) a += __ldcg(&gr.partials[(size_t)b * nacc + i]);
-                publish(i, a);
+        // Warp w takes components w, w + W, ... (eight at a time); its lanes add the partials of CTAs
+        // lane, lane + 32, ... and a xor-shuffle tree combines them: a fixed order for a given grid.
+        // All loads of a batch are independent, so the reduction costs a few L2 round trips -- the
+        // earlier form (one thread per component walking the CTAs one dependent iteration at a time)
+        // took 27 us at nacc = 103 on 148 CTAs, a quarter of a per-sample evaluation at 200k x 48.
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = T >> 5;
+            constexpr int NB = 8;
+            for (int i0 = warp; i0 < nacc; i0 += NB * W) {
+                double a[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) a[k] = 0.0;
+#pragma unroll 2
+                for (unsigned int b = lane; b < G; b += 32) {
+                    const double* row = gr.partials + (size_t)b * nacc;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const int i = i0 + k * W;
+                        if (i < nacc) a[k] += __ldcg(row + i);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                        if (i0 + k * W < nacc) publish(i0 + k * W, a[k]);
+                }
             }
         }
         FN_STAMP_ANY(9);
@@ -313,6 +325,7 @@ struct GeomParams {
     int lpg;
     int stages;
     int width;               // template width C the designs are padded to
+    int rows;                // 1: thread per gene on padded rows (lpg == 1, m even; ps_rows_* in fn_gene.cuh)
 };
 
 // dynamic shared memory of the per-gene kernels: [stage buffers][tables].  The stage area comes
@@ -576,6 +589,7 @@ struct EvalParams {
     TileSrc src;             // y, aux (precision weights / rc), gs, cst (per-gene mode only), status
     const double* xn; const double* xc;
     int c_noise, c_ctrl;
+    int has_ctrl;            // 0: no gene carries the control bit (the control design's per-evaluation tables are skipped)
     int kind, tail_own, v3, is_t;
     double v, theta0;        // one-launch form (resident: from the command)
     double ta0, tb0;         // shared theta_a / theta_b (general kinds); per-sample blocks come from ta / tb
@@ -599,7 +613,7 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
     FN_STAMP(0);
     const TileLayout L = tile_layout(p.src);
     TileRing ring;
-    ring_setup(ring, bars, p.g.stages, p.g.n_tiles, resident);
+    ring_setup(ring, bars, p.g.stages, p.g.n_tiles, resident, tile_barrier_count(p.src));
     // tables behind the stage area: xn, xc (m*C each), [hxn, hxc (m*C each): KIND_SCALE_PS], ta, tb (m each),
     // t0, t1 (m+1 each), vals (ACC_FIXED + 2m), colscr (2*blockDim when a theta block is per-sample).
     // The design-shaped tables come first: their rows must stay 16-byte aligned for LDS.128 (the stage
@@ -636,6 +650,9 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
     // per-sample gradient columns: thread (sub, col) sums column col over genes sub, sub+nsub, ...
     const int nsub = inplace ? blockDim.x / m : 0;
     const int col = inplace ? threadIdx.x % m : 0, sub = inplace ? threadIdx.x / m : 0;
+    // rows layout (thread per gene, m even): thread (sub2, colp) sums the column PAIR colp over genes sub2, sub2+nsub2, ...
+    const int nsub2 = inplace ? (int)blockDim.x / (m >> 1 ? m >> 1 : 1) : 0;
+    const int colp = inplace ? (int)threadIdx.x % (m >> 1 ? m >> 1 : 1) : 0, sub2 = inplace ? (int)threadIdx.x / (m >> 1 ? m >> 1 : 1) : 0;
 
     unsigned long long expect = p.rc.next_seq;
     for (;;) {
@@ -692,9 +709,14 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
         PsDesign<C> pdn, pdc;
         if (fastps) {
             build_ps_design<C>(xn, p.c_noise, ta, tb, m, hxn, cjn, pstri, pssc);
-            build_ps_design<C>(xc, p.c_ctrl, ta, tb, m, hxc, cjc, pstri, pssc + 3);
             pdn.hx = hxn; pdn.cj = cjn; pdn.logdet_a = pssc[0]; pdn.slt = pssc[1]; pdn.ok = pssc[2] != 0.0;
-            pdc.hx = hxc; pdc.cj = cjc; pdc.logdet_a = pssc[3]; pdc.slt = pssc[4]; pdc.ok = pssc[5] != 0.0;
+            if (p.has_ctrl) {                  // control genes present: the second design's tables
+                build_ps_design<C>(xc, p.c_ctrl, ta, tb, m, hxc, cjc, pstri, pssc + 3);
+                pdc.hx = hxc; pdc.cj = cjc; pdc.logdet_a = pssc[3]; pdc.slt = pssc[4]; pdc.ok = pssc[5] != 0.0;
+            } else {
+                pdc = pdn;
+                for (int j = threadIdx.x; j < m; j += blockDim.x) cjc[j] = 0.0;
+            }
             if (threadIdx.x < 2) ps_count[threadIdx.x] = 0;
             __syncthreads();
         }
@@ -779,12 +801,14 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
             });
         } else {
             // PATSEQ keeps 1/sigma2 in the aux tile between its two sweeps: the stage is always written
+            const int S = p.src.row_stride;                  // doubles between the rows of a stage
+            const bool rows = KIND == KIND_SCALE_PS && fastps && p.g.rows != 0;
             ring.pass(smem_raw, bars, p.src, L, inplace || KIND == KIND_PATSEQ, [&](unsigned char* st, long long tile) {
                 const long long gene = tile * p.g.genes + gl;
                 double* ys = (double*)st;
                 double* auxs = (double*)(st + L.aux_off);
-                gv.y = ys + (size_t)gl * m;
-                gv.aux = p.src.aux ? auxs + (size_t)gl * m : nullptr;
+                gv.y = ys + (size_t)gl * S;
+                gv.aux = p.src.aux ? auxs + (size_t)gl * S : nullptr;
                 gv.gs = p.src.gs ? ((const double*)(st + L.gs_off))[gl] : 0.0;
                 const uint8_t status = st[L.status_off + gl];
                 const bool control = (status & 2) != 0;
@@ -797,7 +821,8 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
                     // complete genes: shared normal matrix (PsDesign); the others: the general two sweeps
                     const PsDesign<C>& pd = control ? pdc : pdn;
                     double beta[C];
-                    const bool complete = ps_complete_beta<C>(pd, gv, eligible, beta);
+                    const bool complete = rows ? ps_rows_beta<C>(pd, gv.y, m, eligible, beta)
+                                                : ps_complete_beta<C>(pd, gv, eligible, beta);
                     eval_zero(eo);
                     if constexpr (!LEAN) {
                         if (warp_any(eligible && !complete))
@@ -808,23 +833,45 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
                     }
                     EvalOut ef;
                     double kappa;
-                    ps_complete_finish<C>(ec, pd, gv, X, c_real, complete, LEAN ? !complete : !eligible, beta, cst, ef, kappa);
+                    if (rows) ps_rows_finish<C>(ec, pd, gv.y, m, X, c_real, complete, LEAN ? !complete : !eligible, beta, cst, ef, kappa);
+                    else ps_complete_finish<C>(ec, pd, gv, X, c_real, complete, LEAN ? !complete : !eligible, beta, cst, ef, kappa);
                     if (complete) eo = ef;
-                    if (lane == 0) {
-                        // the column sum multiplies the gene's slots by this: -kappa for s_j = (w_j r_j)^2
-                        kap[gl] = complete ? -kappa : 1.0;
-                        if (complete && kappa > 0.0 && gene < p.g.n) atomicAdd(&ps_count[control ? 1 : 0], 1);
+                    // the column sum multiplies the gene's slots by this: -kappa for s_j = (w_j r_j)^2
+                    if (lane == 0) kap[gl] = complete ? -kappa : 1.0;
+                    {
+                        // complete genes of this warp by design: one shared-memory atomic per warp, not per gene
+                        const bool counted = lane == 0 && complete && kappa > 0.0 && gene < p.g.n;
+                        const unsigned int mn = __ballot_sync(0xffffffffu, counted && !control);
+                        const unsigned int mc = __ballot_sync(0xffffffffu, counted && control);
+                        if ((threadIdx.x & 31) == 0) {
+                            if (mn) atomicAdd(&ps_count[0], __popc(mn));
+                            if (mc) atomicAdd(&ps_count[1], __popc(mc));
+                        }
                     }
                 } else if constexpr (!LEAN) {
                     eval_general<C, KIND>(ec, gv, X, c_real, eligible, cst, p.inplace_a != 0, p.inplace_b != 0, eo);
                 }
                 if (lane == 0) account(eo, gene);
-                if (inplace) {
+                if (inplace && rows) {
+                    // thread (sub2, column pair): one 16-byte load covers two columns of a gene's row
+                    __syncthreads();
+                    if (sub2 < nsub2) {
+                        const double* at = ys + (size_t)sub2 * S + 2 * colp;
+#pragma unroll 4
+                        for (int g = sub2; g < p.g.genes; g += nsub2, at += (size_t)nsub2 * S) {
+                            double s0, s1;
+                            load_pair(at, s0, s1);
+                            const double k = kap[g];
+                            col_a = fma(k, s0, col_a);
+                            col_b = fma(k, s1, col_b);          // (col_b doubles as the odd column's sum here)
+                        }
+                    }
+                } else if (inplace) {
                     __syncthreads();
                     if (sub < nsub) {
                         for (int g = sub; g < p.g.genes; g += nsub) {
-                            if (p.inplace_a) col_a += (KIND == KIND_SCALE_PS && fastps) ? kap[g] * ys[(size_t)g * m + col] : ys[(size_t)g * m + col];
-                            if (p.inplace_b) col_b += auxs[(size_t)g * m + col];
+                            if (p.inplace_a) col_a += (KIND == KIND_SCALE_PS && fastps) ? kap[g] * ys[(size_t)g * S + col] : ys[(size_t)g * S + col];
+                            if (p.inplace_b) col_b += auxs[(size_t)g * S + col];
                         }
                     }
                 }
@@ -833,7 +880,19 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
 
         block_sum<ACC_FIXED>(acc, vals, red_scratch);
         FN_STAMP(5);
-        if (inplace) {
+        if (inplace && KIND == KIND_SCALE_PS && fastps && p.g.rows != 0) {
+            // rows layout: colscr[sub2][m], thread (sub2, pair) holds columns 2 pair and 2 pair + 1
+            if (sub2 < nsub2) { colscr[sub2 * m + 2 * colp] = col_a; colscr[sub2 * m + 2 * colp + 1] = col_b; }
+            __syncthreads();
+            if (threadIdx.x < m) {
+                double sa = 0.0;
+                for (int q = 0; q < nsub2; ++q) sa += colscr[q * m + threadIdx.x];
+                sa += ps_count[0] * cjn[threadIdx.x] + ps_count[1] * cjc[threadIdx.x];
+                vals[ACC_FIXED + threadIdx.x] = sa;
+                vals[ACC_FIXED + m + threadIdx.x] = 0.0;
+            }
+            __syncthreads();
+        } else if (inplace) {
             colscr[threadIdx.x] = col_a;
             colscr[blockDim.x + threadIdx.x] = col_b;
             __syncthreads();

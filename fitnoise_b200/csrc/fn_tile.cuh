@@ -60,6 +60,11 @@ struct TileSrc {
     const uint8_t* status;   // n_pad (bit0 eligible, bit1 control) -- always present
     int m;
     int genes;               // G, a multiple of 16
+    int row_stride;          // doubles between consecutive gene rows of y / aux INSIDE the stage: m (dense: the
+                             // tile is one bulk copy) or m + 2 (padded rows, one bulk copy per gene row: with a
+                             // stride of 2 mod 4 doubles the rows of 8 consecutive genes start in 8 distinct
+                             // 16-byte bank groups, so thread-per-gene LDS.128 reads of a sample pair are
+                             // conflict-free while every thread of the warp visits the SAME samples)
 };
 
 // Byte offsets of the arrays inside one stage buffer (uniform over the CTA, computed once).
@@ -68,28 +73,72 @@ struct TileLayout {
     uint32_t stage_bytes, tx_bytes, row_bytes;
 };
 
-__host__ __device__ inline size_t tile_stage_bytes(int genes, int m, bool aux, bool gs, bool cst) {
-    size_t b = (size_t)genes * m * 8 * (aux ? 2 : 1) + (size_t)genes * 8 * ((gs ? 1 : 0) + (cst ? 1 : 0)) + genes;
+__host__ __device__ inline size_t tile_stage_bytes(int genes, int m, bool aux, bool gs, bool cst, int row_stride = 0) {
+    size_t b = (size_t)genes * (row_stride > 0 ? row_stride : m) * 8 * (aux ? 2 : 1) + (size_t)genes * 8 * ((gs ? 1 : 0) + (cst ? 1 : 0)) + genes;
     return (b + 127) & ~(size_t)127;
 }
 
 __device__ __forceinline__ TileLayout tile_layout(const TileSrc& s) {
     TileLayout L;
-    L.row_bytes = (uint32_t)s.genes * s.m * 8;
-    uint32_t at = L.row_bytes;
-    L.aux_off = at; if (s.aux) at += L.row_bytes;
+    L.row_bytes = (uint32_t)s.genes * s.m * 8;                        // bytes one matrix contributes to a stage's transfer
+    const uint32_t span = (uint32_t)s.genes * s.row_stride * 8;       // bytes it occupies in the stage
+    uint32_t at = span;
+    L.aux_off = at; if (s.aux) at += span;
     L.gs_off = at; if (s.gs) at += (uint32_t)s.genes * 8;
     L.cst_off = at; if (s.cst) at += (uint32_t)s.genes * 8;
     L.status_off = at; at += (uint32_t)s.genes;
-    L.tx_bytes = at;
+    // bytes the bulk copies of a stage deliver: everything when the rows are dense; only the per-gene
+    // scalars when they are padded (the rows then travel as cp.async, counted by arrivals, not bytes)
+    L.tx_bytes = (s.row_stride == s.m) ? at : at - (s.aux ? 2u : 1u) * span;
     L.stage_bytes = (at + 127u) & ~127u;
     return L;
 }
 
-// called by ONE thread: arm the stage's barrier and start the copies of `tile` into it
+// Dense rows: called by ONE thread (threadIdx.x == 0): arm the stage's barrier and start the bulk copies
+// of `tile` into it.
+// Padded rows (row_stride != m): called by EVERY thread of the CTA.  A bulk copy per gene row would be
+// the obvious form, but UBLKCP is a uniform-datapath instruction (one copy per warp instruction, lanes
+// serialised) and the TMA unit sustains only about one such small operation per 100 ns per SM -- measured
+// 0.57 TB/s over the GPU at 384-byte rows, slower than the kernel it was meant to feed.  So the rows move
+// with 16-byte cp.async (LDGSTS) issued by all threads, coalesced in global memory, and each thread's
+// copies arrive on the stage's mbarrier (cp.async.mbarrier.arrive.noinc: the barrier is initialised for
+// blockDim.x + 1 arrivals); thread 0 adds the per-gene scalars as bulk copies with their byte count.
+__device__ __forceinline__ bool tile_padded(const TileSrc& src) { return src.row_stride != src.m; }
+__device__ __forceinline__ bool tile_issuer(const TileSrc& src) { return tile_padded(src) || threadIdx.x == 0; }
+__device__ __forceinline__ uint32_t tile_barrier_count(const TileSrc& src) { return tile_padded(src) ? blockDim.x + 1u : 1u; }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tile_issue(const TileSrc& src, const TileLayout& L, unsigned char* stage,
                                            uint64_t* bar, long long tile) {
     const long long g0 = tile * src.genes;
+    if (tile_padded(src)) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, L.tx_bytes);
+            if (src.gs) bulk_g2s(stage + L.gs_off, src.gs + g0, (uint32_t)src.genes * 8, bar);
+            if (src.cst) bulk_g2s(stage + L.cst_off, src.cst + g0, (uint32_t)src.genes * 8, bar);
+            bulk_g2s(stage + L.status_off, src.status + g0, (uint32_t)src.genes, bar);
+        }
+        const int cpr = src.m >> 1;                              // 16-byte chunks per row (m is even)
+        const int total = src.genes * cpr;
+        const uint32_t pitch = (uint32_t)src.row_stride * 8;
+        int row = (int)threadIdx.x / cpr, k = (int)threadIdx.x - row * cpr;
+        const int drow = (int)blockDim.x / cpr, dk = (int)blockDim.x - drow * cpr;
+        const char* gy = (const char*)(src.y + g0 * src.m);
+        const char* ga = src.aux ? (const char*)(src.aux + g0 * src.m) : nullptr;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint32_t at = (uint32_t)row * pitch + (uint32_t)k * 16u;
+            cp_async16(stage + at, gy + (size_t)i * 16);
+            if (ga) cp_async16(stage + L.aux_off + at, ga + (size_t)i * 16);
+            row += drow; k += dk;
+            if (k >= cpr) { k -= cpr; ++row; }
+        }
+        cp_async_arrive(bar);
+        return;
+    }
     mbar_expect_tx(bar, L.tx_bytes);
     bulk_g2s(stage, src.y + g0 * src.m, L.row_bytes, bar);
     if (src.aux) bulk_g2s(stage + L.aux_off, src.aux + g0 * src.m, L.row_bytes, bar);
@@ -103,8 +152,10 @@ __device__ __forceinline__ void tile_issue(const TileSrc& src, const TileLayout&
 __device__ __forceinline__ void tile_prologue(unsigned char* smem, uint64_t* bars, int stages, const TileSrc& src,
                                               const TileLayout& L, long long n_tiles) {
     if (threadIdx.x == 0) {
-        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);      // dense rows only (K1, K3)
         mbar_fence_init();
+    }
+    if (tile_issuer(src)) {
         for (int s = 0; s < stages - 1; ++s) {
             const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
             if (t < n_tiles) tile_issue(src, L, smem + (size_t)s * L.stage_bytes, &bars[s], t);
@@ -124,7 +175,7 @@ __device__ __forceinline__ void tile_loop(unsigned char* smem, uint64_t* bars, i
     int slot = 0, pre = stages - 1;       // pre: slot consumed in the previous iteration
     uint32_t parity = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += step) {
-        if (threadIdx.x == 0) {
+        if (tile_issuer(src)) {
             const long long ahead = tile + (long long)(stages - 1) * step;
             if (ahead < n_tiles) tile_issue(src, L, smem + (size_t)pre * L.stage_bytes, &bars[pre], ahead);
         }
@@ -160,7 +211,7 @@ struct TileRing {
 
     // all threads; barriers must have been initialised (mbar_init + fence) and published by a __syncthreads
     __device__ __forceinline__ void begin(unsigned char* smem, uint64_t* bars, const TileSrc& src, const TileLayout& L) {
-        if (threadIdx.x == 0 && cnt > 0) {
+        if (tile_issuer(src) && cnt > 0) {
             for (int s = 0; s < stages - 1; ++s) {
                 if (!wrap && s >= cnt) break;
                 const int sl = (slot + s) % stages;
@@ -173,7 +224,7 @@ struct TileRing {
     __device__ __forceinline__ void pass(unsigned char* smem, uint64_t* bars, const TileSrc& src, const TileLayout& L,
                                          bool wrote_smem, Body body) {
         for (long long i = 0; i < cnt; ++i) {
-            if (threadIdx.x == 0) {
+            if (tile_issuer(src)) {
                 const long long ahead = i + (long long)(stages - 1);
                 if (wrap || ahead < cnt) tile_issue(src, L, smem + (size_t)pre * L.stage_bytes, &bars[pre], tile_at(ahead));
             }
@@ -198,12 +249,13 @@ struct TileRing {
     }
 };
 
-__device__ __forceinline__ void ring_setup(TileRing& r, uint64_t* bars, int stages, long long n_tiles, bool wrap) {
+__device__ __forceinline__ void ring_setup(TileRing& r, uint64_t* bars, int stages, long long n_tiles, bool wrap,
+                                           uint32_t barrier_count = 1) {
     r.slot = 0; r.pre = stages - 1; r.parity = 0; r.stages = stages; r.wrap = wrap;
     r.first = blockIdx.x; r.step = gridDim.x;
     r.cnt = (long long)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < stages; ++i) mbar_init(&bars[i], barrier_count);
         mbar_fence_init();
     }
 }
