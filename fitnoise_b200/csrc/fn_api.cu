@@ -834,7 +834,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
     PrepParams pp;
     pp.g = geom_params(h, g);
     pp.src.y = h->y; pp.src.aux = h->aux; pp.src.gs = nullptr; pp.src.cst = nullptr; pp.src.status = h->status;
-    pp.src.m = m; pp.src.genes = g.genes; pp.src.row_stride = m;
+    pp.src.m = m; pp.src.genes = g.genes; pp.src.row_stride = m; pp.src.l2_keep = 0;
     pp.fam = fam;
     pp.xn = h->xn; pp.xc = h->xc; pp.c_noise = c_noise; pp.c_ctrl = c_ctrl;
     pp.status_out = h->status; pp.cst_out = h->cst; pp.avg_out = h->avg; pp.gs_out = h->gs;
@@ -952,7 +952,7 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     Geom g;
     size_t table_bytes = (2 * (size_t)m * h->width + 2 * m + 2 * (m + 1) + ACC_FIXED + 2 * m + (inplace ? 2 * 256 : 0)) * sizeof(double);
     if (h->fam.kind == KIND_SCALE_PS)      // complete-row fast path: two designs' tables, scratch, kappa per gene
-        table_bytes += (2 * (size_t)m * h->width + 2 * m + (size_t)h->width * (h->width + 1) / 2 + 8 + 256) * sizeof(double);
+        table_bytes += (4 * (size_t)m * h->width + 2 * m + (size_t)h->width * (h->width + 1) / 2 + 8 + 256) * sizeof(double);
     const bool patseq_shared = h->fam.kind == KIND_PATSEQ && h->fam.na == 1 && h->fam.nb == 1 && h->width <= 4 &&
                                !getenv("FN_NO_PATSEQ_SHARED");
     const bool one_big_stage = (h->fam.kind == KIND_SCALE1 && h->has_aux) || (h->fam.kind == KIND_SCALE_PS && !h->has_aux) ||
@@ -993,6 +993,13 @@ static int launch_eval(fn_handle* h, const ThetaState& ts, bool per_gene, bool e
     ep.g = geom_params(h, g);
     ep.src.y = h->y; ep.src.aux = h->aux; ep.src.gs = h->gs; ep.src.cst = per_gene ? h->cst : nullptr;
     ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes; ep.src.row_stride = rows ? rows_stride : m;
+    {
+        // the resident matrices of this handle fit the L2: ask it to keep them between evaluations
+        const char* env = getenv("FN_L2_KEEP");
+        const size_t resident_bytes = (size_t)h->n_pad * m * sizeof(double) * (h->has_aux ? 2 : 1);
+        const size_t limit = (size_t)(env ? atof(env) * 1048576.0 : 0.0);
+        ep.src.l2_keep = (limit > 0 && resident_bytes <= limit) ? 1 : 0;
+    }
     ep.g.rows = rows ? 1 : 0;
     ep.xn = h->xn; ep.xc = h->xc; ep.c_noise = h->dn.c; ep.c_ctrl = h->dc.c;
     ep.has_ctrl = h->has_controls ? 1 : 0;
@@ -1254,7 +1261,7 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
     EvalFactorsParams ep;
     ep.g = geom_params(h, g);
     ep.src.y = h->y; ep.src.aux = h->aux; ep.src.gs = nullptr; ep.src.cst = per_gene ? h->cst : nullptr;
-    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes; ep.src.row_stride = m;
+    ep.src.status = h->status; ep.src.m = m; ep.src.genes = g.genes; ep.src.row_stride = m; ep.src.l2_keep = 0;
     ep.zn = h->zn; ep.zc = h->zc; ep.c_noise = h->dn.c; ep.c_ctrl = h->dc.c; ep.nf = nf;
     ep.is_t = ts.is_t; ep.v = ts.v; ep.theta0 = ts.theta0;
     ep.pg_score = per_gene ? h->pg_score : nullptr;
@@ -1493,7 +1500,7 @@ extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, 
     cp.g = geom_params(h, g);
     cp.g.width = d.width;
     cp.src.y = h->y; cp.src.aux = h->aux; cp.src.gs = h->gs; cp.src.cst = nullptr; cp.src.status = h->status;
-    cp.src.m = m; cp.src.genes = g.genes; cp.src.row_stride = m;
+    cp.src.m = m; cp.src.genes = g.genes; cp.src.row_stride = m; cp.src.l2_keep = 0;
     cp.x = h->x_coef; cp.rinv = h->rinv_dev; cp.c = c; cp.nf = nf;
     cp.kind = h->fam.kind; cp.tail_own = h->fam.tail_own; cp.v3 = h->fam.v3; cp.is_t = ts.is_t;
     cp.v = ts.v; cp.theta0 = ts.theta0;

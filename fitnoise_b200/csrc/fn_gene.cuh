@@ -47,9 +47,19 @@ FN_HD bool finite_d(double x) { return fabs(x) < INFINITY; }   // false for NaN 
 // ------------------------------------------------------------------------------------------
 // lane cooperation
 // ------------------------------------------------------------------------------------------
+// (lpg is uniform over the CTA: the fall-through switch runs exactly log2(lpg) shuffle steps with one
+// branch, where a loop over the distances spent more instructions on loop control than on shuffles --
+// 10 % of the instructions of the headline kernel at 1M x 96.)
 FN_HD double lane_sum(double v, int lpg) {
 #ifdef __CUDA_ARCH__
-    for (int off = lpg >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    switch (lpg) {
+        case 32: v += __shfl_xor_sync(0xffffffffu, v, 16);
+        case 16: v += __shfl_xor_sync(0xffffffffu, v, 8);
+        case 8: v += __shfl_xor_sync(0xffffffffu, v, 4);
+        case 4: v += __shfl_xor_sync(0xffffffffu, v, 2);
+        case 2: v += __shfl_xor_sync(0xffffffffu, v, 1);
+        default: break;
+    }
 #else
     (void)lpg;
 #endif
@@ -60,10 +70,16 @@ FN_HD double lane_sum(double v, int lpg) {
 template <int N>
 FN_HD void lane_sum_n(double* v, int lpg) {
 #ifdef __CUDA_ARCH__
-    for (int off = lpg >> 1; off > 0; off >>= 1) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+#define FN_LANE_STEP(off) _Pragma("unroll") for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    switch (lpg) {
+        case 32: FN_LANE_STEP(16)
+        case 16: FN_LANE_STEP(8)
+        case 8: FN_LANE_STEP(4)
+        case 4: FN_LANE_STEP(2)
+        case 2: FN_LANE_STEP(1)
+        default: break;
     }
+#undef FN_LANE_STEP
 #else
     (void)v; (void)lpg;
 #endif
@@ -656,9 +672,14 @@ FN_HD void scale1_sweep(const EvalConst& ec, const GeneView& gv, const double* X
             yy += y * y;
         });
         if (gv.lpg > 1) {
+            double sums[C + 1];
 #pragma unroll
-            for (int i = 0; i < C; ++i) b[i] = lane_sum(b[i], gv.lpg);
-            yy = lane_sum(yy, gv.lpg);
+            for (int i = 0; i < C; ++i) sums[i] = b[i];
+            sums[C] = yy;
+            lane_sum_n<C + 1>(sums, gv.lpg);
+#pragma unroll
+            for (int i = 0; i < C; ++i) b[i] = sums[i];
+            yy = sums[C];
         }
         complete = finite_d(yy);
 #pragma unroll
@@ -988,6 +1009,16 @@ FN_HD void store_pair(double* p, double a, double b) {
 #endif
 }
 
+// Row j of a design-shaped table whose rows are 2C doubles apart: the rows layout keeps the noise design's
+// and the control design's tables INTERLEAVED (row j = [noise_j | control_j]), so that a warp whose genes
+// are a mix of both reads two 16-byte-aligned pieces of one 16C-byte span (distinct banks) instead of two
+// addresses a multiple of 128 bytes apart (the same banks: a two-way conflict on every table read).
+template <int C>
+FN_HD void load_x2(const double* X, int j, double* x) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) x[i] = X[j * (2 * C) + i];
+}
+
 // beta = sum_j hx_j y_j; false when the row holds a non-finite y (m even)
 template <int C>
 FN_HD bool ps_rows_beta(const PsDesign<C>& pd, const double* yrow, int m, bool on, double* beta) {
@@ -999,8 +1030,8 @@ FN_HD bool ps_rows_beta(const PsDesign<C>& pd, const double* yrow, int m, bool o
         double y0, y1;
         load_pair(yrow + t, y0, y1);
         double h0[C], h1[C];
-        load_x<C>(pd.hx, t, h0);
-        load_x<C>(pd.hx, t + 1, h1);
+        load_x2<C>(pd.hx, t, h0);
+        load_x2<C>(pd.hx, t + 1, h1);
 #pragma unroll
         for (int i = 0; i < C; ++i) beta[i] = fma(h0[i], y0, beta[i]);
 #pragma unroll
@@ -1029,8 +1060,8 @@ FN_HD void ps_rows_finish(const EvalConst& ec, const PsDesign<C>& pd, double* yr
         load_pair(yrow + t, y0, y1);
         load_pair(ec.ta + t, w0, w1);
         double x0[C], x1[C];
-        load_x<C>(X, t, x0);
-        load_x<C>(X, t + 1, x1);
+        load_x2<C>(X, t, x0);
+        load_x2<C>(X, t + 1, x1);
         double r0 = y0, r1 = y1;
 #pragma unroll
         for (int i = 0; i < C; ++i) { r0 = fma(-x0[i], beta[i], r0); r1 = fma(-x1[i], beta[i], r1); }

@@ -552,7 +552,7 @@ __device__ __forceinline__ int resident_wait(const ResidentCtl& rc, unsigned lon
 // then one table row per thread.  `tri`: Tri<C>::N doubles of scratch, `sc`: 3 doubles.
 template <int C>
 __device__ __forceinline__ void build_ps_design(const double* X, int c_real, const double* w, const double* lt, int m,
-                                                double* hx, double* cj, double* tri, double* sc) {
+                                                double* hx, int hx_stride, double* cj, double* tri, double* sc) {
     constexpr int N = Tri<C>::N;
     for (int e = threadIdx.x; e < N; e += blockDim.x) {
         int i = 0;
@@ -579,7 +579,7 @@ __device__ __forceinline__ void build_ps_design(const double* X, int c_real, con
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         double x[C];
         load_x<C>(X, j, x);
-        ps_table_row<C>(tri, x, w[j], hx + j * C, cj[j]);
+        ps_table_row<C>(tri, x, w[j], hx + j * hx_stride, cj[j]);
     }
     __syncthreads();
 }
@@ -636,10 +636,22 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
     double* cjc = cjn + m;
     double* pstri = cjc + m;
     double* pssc = pstri + Tri<C>::N;          // 2 x 3
-    double* kap = pssc + 8;                    // genes per tile
+    double* kap = pssc + 8;                    // genes per tile (<= 256)
+    // rows layout: the two designs' tables interleaved row by row (fn_gene.cuh load_x2): hx2 re-uses the
+    // hxn / hxc area (2 m C doubles), x2 is a second copy of the designs
+    const bool rows_tables = fastps && p.g.rows != 0;
+    double* x2 = kap + 256;
+    const int hx_stride = rows_tables ? 2 * C : XS;
+    double* hxc_at = rows_tables ? hxn + C : hxc;
     __shared__ int ps_count[2];
     stage_design<C>(xn, p.xn, m);
     stage_design<C>(xc, p.xc, m);
+    if (rows_tables)
+        for (int i = threadIdx.x; i < m * C; i += blockDim.x) {
+            const int j = i / C, k = i - j * C;
+            x2[j * 2 * C + k] = p.xn[i];
+            x2[j * 2 * C + C + k] = p.xc[i];
+        }
     __syncthreads();                                   // barrier initialisation + designs visible
     ring.begin(smem_raw, bars, p.src, L);              // the first tiles are in flight
     FN_STAMP(1);
@@ -708,11 +720,11 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
         else if (KIND != KIND_SCALE1) __syncthreads();
         PsDesign<C> pdn, pdc;
         if (fastps) {
-            build_ps_design<C>(xn, p.c_noise, ta, tb, m, hxn, cjn, pstri, pssc);
+            build_ps_design<C>(xn, p.c_noise, ta, tb, m, hxn, hx_stride, cjn, pstri, pssc);
             pdn.hx = hxn; pdn.cj = cjn; pdn.logdet_a = pssc[0]; pdn.slt = pssc[1]; pdn.ok = pssc[2] != 0.0;
             if (p.has_ctrl) {                  // control genes present: the second design's tables
-                build_ps_design<C>(xc, p.c_ctrl, ta, tb, m, hxc, cjc, pstri, pssc + 3);
-                pdc.hx = hxc; pdc.cj = cjc; pdc.logdet_a = pssc[3]; pdc.slt = pssc[4]; pdc.ok = pssc[5] != 0.0;
+                build_ps_design<C>(xc, p.c_ctrl, ta, tb, m, hxc_at, hx_stride, cjc, pstri, pssc + 3);
+                pdc.hx = hxc_at; pdc.cj = cjc; pdc.logdet_a = pssc[3]; pdc.slt = pssc[4]; pdc.ok = pssc[5] != 0.0;
             } else {
                 pdc = pdn;
                 for (int j = threadIdx.x; j < m; j += blockDim.x) cjc[j] = 0.0;
@@ -833,7 +845,7 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
                     }
                     EvalOut ef;
                     double kappa;
-                    if (rows) ps_rows_finish<C>(ec, pd, gv.y, m, X, c_real, complete, LEAN ? !complete : !eligible, beta, cst, ef, kappa);
+                    if (rows) ps_rows_finish<C>(ec, pd, gv.y, m, control ? x2 + C : x2, c_real, complete, LEAN ? !complete : !eligible, beta, cst, ef, kappa);
                     else ps_complete_finish<C>(ec, pd, gv, X, c_real, complete, LEAN ? !complete : !eligible, beta, cst, ef, kappa);
                     if (complete) eo = ef;
                     // the column sum multiplies the gene's slots by this: -kappa for s_j = (w_j r_j)^2

@@ -42,6 +42,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// The same with an L2 eviction-priority hint (evict_last): a shard that fits the 126 MB L2 is re-read by
+// every evaluation of the optimiser loop, and a cyclic sweep over a working set near the cache size
+// evicts each line just before its reuse unless the lines are marked to stay.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 // order this thread's generic-proxy shared-memory writes before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -60,6 +73,7 @@ struct TileSrc {
     const uint8_t* status;   // n_pad (bit0 eligible, bit1 control) -- always present
     int m;
     int genes;               // G, a multiple of 16
+    int l2_keep;             // 1: the y / aux tiles are fetched with the L2 evict_last hint (shard fits the L2)
     int row_stride;          // doubles between consecutive gene rows of y / aux INSIDE the stage: m (dense: the
                              // tile is one bulk copy) or m + 2 (padded rows, one bulk copy per gene row: with a
                              // stride of 2 mod 4 doubles the rows of 8 consecutive genes start in 8 distinct
@@ -109,6 +123,9 @@ __device__ __forceinline__ uint32_t tile_barrier_count(const TileSrc& src) { ret
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t dst_shared, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -122,26 +139,45 @@ __device__ __forceinline__ void tile_issue(const TileSrc& src, const TileLayout&
             if (src.cst) bulk_g2s(stage + L.cst_off, src.cst + g0, (uint32_t)src.genes * 8, bar);
             bulk_g2s(stage + L.status_off, src.status + g0, (uint32_t)src.genes, bar);
         }
+        // chunk i (16 bytes) of the tile: row i / cpr, position i % cpr; thread t takes t, t + T, ...  The
+        // shared-memory offset is carried along instead of being recomputed (one division per tile).
         const int cpr = src.m >> 1;                              // 16-byte chunks per row (m is even)
-        const int total = src.genes * cpr;
-        const uint32_t pitch = (uint32_t)src.row_stride * 8;
-        int row = (int)threadIdx.x / cpr, k = (int)threadIdx.x - row * cpr;
-        const int drow = (int)blockDim.x / cpr, dk = (int)blockDim.x - drow * cpr;
-        const char* gy = (const char*)(src.y + g0 * src.m);
-        const char* ga = src.aux ? (const char*)(src.aux + g0 * src.m) : nullptr;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const uint32_t at = (uint32_t)row * pitch + (uint32_t)k * 16u;
-            cp_async16(stage + at, gy + (size_t)i * 16);
-            if (ga) cp_async16(stage + L.aux_off + at, ga + (size_t)i * 16);
-            row += drow; k += dk;
-            if (k >= cpr) { k -= cpr; ++row; }
+        const int total = src.genes * cpr, T = (int)blockDim.x;
+        const uint32_t pitch = (uint32_t)src.row_stride * 8, gap = pitch - (uint32_t)cpr * 16u;
+        const int row0 = (int)threadIdx.x / cpr, drow = T / cpr, dk = T - drow * cpr;
+        int k = (int)threadIdx.x - row0 * cpr;
+        const uint32_t step = (uint32_t)drow * pitch + (uint32_t)dk * 16u;
+        uint32_t at = smem_u32(stage) + (uint32_t)row0 * pitch + (uint32_t)k * 16u;
+        const char* gy = (const char*)(src.y + g0 * src.m) + (size_t)threadIdx.x * 16;
+        const size_t gstep = (size_t)T * 16;
+        if (src.aux) {
+            const char* ga = (const char*)(src.aux + g0 * src.m) + (size_t)threadIdx.x * 16;
+            for (int i = threadIdx.x; i < total; i += T, gy += gstep, ga += gstep) {
+                cp_async16_s(at, gy);
+                cp_async16_s(at + L.aux_off, ga);
+                at += step; k += dk;
+                if (k >= cpr) { k -= cpr; at += gap; }
+            }
+        } else {
+#pragma unroll 4
+            for (int i = threadIdx.x; i < total; i += T, gy += gstep) {
+                cp_async16_s(at, gy);
+                at += step; k += dk;
+                if (k >= cpr) { k -= cpr; at += gap; }
+            }
         }
         cp_async_arrive(bar);
         return;
     }
     mbar_expect_tx(bar, L.tx_bytes);
-    bulk_g2s(stage, src.y + g0 * src.m, L.row_bytes, bar);
-    if (src.aux) bulk_g2s(stage + L.aux_off, src.aux + g0 * src.m, L.row_bytes, bar);
+    if (src.l2_keep) {
+        const uint64_t pol = l2_policy_evict_last();
+        bulk_g2s_hint(stage, src.y + g0 * src.m, L.row_bytes, bar, pol);
+        if (src.aux) bulk_g2s_hint(stage + L.aux_off, src.aux + g0 * src.m, L.row_bytes, bar, pol);
+    } else {
+        bulk_g2s(stage, src.y + g0 * src.m, L.row_bytes, bar);
+        if (src.aux) bulk_g2s(stage + L.aux_off, src.aux + g0 * src.m, L.row_bytes, bar);
+    }
     if (src.gs) bulk_g2s(stage + L.gs_off, src.gs + g0, (uint32_t)src.genes * 8, bar);
     if (src.cst) bulk_g2s(stage + L.cst_off, src.cst + g0, (uint32_t)src.genes * 8, bar);
     bulk_g2s(stage + L.status_off, src.status + g0, (uint32_t)src.genes, bar);
@@ -207,7 +243,10 @@ struct TileRing {
     int stages;
     bool wrap;
 
-    __device__ __forceinline__ long long tile_at(long long i) const { return first + (i % cnt) * step; }
+    __device__ __forceinline__ long long tile_at(long long i) const {      // i < 2 cnt except when cnt < stages
+        if (i >= cnt) { i -= cnt; if (i >= cnt) i %= cnt; }
+        return first + i * step;
+    }
 
     // all threads; barriers must have been initialised (mbar_init + fence) and published by a __syncthreads
     __device__ __forceinline__ void begin(unsigned char* smem, uint64_t* bars, const TileSrc& src, const TileLayout& L) {

@@ -42,7 +42,7 @@ int main() {
     int genes_opts[] = {32, 64, 128};
     for (int gi = 0; gi < 3; ++gi) for (int stages = 2; stages <= 4; ++stages) for (int ctas = 1; ctas <= 4; ++ctas) {
         const int genes = genes_opts[gi];
-        TileSrc src; src.y = y; src.aux = nullptr; src.gs = nullptr; src.cst = nullptr; src.status = status; src.m = m; src.genes = genes; src.row_stride = m;
+        TileSrc src; src.y = y; src.aux = nullptr; src.gs = nullptr; src.cst = nullptr; src.status = status; src.m = m; src.genes = genes; src.row_stride = m; src.l2_keep = 0;
         const size_t smem = tile_stage_bytes(genes, m, false, false, false) * stages;
         if (smem * ctas > 220000) continue;
         cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

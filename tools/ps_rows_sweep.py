@@ -1,7 +1,7 @@
 """Per-sample variance models: the thread-per-gene kernel on padded rows against the lanes-per-gene
 kernel (FN_NO_ROWS=1), over tile geometries.  Checks value and gradient agreement, prints kernel times.
 
-    python tools/ps_rows_sweep.py [n] [m] [c] [missing fraction]
+    python tools/ps_rows_sweep.py [n] [m] [c] [missing fraction] [controls]
 """
 import json
 import os
@@ -35,7 +35,12 @@ P = fam.theta_length()
 theta = np.concatenate([[8.0], 0.8 + 0.5 * np.random.default_rng(2).random(P - 1)])
 
 e = _native.Engine(0)
-e.upload_dev(n, m, y.data_ptr(), 0, fam, 0, design)
+if "controls" in sys.argv:                      # half of the genes are control genes with their own design (cfg4)
+    ctl = (torch.rand(n, device=dev, generator=gen) < 0.5).to(torch.uint8)
+    torch.cuda.synchronize()
+    e.upload_dev(n, m, y.data_ptr(), 0, fam, ctl.data_ptr(), design, np.delete(design, 1, axis=1))
+else:
+    e.upload_dev(n, m, y.data_ptr(), 0, fam, 0, design)
 e.set_timing(True)
 
 
