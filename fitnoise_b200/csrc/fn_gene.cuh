@@ -528,6 +528,37 @@ FN_HD void prepare_gene(const Family& fam, const GeneView& gv, const double* X, 
         if (patseq) return finite_d(y) && finite_d(aux);
         return finite_d(y) && aux != 0.0 && aux == aux;
     };
+    // Unweighted, not PAT-Seq (the streaming case): ONE unrolled sweep gives the row sum and the squared
+    // deviations about a shift taken from the row itself (its first value: a point of the sample, so
+    // s2 - s1^2/m loses no more digits than the two-pass form has to spare); a non-finite value anywhere
+    // makes s2 non-finite, and only such rows take the general two sweeps below.
+    bool fast = false;
+    double fast_sum = 0.0, fast_ss = 0.0;
+    if (!gv.aux && !patseq) {
+        const double y0 = gv.y[0];
+        const double shift = finite_d(y0) ? y0 : 0.0;
+        double s12[2] = {0.0, 0.0};
+        gv.for_each_hot(true, [&](int j) {
+            const double d = gv.y[j] - shift;
+            s12[0] += d;
+            s12[1] = fma(d, d, s12[1]);
+        });
+        lane_sum_n<2>(s12, gv.lpg);
+        fast = finite_d(s12[1]);
+        fast_sum = fma((double)gv.m, shift, s12[0]);
+        fast_ss = s12[1] - s12[0] * s12[0] / (double)gv.m;
+        if (fast_ss < 0.0) fast_ss = 0.0;
+    }
+    if (!warp_any(!fast)) {                      // every gene of this warp is complete
+        out.k = gv.m;
+        out.eligible = gv.m > c_real;
+        out.cst = 0.0;
+        out.average = (gv.m > c_real) ? fast_sum / gv.m : NAN;
+        out.ysum = fast_sum; out.yss = fast_ss; out.nfinite = gv.m;
+        out.bad_counts = 0;
+        out.avg_tail = 0.0;
+        return;
+    }
     gv.for_each(true, [&](int j) {
         const double y = gv.y[j];
         const bool yok = finite_d(y);

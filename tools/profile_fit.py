@@ -15,6 +15,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fitnoise_b200 as fitnoise  # noqa: E402
 from helpers import synthetic  # noqa: E402
 
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+if world > 1:                                      # under torchrun: genes sharded over the ranks by the session
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+
 config = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 s = synthetic(config)
 model = sys.argv[2] if len(sys.argv) > 2 else s["model"]
@@ -38,9 +46,13 @@ run()
 for _ in range(3):
     t0 = time.perf_counter()
     run()
-    print("warm fit+test: %.2f ms" % ((time.perf_counter() - t0) * 1000))
+    if rank == 0:
+        print("warm fit+test: %.2f ms" % ((time.perf_counter() - t0) * 1000))
 pr = cProfile.Profile()
 pr.enable()
 run()
 pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+if rank == 0:
+    pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+if world > 1:
+    dist.destroy_process_group()
