@@ -67,7 +67,9 @@ class Session(object):
         # exchanges, gathers and rendezvous of a sharded fit cost more than the work they spread (3.1 ms on
         # 8 GPUs against 1.8 ms on one).  Below the threshold every rank fits ALL genes on its own GPU --
         # same kernels, same order of summation, identical results on every rank, no collective.
-        if self.world > 1 and engine_factory is None and y.nbytes < _shard_min_bytes():
+        # (with a stand-in evaluator -- the CPU tests -- only when the threshold is set explicitly)
+        if (self.world > 1 and (engine_factory is None or "FN_SHARD_MIN_MB" in os.environ)
+                and y.nbytes < _shard_min_bytes()):
             self.rank, self.world = 0, 1
         self.bounds = parallel.shard_bounds(self.n, self.world)
         self.lo, self.hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
@@ -265,6 +267,8 @@ class Session(object):
         return (self._gather(_native.RES_SCORE), self._gather(_native.RES_D2), self._gather(_native.RES_PDF))
 
     def noise_stats(self, theta):
+        if self.world == 1:                          # one GPU, or a small problem every rank fits whole
+            return self.local.noise_stats(theta)
         if not self._device_gather:
             noise_p, averages = self.local.noise_stats(theta)
             return parallel.allgather_rows(noise_p, self.n), parallel.allgather_rows(averages, self.n)
@@ -348,6 +352,8 @@ class Session(object):
         return self.local.bh(p)
 
     def weights(self, theta):
+        if self.world == 1:
+            return self.local.weights(theta)
         return parallel.allgather_rows(self.local.weights(theta), self.n)
 
 

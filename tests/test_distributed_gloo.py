@@ -86,6 +86,36 @@ def test_two_ranks_match_one(tmp_path):
         assert ranks[0][key]["description"] == ranks[1][key]["description"]
 
 
+def _replicated_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["FN_SHARD_MIN_MB"] = "64"               # every case is "small": fitted whole by every rank
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        results = {"t_twogroup:fit": _run_case("t_twogroup", False), "independent_weights:forced": _run_case("independent_weights", True)}
+        np.save(os.path.join(out_dir, "rep%d.npy" % rank), results, allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_small_problems_are_replicated_not_sharded(tmp_path):
+    """Below FN_SHARD_MIN_MB every rank fits all genes itself (session.py): same numbers as one
+    process, bit for bit, and no collective is entered (a hang here would be one)."""
+    single = {"t_twogroup:fit": _run_case("t_twogroup", False), "independent_weights:forced": _run_case("independent_weights", True)}
+    port = _free_port()
+    mp.spawn(_replicated_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), "rep%d.npy" % r), allow_pickle=True).item()
+        for key, one in single.items():
+            two = got[key]
+            assert two["shard"] == (0, len(one["noise_p"]), 1)
+            assert two["value"] == one["value"] and np.array_equal(two["x"], one["x"])
+            for field in ("noise_p", "averages", "coef", "covar", "p", "q", "weights", "grad"):
+                assert np.array_equal(two[field], one[field], equal_nan=True), "%s %s" % (key, field)
+
+
 def _tiny_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -88,10 +88,18 @@ for config, n in cases:
         a, b = np.asarray(got[key]), np.asarray(forced[config][key])
         if key == "order":
             return np.array_equal(a, b)
+        if key in ("coef", "contrasts", "covar"):
+            # coefficients near zero have no relative accuracy to speak of: the bar of the parity tests
+            # (1e-9 relative, 1e-10 absolute) on the scale of the array
+            scale = float(np.nanmax(np.abs(b))) if b.size else 1.0
+            return a.shape == b.shape and np.allclose(a, b, rtol=1e-9, atol=1e-10 * max(scale, 1e-300), equal_nan=True)
         return a.shape == b.shape and np.allclose(a, b, rtol=1e-11, atol=0.0, equal_nan=True)
-    bad = [k for k in got if not same(k)]
+    def worst(key):
+        a, b = np.asarray(got[key], dtype=float), np.asarray(forced[config][key], dtype=float)
+        return float(np.nanmax(np.abs(a - b))) if a.shape == b.shape and a.size else float("nan")
+    bad = ["%s (max abs diff %.2e)" % (k, worst(k)) for k in got if not same(k)]
     ok &= not bad
-    print("rank %d config %s forced theta: %s" % (rank, config, "all per-gene results equal to one GPU (1e-11), top-table order identical" if not bad
+    print("rank %d config %s forced theta: %s" % (rank, config, "all per-gene results equal to one GPU (1e-11; coefficients 1e-9 / 1e-10 of their scale), top-table order identical" if not bad
                                                    else "DIFFER: %s" % bad), flush=True)
     f._session.close()
     f2._session.close()
