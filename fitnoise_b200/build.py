@@ -29,7 +29,7 @@ LINK_FLAGS = ["-shared", "--cudart", "static", "-gencode", "arch=compute_100a,co
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h")))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h", ".c")))
 
 
 HEADER = os.path.join(os.path.dirname(HERE), "include", "fitnoise_b200.h")
@@ -60,6 +60,29 @@ def needs_build():
     return not os.path.exists(LIB_PATH) or built_hash() != source_hash()
 
 
+def pycall_path():
+    """The optional CPython entry for fn_nll_grad (csrc/fn_pycall.c), built for the running interpreter."""
+    import sysconfig
+    return os.path.join(LIB_DIR, "_fn_pycall" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pycall():
+    """gcc build of csrc/fn_pycall.c; returns its path or None (no compiler / no Python.h: the ctypes
+    path is used instead -- this module only marshals arguments, it computes nothing)."""
+    import sysconfig
+    include = sysconfig.get_paths().get("include")
+    if not include or not os.path.exists(os.path.join(include, "Python.h")):
+        return None
+    out = pycall_path()
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", include,
+           os.path.join(CSRC, "fn_pycall.c"), "-o", out]
+    try:
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+    except OSError:
+        return None
+    return out if proc.returncode == 0 else None
+
+
 def build(force=False, verbose=False):
     """Compile csrc/fn_api.cu (which includes every kernel header) into _lib/libfitnoise_b200.so."""
     if not force and not needs_build():
@@ -86,6 +109,7 @@ def build(force=False, verbose=False):
     objs = [c[-1] for c in jobs]
     log = run([nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + objs)
     shutil.rmtree(OBJ_DIR, ignore_errors=True)     # only the .so travels to the GPU box
+    build_pycall()
     with open(HASH_PATH, "w") as f:
         f.write(digest + "\n")
     if verbose:
