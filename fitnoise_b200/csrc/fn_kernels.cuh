@@ -258,25 +258,32 @@ __device__ __forceinline__ void grid_reduce(const GridReduce& gr, const StepVars
     }
     if (!exchange) return;
 
-    // every component: wait for all senders' slots of this evaluation in my own mailbox, add in rank
+    // Every component: wait for all senders' slots of this evaluation in my own mailbox, add in rank
     // order.  A peer that never shows up turns EVERY total into NaN, which the host reports as an error.
-    for (int i = threadIdx.x; i < nacc; i += T) {
-        double s = 0.0;
-        bool failed = false;
-        const unsigned long long t0 = global_ns();
-        for (int r = 0; r < pc.world; ++r) {
-            const Slot* slot = &pc.mailbox[pc.rank][((size_t)parity * pc.world + r) * pc.slot_count + i];
+    // Thread (component, sender) polls ONE slot, so all slots are waited for at the same time (the
+    // earlier form had one thread per component walk the senders one L2 round trip after the other);
+    // the values meet in shared memory (256 / world components per round).
+    const int W = pc.world, per = 256 / W;
+    for (int c0 = 0; c0 < nacc; c0 += per) {
+        const int cnt = (nacc - c0 < per) ? nacc - c0 : per;
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * W; e += T) {
+            const int k = e / W, r = e - k * W;
+            const Slot* slot = &pc.mailbox[pc.rank][((size_t)parity * W + r) * pc.slot_count + c0 + k];
+            const unsigned long long t0 = global_ns();
             double got;
             while (!slot_try_load(slot, sv.comm_seq, got)) {
-                if (global_ns() - t0 > pc.timeout_ns) { failed = true; break; }
-                __nanosleep(40);
+                if (global_ns() - t0 > pc.timeout_ns) { got = NAN; break; }
             }
-            if (failed) break;
-            s += got;
+            gsum[e] = got;
         }
-        if (failed) s = NAN;
-        gr.out_dev[i] = s;
-        if (gr.out_host) slot_store(&gr.out_host[i], s, sv.host_seq);
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt; k += T) {
+            double s = 0.0;
+            for (int r = 0; r < W; ++r) s += gsum[k * W + r];          // rank order: the same total on every rank
+            gr.out_dev[c0 + k] = s;
+            if (gr.out_host) slot_store(&gr.out_host[c0 + k], s, sv.host_seq);
+        }
     }
 }
 
