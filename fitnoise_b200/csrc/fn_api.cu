@@ -14,6 +14,7 @@
 #include <thread>
 #include <tuple>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>      // header-only; a no-op unless a profiler attaches
 
 #include "../../include/fitnoise_b200.h"
 #include "fn_bh.cuh"
@@ -70,6 +71,16 @@ static const KernelSet* kernel_set(int width) {
         default: return nullptr;
     }
 }
+
+// NVTX range over one C-ABI call (K1 = fn_upload, K2 = fn_nll_grad / fn_noise_stats, K3 = fn_coef,
+// K3b / K4 = fn_test*, fn_bh*): shows up as a named span in nsys / ncu timelines, costs a few ns otherwise.
+// The per-evaluation call is only marked when FN_NVTX=1 (it runs every 10-25 us).
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name, bool enabled = true) : on(enabled) { if (on) nvtxRangePushA(name); }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
+static const bool g_nvtx_hot = getenv("FN_NVTX") != nullptr;
 
 static thread_local std::string g_error;
 
@@ -720,6 +731,7 @@ static int upload_common(fn_handle* h, int64_t n, int32_t m, const double* y, co
                          const fn_family* family, const uint8_t* controls, int32_t c_noise,
                          const double* design_noise, int32_t c_ctrl, const double* design_ctrl,
                          fn_prep_info* info, cudaMemcpyKind kind) {
+    NvtxRange nvtx_range("fitnoise:K1 upload+prepare");
     if (!h) return fail(FN_ERR_ARG, "NULL handle");
     LEAVE_RESIDENT(h);
     // n == 0 is allowed: an empty shard (fewer genes than GPUs) still takes part in every exchange
@@ -1283,6 +1295,7 @@ static int launch_eval_factors(fn_handle* h, const ThetaState& ts, bool per_gene
 
 extern "C" int fn_nll_grad_factors(fn_handle* h, const double* theta, int32_t P, const double* factors,
                                    double* value, double* grad, double* grad_factors, int64_t* n_used, int64_t* n_bad) {
+    NvtxRange nvtx_range("fitnoise:K2f nll_grad_factors", g_nvtx_hot);
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts, false);
     if (rc) return rc;
@@ -1331,6 +1344,7 @@ static void assemble(const fn_handle* h, const double* acc, const double* ta, do
 
 extern "C" int fn_nll_grad(fn_handle* h, const double* theta, int32_t P, double* value, double* grad,
                            int64_t* n_used, int64_t* n_bad) {
+    NvtxRange nvtx_range("fitnoise:K2 nll_grad", g_nvtx_hot);
     FN_HOST_STAMP(0);
     ThetaState ts;
     int rc = stage_theta(h, theta, P, ts, !h->resident && (table_a(h) || table_b(h)));
@@ -1420,6 +1434,7 @@ extern "C" int fn_nll_grad_dev(fn_handle* h, const double* theta, int32_t P, dou
 }
 
 extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double* score, double* d2, int32_t* p) {
+    NvtxRange nvtx_range("fitnoise:K2 per_gene");
     ThetaState ts;
     int rc = leave_resident(h);
     if (rc) return rc;
@@ -1435,6 +1450,7 @@ extern "C" int fn_per_gene(fn_handle* h, const double* theta, int32_t P, double*
 }
 
 extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, double* noise_p, double* averages) {
+    NvtxRange nvtx_range("fitnoise:K2 noise_stats");
     ThetaState ts;
     int rc = leave_resident(h);
     if (rc) return rc;
@@ -1463,6 +1479,7 @@ extern "C" int fn_noise_stats(fn_handle* h, const double* theta, int32_t P, doub
 // ------------------------------------------------------------------------------------------
 extern "C" int fn_coef(fn_handle* h, const double* theta, int32_t P, int32_t c, const double* design,
                        double* coef, double* covar, double* dfpost) {
+    NvtxRange nvtx_range("fitnoise:K3 coef");
     ThetaState ts;
     int rc = leave_resident(h);
     if (rc) return rc;
@@ -1526,6 +1543,7 @@ static size_t bh_work_bytes(int64_t n);
 
 static int test_core(fn_handle* h, int32_t kc, const double* contrasts, double* contrasted, double* ccov,
                      double* pval, double* qval, uint32_t* order) {
+    NvtxRange nvtx_range("fitnoise:K3b test");
     if (!h || !h->loaded || h->coef_c == 0) return fail(FN_ERR_STATE, "fn_test needs a preceding fn_coef");
     LEAVE_RESIDENT(h);
     const int c = h->coef_c;
@@ -1602,6 +1620,7 @@ extern "C" int fn_coef_fetch(fn_handle* h, double* coef, double* covar, double* 
 }
 
 extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* weights) {
+    NvtxRange nvtx_range("fitnoise:weights");
     ThetaState ts;
     int rc = leave_resident(h);
     if (rc) return rc;
@@ -1664,6 +1683,7 @@ static void bh_enqueue(fn_handle* h, int64_t n, const double* p_dev, double* q_d
 // p-values -- so it is captured once into a CUDA graph per (n, buffers) and replayed with a single
 // cudaGraphLaunch afterwards.  Any failure of the capture machinery falls back to plain launches.
 static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev) {
+    NvtxRange nvtx_range("fitnoise:K4 bh");
     const bool use_graph = getenv("FN_NO_GRAPH") == nullptr;
     if (use_graph && h->bh_exec && h->bh_n == n && h->bh_p == p_dev && h->bh_q == q_dev && h->bh_work == work) {
         if (cudaGraphLaunch(h->bh_exec, h->stream) == cudaSuccess) {
