@@ -194,3 +194,28 @@ def test_staged_upload_of_two_large_pageable_arrays():
         e.close()
     # (the two uploads use different tile geometries, so the sums associate differently)
     assert_close(big[rows], small, 1e-12, what="per-gene score after two staged uploads")
+
+
+@pytest.mark.parametrize("model", ["Model_t", "Model_t_per_sample", "Model_t_patseq"])
+def test_cpython_fast_call_equals_ctypes(model):
+    """fn_nll_grad through the thin CPython entry (csrc/fn_pycall.c, taken for float64 ndarrays) and
+    through ctypes (taken for anything else, e.g. a list) is the same C-ABI call: identical bits."""
+    if _native._pycall() is None:
+        pytest.skip("the optional _fn_pycall module was not built")
+    y, aux, fam, design, theta = _case(model, n=1500)
+    e = _native.Engine(0)
+    try:
+        e.upload(y, aux, fam, None, design)
+        for resident in (False, True):
+            if resident:
+                e.resident_begin()
+            fast = e.nll_grad(np.ascontiguousarray(theta, dtype=np.float64))
+            slow = e.nll_grad([float(t) for t in theta])
+            if resident:
+                e.resident_end()
+            assert fast[0] == slow[0] and np.array_equal(fast[1], slow[1]) and fast[2:] == slow[2:]
+            assert isinstance(fast[1], np.ndarray) and fast[1].shape == (len(theta),)
+        with pytest.raises(_native.NativeError):
+            e.nll_grad(np.zeros(len(theta) + 1))                # wrong length: the library's own error, raised
+    finally:
+        e.close()
