@@ -1245,6 +1245,8 @@ static int check_totals(fn_handle* h, const double* acc) {
     if (h->comm_world > 1 && acc[ACC_USED] != acc[ACC_USED])
         return fail(FN_ERR_COMM, "multi-GPU exchange failed: a peer rank did not deliver its sums in time "
                                  "(rank %d of %d); the ranks must call fn_nll_grad the same number of times", h->comm_rank, h->comm_world);
+    if (acc[ACC_USED] != acc[ACC_USED])      // the grid reducer gave up on a CTA's partial sums (NaN counts are never cast to integers)
+        return fail(FN_ERR_CUDA, "evaluation failed: the partial sums of a thread block never arrived");
     return 0;
 }
 
