@@ -23,6 +23,8 @@ from oracle import fitnoise_oracle as oracle  # noqa: E402
 MODELS = ["Model_t", "Model_normal", "Model_independent", "Model_t_per_sample", "Model_normal_per_sample",
           "Model_t_patseq", "Model_t_patseq_v1", "Model_normal_patseq_v3", "Model_t_patseq_per_sample",
           "Model_t_patseq_v1_per_sample"]
+if os.environ.get("FUZZ_MODELS"):                      # e.g. FUZZ_MODELS=Model_t_per_sample,Model_normal_per_sample
+    MODELS = os.environ["FUZZ_MODELS"].split(",")
 
 
 def random_case(rng):
