@@ -86,6 +86,8 @@ def build_pycall():
 def build(force=False, verbose=False):
     """Compile csrc/fn_api.cu (which includes every kernel header) into _lib/libfitnoise_b200.so."""
     if not force and not needs_build():
+        if not os.path.exists(pycall_path()):
+            build_pycall()
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ_DIR, exist_ok=True)

@@ -623,3 +623,40 @@ def test_integration_stub_from_the_docs():
     assert info.n_eligible == info2.n_eligible == n and used == n
     assert value == v2 and np.array_equal(grad, g2)
     ns["_check"](ns["_lib"].fn_destroy(h.h))
+
+
+def test_p_values_from_1_down_to_the_far_tails_against_host_build():
+    """The device evaluates the F / chi-square continued fractions with a Newton-refined reciprocal
+    (fn_special.cuh cf_rcp) where the host build divides: p-values from ~1 down to 1e-30 (t) and 1e-300 (normal; effects of
+    0 ... 150 standard deviations), t and normal models, one and two contrasts, must agree to 1e-10."""
+    import hostcheck
+    rng = np.random.default_rng(77)
+    n, m = 4000, 12
+    group = (np.arange(m) >= m // 2) * 1.0
+    batch = (np.arange(m) % 2) * 1.0
+    design = np.stack([np.ones(m), group, batch], axis=1)
+    y = rng.normal(size=(n, m))
+    y += np.linspace(0.0, 150.0, n)[:, None] * group[None, :]
+    y += rng.normal(size=(n, 1)) * batch[None, :]
+    for model, theta in (("Model_t", [6.5, 1.1]), ("Model_normal", [0.9]), ("Model_independent", [])):
+        fam = getattr(fitnoise, model)()._family(m)
+        theta = np.asarray(theta, dtype=float)
+        host = hostcheck.HostEvaluator()
+        host.upload(y, None, fam, None, design)
+        e = _native.Engine(0)
+        try:
+            e.upload(y, None, fam, None, design)
+            hn, _ = host.noise_stats(theta)
+            gn, _ = e.noise_stats(theta)
+            assert_close(gn, hn, 1e-10, what=model + " noise p")
+            host.coef(theta, design)
+            e.coef(theta, design)
+            for contrasts in (np.array([[0.0], [1.0], [0.0]]), np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])):
+                _, _, hp = host.test(contrasts)
+                _, gp, _ = e.test_bh(contrasts)
+                assert np.nanmin(hp) < 1e-15 and np.nanmax(hp) > 0.5, (np.nanmin(hp), np.nanmax(hp))   # t tails are heavy; the normal models reach 1e-300
+                positive = hp > 0
+                assert_close(gp[positive], hp[positive], 1e-10, what="%s p, %d contrast(s)" % (model, contrasts.shape[1]))
+                assert np.all(gp[~positive] < 1e-300)
+        finally:
+            e.close()
