@@ -1440,7 +1440,8 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
     // accumulation of A, no factorisation, no inverse.  A missing value makes y'y non-finite, which is
     // how the other genes are found (as in scale1_sweep); they take the general route below.
     const bool unit = ec.kind == KIND_SCALE1 && gv.aux == nullptr && nf == 0;
-    bool done = false;
+    bool done = false, unit_d2_ok = false;
+    double unit_d2 = 0.0;
     int k = 0;
     if (unit) {
         double b[C], yy = 0.0;
@@ -1459,6 +1460,11 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
         done = finite_d(yy);
         if (done) {
             k = gv.m;
+            // d2 = y'y - |b|^2 as in scale1_sweep; redone from residuals below when it cancels
+            unit_d2 = yy;
+#pragma unroll
+            for (int i = 0; i < C; ++i) if (i < c_real) unit_d2 -= b[i] * b[i];
+            unit_d2_ok = unit_d2 >= 1e-4 * yy;
 #pragma unroll
             for (int i = 0; i < C; ++i) beta[i] = (i < c_real) ? b[i] : 0.0;
 #pragma unroll
@@ -1514,18 +1520,24 @@ FN_HD void coef_gene(const EvalConst& ec, const GeneView& gv, const double* X, i
             chol_inverse<C>(nm.a, ainv);
         }
     }
+    // residual sum of squares: a sweep of its own, except for complete unweighted genes whose d2 came
+    // out of the first sweep without cancellation (every gene of a data set without missing values)
     double d2 = 0.0;
-    gv.for_each(true, [&](int j) {
-        const double y = gv.y[j];
-        const SampleVar sv = sample_var(ec, gv, j, y);
-        double x[C];
-        load_x<C>(X, j, x);
-        double r = sv.valid ? y : 0.0;
+    const bool from_sums = done && unit_d2_ok;
+    if (warp_any(!from_sums)) {
+        gv.for_each(!from_sums, [&](int j) {
+            const double y = gv.y[j];
+            const SampleVar sv = sample_var(ec, gv, j, y);
+            double x[C];
+            load_x<C>(X, j, x);
+            double r = sv.valid ? y : 0.0;
 #pragma unroll
-        for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
-        d2 += sv.w * wscale * r * r;
-    });
-    d2 = lane_sum(d2, gv.lpg);
+            for (int t = 0; t < C; ++t) r -= x[t] * beta[t];
+            d2 += sv.w * wscale * r * r;
+        });
+        d2 = lane_sum(d2, gv.lpg);
+    }
+    if (from_sums) d2 = unit_d2;
 #pragma unroll
     for (int i = 0; i < C; ++i) if (i >= c_real && i < c_real + nf) d2 += beta[i] * beta[i];   // + u'u
     if (ec.kind == KIND_SCALE1 && nf == 0) {  // sums were taken at theta = 1
