@@ -1650,7 +1650,15 @@ extern "C" int fn_weights(fn_handle* h, const double* theta, int32_t P, double* 
 // ------------------------------------------------------------------------------------------
 // Benjamini-Hochberg
 // ------------------------------------------------------------------------------------------
-// Enqueue the 44 kernels of one Benjamini-Hochberg adjustment on the handle's stream.
+// Enqueue the kernels of one Benjamini-Hochberg adjustment on the handle's stream (15 launches in the
+// one-sweep form, 44 in the five-kernels-per-digit form).
+// number of kernel launches / graph nodes of one adjustment (what h->launches counts)
+static bool bh_onesweep(int64_t n) {
+    if (getenv("FN_BH_CLASSIC")) return false;
+    return n <= BH_ONESWEEP_MAX || getenv("FN_BH_ONESWEEP") != nullptr;
+}
+static int bh_launch_count(int64_t n) { return bh_onesweep(n) ? 15 : 44; }
+
 static void bh_enqueue(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev) {
     const int nblocks = (int)((n + BH_CHUNK - 1) / BH_CHUNK);
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -1662,6 +1670,30 @@ static void bh_enqueue(fn_handle* h, int64_t n, const double* p_dev, double* q_d
     double* chunk_min = (double*)work; work += up((size_t)nblocks * 8);
     double* carry = (double*)work; work += up((size_t)nblocks * 8);
     uint32_t* seg = (uint32_t*)work;
+    if (bh_onesweep(n)) {
+        // one-sweep sort (fn_bh.cuh): [digit counts 8 x 256][tickets 8 (padded)][state words 8 x tiles x 256], zeroed together
+        const size_t nseg_bytes = up((((size_t)256 * nblocks + BH_SEG - 1) / BH_SEG) * 4);
+        char* zone = (char*)seg + nseg_bytes;
+        uint32_t* hist_all = (uint32_t*)zone;
+        unsigned int* tickets = (unsigned int*)(zone + 8 * 256 * 4);
+        unsigned long long* state = (unsigned long long*)(zone + 8 * 256 * 4 + 256);
+        const size_t state_words = (size_t)nblocks * 256;
+        cudaMemsetAsync(zone, 0, 8 * 256 * 4 + 256 + 8 * state_words * 8, h->stream);
+        bh_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, p_dev, keys0, idx0);
+        bh_hist_all_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, hist_all);
+        bh_bases_kernel<<<8, 256, 0, h->stream>>>(hist_all);
+        for (int pass = 0; pass < 8; ++pass) {
+            bh_onesweep_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, keys1, idx1, 8 * pass, hist_all + 256 * pass,
+                                                                      state + (size_t)pass * state_words, tickets + pass);
+            std::swap(keys0, keys1);
+            std::swap(idx0, idx1);
+        }
+        bh_chunkmin_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, chunk_min);
+        bh_carry_scan_kernel<<<1, 1024, 0, h->stream>>>(nblocks, chunk_min, carry);
+        bh_finish_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, carry, q_dev);
+        if (order_dev) *order_dev = idx0;
+        return;
+    }
     const long long hist_total = (long long)256 * nblocks;
     const int nseg = (int)((hist_total + BH_SEG - 1) / BH_SEG);
     bh_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, p_dev, keys0, idx0);
@@ -1681,7 +1713,7 @@ static void bh_enqueue(fn_handle* h, int64_t n, const double* p_dev, double* q_d
     if (order_dev) *order_dev = idx0;          // genes by ascending p (stable, NaN last)
 }
 
-// The adjustment is a fixed sequence of 44 small launches -- launch-bound at the usual 10^4..10^6
+// The adjustment is a fixed sequence of 15 or 44 small launches -- launch-bound at the usual 10^4..10^6
 // p-values -- so it is captured once into a CUDA graph per (n, buffers) and replayed with a single
 // cudaGraphLaunch afterwards.  Any failure of the capture machinery falls back to plain launches.
 static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, char* work, uint32_t** order_dev) {
@@ -1689,7 +1721,7 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
     const bool use_graph = getenv("FN_NO_GRAPH") == nullptr;
     if (use_graph && h->bh_exec && h->bh_n == n && h->bh_p == p_dev && h->bh_q == q_dev && h->bh_work == work) {
         if (cudaGraphLaunch(h->bh_exec, h->stream) == cudaSuccess) {
-            h->launches += 44;
+            h->launches += bh_launch_count(n);
             if (order_dev) *order_dev = h->bh_order;
             return 0;
         }
@@ -1705,7 +1737,7 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
             cudaGraphDestroy(graph);
             h->bh_n = n; h->bh_p = p_dev; h->bh_q = q_dev; h->bh_work = work; h->bh_order = order;
             if (cudaGraphLaunch(h->bh_exec, h->stream) == cudaSuccess) {
-                h->launches += 44;
+                h->launches += bh_launch_count(n);
                 if (order_dev) *order_dev = order;
                 return 0;
             }
@@ -1717,7 +1749,7 @@ static int bh_run(fn_handle* h, int64_t n, const double* p_dev, double* q_dev, c
         cudaGetLastError();
     }
     bh_enqueue(h, n, p_dev, q_dev, work, order_dev);
-    h->launches += 44;
+    h->launches += bh_launch_count(n);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1726,7 +1758,9 @@ static size_t bh_work_bytes(int64_t n) {
     const size_t nblocks = (n + BH_CHUNK - 1) / BH_CHUNK;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t nseg = (256 * nblocks + BH_SEG - 1) / BH_SEG;
-    return 2 * up(n * 8) + 2 * up(n * 4) + up(256 * nblocks * 4) + 2 * up(nblocks * 8) + up(nseg * 4);
+    // + the one-sweep zone: digit counts, tickets, 8 x tiles x 256 state words
+    return 2 * up(n * 8) + 2 * up(n * 4) + up(256 * nblocks * 4) + 2 * up(nblocks * 8) + up(nseg * 4) +
+           (bh_onesweep(n) ? up(8 * 256 * 4 + 256 + 8 * nblocks * 256 * 8) : 0);
 }
 
 extern "C" int fn_bh_dev(fn_handle* h, int64_t n, const double* p_dev, double* q_dev) {
