@@ -26,7 +26,7 @@ for config in configs:
     kw = {k: s[k] for k in ("controls", "control_design") if k in s}
     data = fitnoise.Dataset(s["y"], s["context"])
     for name in models[config]:
-        for rep in range(2):                     # second repetition: warm (context, allocator, clocks)
+        for rep in range(4):                     # rep 0: cold (context, allocator, graph capture); reps 2-3: steady state
             t0 = time.perf_counter()
             fitted = getattr(fitnoise, name)().fit(data, s["design"], **kw)
             t1 = time.perf_counter()
