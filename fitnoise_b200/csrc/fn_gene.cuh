@@ -1046,8 +1046,12 @@ FN_HD void store_pair(double* p, double a, double b) {
 // addresses a multiple of 128 bytes apart (the same banks: a two-way conflict on every table read).
 template <int C>
 FN_HD void load_x2(const double* X, int j, double* x) {
+    const double* row = X + j * (2 * C);
+#ifdef __CUDA_ARCH__
+    if (C % 2 == 0) row = (const double*)__builtin_assume_aligned(row, 16);    // table base and both halves of a row are 16-byte aligned
+#endif
 #pragma unroll
-    for (int i = 0; i < C; ++i) x[i] = X[j * (2 * C) + i];
+    for (int i = 0; i < C; ++i) x[i] = row[i];
 }
 
 // beta = sum_j hx_j y_j; false when the row holds a non-finite y (m even)

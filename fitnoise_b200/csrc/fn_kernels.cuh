@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(256, ((C <= 4 || (LEAN && C <= 8)) ? 2 : 1)) e
     // hxn / hxc area (2 m C doubles), x2 is a second copy of the designs
     const bool rows_tables = fastps && p.g.rows != 0;
     double* x2 = kap + 256;
+    x2 += (smem_u32(x2) >> 3) & 1u;           // 16-byte aligned (LDS.128 rows); the carve-up has the slack
     const int hx_stride = rows_tables ? 2 * C : XS;
     double* hxc_at = rows_tables ? hxn + C : hxc;
     __shared__ int ps_count[2];

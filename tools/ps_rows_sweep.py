@@ -1,7 +1,9 @@
 """Per-sample variance models: the thread-per-gene kernel on padded rows against the lanes-per-gene
 kernel (FN_NO_ROWS=1), over tile geometries.  Checks value and gradient agreement, prints kernel times.
 
-    python tools/ps_rows_sweep.py [n] [m] [c] [missing fraction] [controls]
+    python tools/ps_rows_sweep.py [n] [m] [c] [missing fraction] [controls] [model=Model_t]
+
+(model=Model_t / Model_normal: the unweighted SCALE1 models, whose wide designs (c >= 4) take the same layout)
 """
 import json
 import os
@@ -30,9 +32,11 @@ design = np.array([[1.0, 0.0]] * (m // 2) + [[1.0, 1.0]] * (m - m // 2))
 if c > 2:
     design = np.column_stack([design, np.random.default_rng(1).normal(size=(m, c - 2))])
 design = design[:, :c]
-fam = fitnoise.Model_t_per_sample()._family(m)
+model = ([a.split("=", 1)[1] for a in sys.argv if a.startswith("model=")] or ["Model_t_per_sample"])[0]
+fam = getattr(fitnoise, model)()._family(m)
 P = fam.theta_length()
-theta = np.concatenate([[8.0], 0.8 + 0.5 * np.random.default_rng(2).random(P - 1)])
+head = [8.0] if fam.dist == _native.DIST_T else []
+theta = np.concatenate([head, 0.8 + 0.5 * np.random.default_rng(2).random(P - len(head))])
 
 e = _native.Engine(0)
 if "controls" in sys.argv:                      # half of the genes are control genes with their own design (cfg4)
