@@ -183,3 +183,40 @@ def test_results_are_released_without_the_cycle_collector():
         assert [r() is not None for r in refs] == [False] * len(refs)
     finally:
         gc.enable()
+
+
+def test_cpython_fast_call_marshals_like_the_abi():
+    """csrc/fn_pycall.c (the optional thin entry for fn_nll_grad) against a stand-in with the ABI's
+    signature: theta and P go in, value / gradient / counts come out, the return code is passed on,
+    and anything but contiguous float64 buffers is refused.  No GPU involved."""
+    import ctypes
+    from fitnoise_b200 import _native, build
+    if build.build_pycall() is None:
+        pytest.skip("no Python.h / C compiler here: the ctypes path is used instead")
+    fast = _native._pycall()
+    if fast is None:
+        pytest.skip("FN_NO_PYCALL is set")
+    c_double_p = ctypes.POINTER(ctypes.c_double)
+    proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p,
+                             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64))
+    seen = {}
+
+    def stand_in(handle, theta, P, value, grad, used, bad):
+        seen.update(handle=handle, P=P, theta=[theta[i] for i in range(P)])
+        value[0] = sum(seen["theta"])
+        for i in range(P):
+            grad[i] = 10.0 * theta[i]
+        used[0], bad[0] = 2**40 + 7, 3
+        return -5 if P == 1 else 0
+
+    callback = proto(stand_in)
+    address = ctypes.cast(callback, ctypes.c_void_p).value
+    theta, grad = np.array([1.5, 2.5, 4.0]), np.empty(3)
+    assert fast(address, 0xABCDEF, theta, grad) == (0, 8.0, 2**40 + 7, 3)
+    assert seen == dict(handle=0xABCDEF, P=3, theta=[1.5, 2.5, 4.0]) and np.array_equal(grad, [15.0, 25.0, 40.0])
+    assert fast(address, 1, np.array([2.0]), np.empty(1))[0] == -5                  # the library's error code comes through
+    assert fast(address, 1, np.zeros(0), np.empty(0))[:2] == (0, 0.0)               # P = 0 (Model_independent)
+    for bad_theta, bad_grad in ((np.array([1, 2]), np.empty(2)), (np.ones(4)[::2], np.empty(2)),
+                                (np.ones(3), np.empty(2)), (np.ones(2), np.empty(2, dtype=np.float32))):
+        with pytest.raises((TypeError, BufferError, ValueError)):
+            fast(address, 1, bad_theta, bad_grad)
