@@ -140,6 +140,7 @@ class Model(Withable):
             "only through its CUDA kernels and has no per-gene Python fallback" % type(self).__name__)
 
     _aux_key = None                     # which Dataset.context entry is the second n x m array
+    _has_model_cost = False             # True for plug-ins with a _model_cost / factor vectors (_split_theta, _cost_grad)
 
     # theta as the optimiser sees it <-> what the kernels take: the variance parameters (and df)
     # plus, for the factor models, the m x nf matrix of factor vectors.  Composed by the mix-ins.
@@ -189,6 +190,11 @@ class Model(Withable):
         """REML objective (model cost + sum of score_row over all genes, fitnoise.py:63-68) and its
         gradient at the packed theta, evaluated on the GPU: (value, grad, n_used, n_bad)."""
         theta = as_vector(theta)
+        if not self._has_model_cost:
+            # no factor vectors, no model cost: theta goes to the kernels as it is (the split / join /
+            # cost plumbing below costs several numpy calls per evaluation, which shows at ~10 us per evaluation)
+            value, grad, _, used, bad = self._session.nll_grad(theta, None)
+            return value, grad, used, bad
         core, factors = self._split_theta(theta)
         value, grad_core, grad_factors, used, bad = self._session.nll_grad(core, factors)
         cost, cost_grad = self._cost_grad(theta)
@@ -444,6 +450,8 @@ class Model_factors_mixin(Model):
         the (control) design.  The kernels fit it as the diagonal model with the design augmented by
         the factor vectors and a unit ridge on them (csrc/fn_gene.cuh, eval_factors); the penalty
         sum_{i<j} (f_i . f_j)^2 and the chain rule through Q2 are host-side (m x nf numbers). """
+
+    _has_model_cost = True
 
     def __init__(self, n_factors, *etc):
         self.n_factors = n_factors
