@@ -1708,7 +1708,7 @@ static void bh_enqueue(fn_handle* h, int64_t n, const double* p_dev, double* q_d
         std::swap(idx0, idx1);
     }
     bh_chunkmin_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, chunk_min);
-    bh_carry_kernel<<<(nblocks + 127) / 128, 128, 0, h->stream>>>(nblocks, chunk_min, carry);
+    bh_carry_scan_kernel<<<1, 1024, 0, h->stream>>>(nblocks, chunk_min, carry);
     bh_finish_kernel<<<nblocks, BH_THREADS, 0, h->stream>>>(n, keys0, idx0, carry, q_dev);
     if (order_dev) *order_dev = idx0;          // genes by ascending p (stable, NaN last)
 }

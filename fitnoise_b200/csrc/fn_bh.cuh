@@ -355,15 +355,6 @@ __global__ void __launch_bounds__(BH_THREADS) bh_chunkmin_kernel(long long n, co
     if (threadIdx.x == 0) chunk_min[blockIdx.x] = red[0];
 }
 
-// carry[b] = min over chunks > b (inf for the last); thread b scans the later chunk minima
-__global__ void bh_carry_kernel(int nchunks, const double* chunk_min, double* carry) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nchunks) return;
-    double run = INFINITY;
-    for (int i = b + 1; i < nchunks; ++i) run = fmin(run, chunk_min[i]);
-    carry[b] = run;
-}
-
 // q_(r) = min(1, suffix-min), scattered back to gene order
 __global__ void __launch_bounds__(BH_THREADS) bh_finish_kernel(long long n, const uint64_t* keys, const uint32_t* idx,
                                                                const double* carry, double* q) {
