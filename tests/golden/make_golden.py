@@ -427,6 +427,40 @@ def transform_fixture():
         vcentered = vy - vy.mean(axis=0)[None, :]
         vresidual = ft.dot(vcentered, q_null)
         cost = ft.log((vresidual * vresidual).flatten().sum()) - ft.log((vcentered * vcentered).flatten().sum())
+        # The reference's objective as a function of pack (its own methods and numpy-level functions), its
+        # central-difference gradient (what Theano's autodiff of the same expression returns, to ~1e-9),
+        # and the reference's OWN driver loop (fittransform.py:140-156: up to 100 L-BFGS-B runs, stop when
+        # the improvement is <= 1e-6) fed with that value and gradient: the fitted parameters and
+        # objective the reference's Transform.fit arrives at, up to the noise of the numerical gradient.
+        def ref_cost(pk, cfg=cfg):
+            y_ = cfg._apply_transform(cfg._unpack_transform(m, pk), x)
+            c_ = y_ - y_.mean(axis=0)[None, :]
+            r_ = ft.dot(c_, q_null)
+            return float(ft.log((r_ * r_).flatten().sum()) - ft.log((c_ * c_).flatten().sum()))
+
+        def ref_grad(pk):
+            g_ = np.zeros(len(pk))
+            for i in range(len(pk)):
+                h = 1e-6 * max(1.0, abs(pk[i]))
+                up, dn = pk.copy(), pk.copy()
+                up[i] += h
+                dn[i] -= h
+                g_[i] = (ref_cost(up) - ref_cost(dn)) / (2 * h)
+            return g_
+
+        assert abs(ref_cost(pack) - float(cost)) <= 1e-14
+        out["ref_grad%d" % order] = ref_grad(pack)
+        import scipy.optimize
+        a, last = np.asarray(cfg._param_initial, dtype=float), None
+        for _ in range(100):
+            fit = scipy.optimize.minimize(lambda pk: (ref_cost(pk), ref_grad(pk)), a, method="L-BFGS-B", jac=True,
+                                          bounds=cfg._param_bounds)
+            a = fit.x
+            if last is not None and last - fit.fun <= 1e-6:
+                break
+            last = fit.fun
+        out["ref_fit_pack%d" % order] = fit.x.copy()
+        out["ref_fit_fun%d" % order] = float(fit.fun)
         out["pack%d" % order] = pack
         out["ref_y%d" % order] = vy
         out["ref_cost%d" % order] = float(cost)

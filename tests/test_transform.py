@@ -94,3 +94,25 @@ def test_transform_api_matches_oracle_fit():
     assert len(fitted.transform) == 2 and all(len(v) == 6 for v in fitted.transform)
     assert repr(fitted).startswith("Transform_polynomial\n")
     assert fitnoise.transform is fittransform.transform
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_gradient_and_fit_against_the_reference_expression(order):
+    """What can be pinned of Transform.fit without Theano (tests/golden/make_golden.py --transform): the
+    central-difference gradient of the reference's own objective expression (= what its autodiff returns,
+    to ~1e-9) and the result of the reference's own driver loop (fittransform.py:140-156) fed with that
+    value and gradient.  The oracle's analytic gradient must match the former; the package's fit must
+    reach the latter's objective for orders 1 and 2 (order 3 is ill-conditioned on this fixture: the
+    loop's 1e-6 improvement rule stops the three implementations at different points of a flat valley)."""
+    from conftest import load_golden
+    g = load_golden("transform_poly")
+    x, design, pack = g["x"], g["design"], g["pack%d" % order]
+    _, grad = oracle.transform_cost_grad(pack, x, design, order)
+    assert_close(grad, g["ref_grad%d" % order], 1e-5, atol=1e-8, what="gradient vs the reference expression")
+    ref_pack, ref_fun = g["ref_fit_pack%d" % order], float(g["ref_fit_fun%d" % order])
+    assert_close(oracle.transform_cost(ref_pack, x, design, order), ref_fun, 1e-12, what="objective at the reference's optimum")
+    fitted = fitnoise.Transform_polynomial(order)._with(_engine_factory=hostcheck.HostEvaluator).fit(x, design)
+    if order < 3:
+        assert abs(fitted.optimization_result.fun - ref_fun) <= 5e-4 * abs(ref_fun), (fitted.optimization_result.fun, ref_fun)
+    else:
+        assert np.isfinite(fitted.optimization_result.fun) and fitted.optimization_result.fun < -4.0
