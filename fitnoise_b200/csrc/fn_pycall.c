@@ -21,6 +21,7 @@ static PyObject* nll_grad(PyObject* self, PyObject* const* args, Py_ssize_t narg
     fn_nll_grad_t fn = (fn_nll_grad_t)PyLong_AsVoidPtr(args[0]);
     void* handle = PyLong_AsVoidPtr(args[1]);
     if (PyErr_Occurred()) return NULL;
+    if (!fn || !handle) { PyErr_SetString(PyExc_ValueError, "nll_grad: null function or handle address"); return NULL; }
     Py_buffer theta, grad;
     if (PyObject_GetBuffer(args[2], &theta, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) != 0) return NULL;
     if (PyObject_GetBuffer(args[3], &grad, PyBUF_C_CONTIGUOUS | PyBUF_WRITABLE | PyBUF_FORMAT) != 0) {

@@ -216,6 +216,8 @@ def test_cpython_fast_call_marshals_like_the_abi():
     assert seen == dict(handle=0xABCDEF, P=3, theta=[1.5, 2.5, 4.0]) and np.array_equal(grad, [15.0, 25.0, 40.0])
     assert fast(address, 1, np.array([2.0]), np.empty(1))[0] == -5                  # the library's error code comes through
     assert fast(address, 1, np.zeros(0), np.empty(0))[:2] == (0, 0.0)               # P = 0 (Model_independent)
+    with pytest.raises(ValueError):
+        fast(0, 1, theta, grad)
     for bad_theta, bad_grad in ((np.array([1, 2]), np.empty(2)), (np.ones(4)[::2], np.empty(2)),
                                 (np.ones(3), np.empty(2)), (np.ones(2), np.empty(2, dtype=np.float32))):
         with pytest.raises((TypeError, BufferError, ValueError)):
