@@ -222,3 +222,17 @@ def test_cpython_fast_call_marshals_like_the_abi():
                                 (np.ones(3), np.empty(2)), (np.ones(2), np.empty(2, dtype=np.float32))):
         with pytest.raises((TypeError, BufferError, ValueError)):
             fast(address, 1, bad_theta, bad_grad)
+
+
+def test_shard_threshold_setting(monkeypatch):
+    """FN_SHARD_MIN_MB: matrices below it are fitted whole by every rank (session.py); default 8 MB,
+    garbage falls back to the default, 0 shards everything."""
+    from fitnoise_b200 import session
+    monkeypatch.delenv("FN_SHARD_MIN_MB", raising=False)
+    assert session._shard_min_bytes() == 8 * 1048576
+    monkeypatch.setenv("FN_SHARD_MIN_MB", "0")
+    assert session._shard_min_bytes() == 0
+    monkeypatch.setenv("FN_SHARD_MIN_MB", "2.5")
+    assert session._shard_min_bytes() == 2.5 * 1048576
+    monkeypatch.setenv("FN_SHARD_MIN_MB", "many")
+    assert session._shard_min_bytes() == 8 * 1048576
