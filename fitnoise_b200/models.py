@@ -254,13 +254,17 @@ class Model(Withable):
             session.set_factors(factors)
         noise_p_values, averages = session.noise_stats(theta)         # :257-267
 
-        good_p = noise_p_values[np.isfinite(noise_p_values)]          # :270-274
-        if not len(good_p):
+        # :270-274 -- min(1, min(good p) * number of good p), without the boolean-indexed copy of the
+        # reference (3 ms of a 20 ms fit at a million genes)
+        finite = np.isfinite(noise_p_values)
+        n_good = int(np.count_nonzero(finite))
+        if not n_good:
             noise_combined_p_value = 0.0
         else:
-            noise_combined_p_value = min(1, np.minimum.reduce(good_p) * len(good_p))
+            # (p-values are NaN or in [0, 1]: fmin skips the NaN, and an infinity could never be the minimum)
+            noise_combined_p_value = min(1, float(np.fmin.reduce(noise_p_values)) * n_good)
 
-        n_controls = int(np.sum(controls))                            # :276-277
+        n_controls = int(np.count_nonzero(controls))                  # :276-277
         n_residuals = (n - n_controls) * (m - design.shape[1]) + n_controls * (m - control_design.shape[1])
         df = n_residuals - len(initial)
 
@@ -352,7 +356,7 @@ class Model(Withable):
 
         return self._with(contrasts=contrasted, contrast_dists=_LazyDists(len(mean), make),
                           p_values=p_values, q_values=q_values,
-                          _order=np.asarray(order, dtype=np.int64), _contrast_names=names)
+                          _order=order, _contrast_names=names)       # (uint32 from the device sort; widened on use)
 
     # ---- top table (legacy R test.fit, backyard/old_fitnoise.R:783-826) ---------------------
     def top_table(self, sort=True, genes=None):

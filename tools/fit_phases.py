@@ -17,6 +17,11 @@ config = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 s = synthetic(config)
 model = sys.argv[2] if len(sys.argv) > 2 else s["model"]
 kw = {k: s[k] for k in ("controls", "control_design") if k in s}
+if os.environ.get("FN_PIN"):                       # inputs in pinned host memory (one DMA instead of the staged copy)
+    import torch
+    pinned = torch.empty(s["y"].shape, dtype=torch.float64, pin_memory=True)
+    pinned.numpy()[:] = s["y"]
+    s["y"] = pinned.numpy()
 data = fitnoise.Dataset(s["y"], s["context"])
 spent = {}
 
